@@ -1,0 +1,154 @@
+/*
+ * rcz.h — C ABI of librcz.so: B200 (sm_100a) kernels for the hot inner loops of the Rust crate
+ * `compress` 0.2.1 (rusty-shell/rust-compress).
+ *
+ * The crate exposes no FFI; its drop-in boundary is the Rust API (`Decoder<R>: Read`,
+ * `Encoder<W>: Write`, and the per-block free functions).  Each entry point below replaces the
+ * per-block call that one of those types makes, batched over independent blocks/streams so that a
+ * host shim (rust/ shim in INTEGRATION.md, the C++ mirrors in rust-compress_b200/host/rcz_stream.hpp,
+ * or the Python mirrors in rust-compress_b200/ python modules) can parse framing on the CPU, collect block
+ * descriptors, and hand the batch to the GPU.  Paths cited are relative to the reference tree.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no global state; one rcz_ctx per host thread, bound to one device
+ *     and one CUDA stream.
+ *   - every call returns an rcz_status; per-block outcomes go to status[i] (same codes).
+ *   - mem_kind selects where the buffers live:
+ *       RCZ_MEM_HOST          data + descriptor arrays in host memory; the library stages H2D/D2H and
+ *                             returns when the results are in the caller's host buffers.
+ *       RCZ_MEM_DEVICE        data pointers are device pointers; descriptor/result arrays
+ *                             (offsets, lengths, status) are host arrays; returns when results are valid.
+ *       RCZ_MEM_DEVICE_ASYNC  data pointers AND result arrays (out_len, status, origin-out, in_used, detail)
+ *                             are device pointers; input descriptor arrays (offsets, lengths, origin-in)
+ *                             stay host arrays (the host sizes the grids from them).  The call only
+ *                             enqueues work on the context's stream (pipelines, benchmarks).
+ *   - device data buffers must come from cudaMalloc-class allocators (the kernels may read up to the
+ *     next 16-byte boundary past a block, which always stays inside such an allocation).
+ *   - block/stream sizes are limited to < 2 GiB each (in_len, out_cap < 2^31).
+ */
+#ifndef RCZ_H
+#define RCZ_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rcz_ctx rcz_ctx;
+
+typedef enum rcz_status {
+    RCZ_OK = 0,
+    RCZ_E_INVALID_INPUT = -1,  /* io::ErrorKind::InvalidInput (lz4.rs:365-377, flate.rs:53-66)          */
+    RCZ_E_UNEXPECTED_EOF = -2, /* "unexpected end of file" (lib.rs:53-62,109-125) / raw UnexpectedEof    */
+    RCZ_E_OVERLONG_RUN = -3,   /* rle.rs:151-154 "Overly long run"                                       */
+    RCZ_E_MALFORMED = -4,      /* input on which the reference panics (index OOB / assert!)              */
+    RCZ_E_OUTPUT_FULL = -5,    /* caller-provided out_cap too small                                      */
+    RCZ_E_ARG = -6,            /* bad argument (null pointer, size >= 2 GiB, unknown mem_kind)           */
+    RCZ_E_CUDA = -7,           /* CUDA runtime failure; see rcz_last_error()                             */
+    RCZ_E_NO_DEVICE = -8,      /* no CUDA device: there is NO CPU fallback                               */
+    RCZ_E_UNSUPPORTED = -9
+} rcz_status;
+
+/* flate detail codes (flate.rs:42-51), delivered in detail[i] when status[i] == RCZ_E_INVALID_INPUT */
+enum {
+    RCZ_FL_NONE = 0,
+    RCZ_FL_HUFFMAN_TREE_TOO_LARGE = 1,
+    RCZ_FL_INVALID_BLOCK_CODE = 2,
+    RCZ_FL_INVALID_HUFFMAN_HEADER_SYMBOL = 3,
+    RCZ_FL_INVALID_HUFFMAN_TREE = 4,
+    RCZ_FL_INVALID_HUFFMAN_TREE_HEADER = 5,
+    RCZ_FL_INVALID_HUFFMAN_CODE = 6,
+    RCZ_FL_INVALID_STATIC_SIZE = 7,
+    RCZ_FL_NOT_ENOUGH_BITS = 8
+};
+
+typedef enum rcz_mem_kind { RCZ_MEM_HOST = 0, RCZ_MEM_DEVICE = 1, RCZ_MEM_DEVICE_ASYNC = 2 } rcz_mem_kind;
+
+/* ---------------- context ---------------- */
+int rcz_ctx_create(int device, unsigned flags, rcz_ctx** out);
+int rcz_ctx_destroy(rcz_ctx* ctx);
+/* use an externally owned CUDA stream (cudaStream_t as void*), e.g. torch.cuda.current_stream().cuda_stream */
+int rcz_ctx_set_stream(rcz_ctx* ctx, void* cuda_stream);
+int rcz_ctx_sync(rcz_ctx* ctx);
+const char* rcz_strerror(int status);
+const char* rcz_last_error(rcz_ctx* ctx);
+/* number of librcz kernels launched through this context so far (bench.py "gpu_launches") */
+uint64_t rcz_kernel_launches(rcz_ctx* ctx);
+/* device time of the kernels of the most recent batch call, from CUDA events on the context's stream
+ * (valid after rcz_ctx_sync or a synchronous call) */
+float rcz_last_kernel_ms(rcz_ctx* ctx);
+/* pinned host memory for staging (cudaMallocHost) */
+int rcz_host_alloc(void** p, size_t bytes);
+int rcz_host_free(void* p);
+const char* rcz_build_info(void);
+
+/* ---------------- lz4.rs ----------------
+ * rcz_lz4_decode_blocks replaces `BlockDecoder::decode` / `lz4::decode_block` (lz4.rs:64-162, 602-611),
+ * called once per compressed frame block at lz4.rs:447-455.  Block i is in_base[in_off[i] .. +in_len[i]];
+ * its bytes are written to out_base[out_off[i] .. +out_len[i]], out_len[i] <= out_cap[i]. */
+int rcz_lz4_decode_blocks(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                          void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
+                          uint64_t* out_len, int32_t* status, size_t nblocks, int mem_kind);
+/* `lz4::compression_bound` (lz4.rs:175-181); -1 == None */
+int64_t rcz_lz4_compression_bound(uint32_t size);
+
+/* ---------------- bwt/mod.rs ----------------
+ * rcz_bwt_decode_blocks replaces `compute_inversion_table` + `InverseIterator` (bwt/mod.rs:223-282) as
+ * driven by the stream decoder at bwt/mod.rs:388-393: block i = L column in_base[in_off[i] .. +n[i]] with
+ * origin[i]; output written to out_base[out_off[i] ..], out_len[i] bytes (== n[i] for a well-formed block).
+ * rcz_bwt_encode_blocks replaces `compute_suffixes` + `TransformIterator` (bwt/mod.rs:136-204) as called
+ * at bwt/mod.rs:470-475: writes the L column (n[i] bytes) and origin[i]. */
+int rcz_bwt_decode_blocks(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* n,
+                          const uint32_t* origin, void* out_base, const uint64_t* out_off,
+                          uint64_t* out_len, int32_t* status, size_t nblocks, int mem_kind);
+int rcz_bwt_encode_blocks(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* n,
+                          void* out_base, const uint64_t* out_off, uint32_t* origin, int32_t* status,
+                          size_t nblocks, int mem_kind);
+
+/* ---------------- flate.rs ----------------
+ * rcz_flate_decode_streams replaces `Decoder::block` + `codes` + `HuffmanTree::decode`
+ * (flate.rs:129-146, 195-206, 262-450) driven to BFINAL for every independent raw-DEFLATE stream.
+ * in_used[i] (optional) = bytes of the stream consumed; detail[i] (optional) = RCZ_FL_* code. */
+int rcz_flate_decode_streams(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                             void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
+                             uint64_t* out_len, uint64_t* in_used, int32_t* status, int32_t* detail,
+                             size_t nstreams, int mem_kind);
+
+/* ---------------- entropy/ari ----------------
+ * rcz_ari_encode_streams replaces `ByteEncoder::write` + `finish` (table.rs:203-219 -> ari/mod.rs:117-150,
+ * 230-237); rcz_ari_decode_streams replaces `ByteDecoder::read` to the terminator (table.rs:255-272).
+ * in_used[i] = bytes consumed including the ones only `finish()` pulls (ari/mod.rs:289-292). */
+int rcz_ari_encode_streams(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                           void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
+                           uint64_t* out_len, int32_t* status, size_t nstreams, int mem_kind);
+int rcz_ari_decode_streams(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                           void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
+                           uint64_t* out_len, uint64_t* in_used, int32_t* status, size_t nstreams, int mem_kind);
+
+/* ---------------- bwt/dc.rs ----------------
+ * rcz_dc_encode_blocks replaces `dc::encode` + `EncodeIterator` (dc.rs:62-149): per block, init[256]
+ * (u32, first position of each symbol or n) followed by the emitted distances (u32) are written to
+ * out_base (as uint32) at element offset out_off[i]; out_len[i] = 256 + number of distances.
+ * rcz_dc_decode_blocks replaces `dc::decode` (dc.rs:162-233) fed by `decode_simple`'s closure. */
+int rcz_dc_encode_blocks(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* n,
+                         uint32_t* out_base, const uint64_t* out_off, const uint64_t* out_cap,
+                         uint64_t* out_len, int32_t* status, size_t nblocks, int mem_kind);
+int rcz_dc_decode_blocks(rcz_ctx* ctx, const uint32_t* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                         void* out_base, const uint64_t* out_off, const uint64_t* n, int32_t* status,
+                         size_t nblocks, int mem_kind);
+
+/* ---------------- rle.rs ----------------
+ * rcz_rle_decode_streams replaces `Decoder::read_run` (rle.rs:212-259); rcz_rle_encode_streams replaces
+ * `Encoder::write` + `finish` (rle.rs:62-122) for one whole-buffer write. */
+int rcz_rle_decode_streams(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                           void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
+                           uint64_t* out_len, int32_t* status, size_t nstreams, int mem_kind);
+int rcz_rle_encode_streams(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                           void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
+                           uint64_t* out_len, int32_t* status, size_t nstreams, int mem_kind);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCZ_H */

@@ -1,0 +1,442 @@
+// bwt_decode.cu — K4 (link-table build) + K5 (inverse-BWT walk) for batches of independent BWT blocks.
+//
+// Replaces /root/reference/src/bwt/mod.rs:223-239 `compute_inversion_table` and :243-282 `InverseIterator`
+// (one dependent `cur = table[cur]-1` hop per output byte, bwt/mod.rs:270) as driven by the stream decoder at
+// bwt/mod.rs:388-393.  Same bytes out; the serial chain is cut into thousands of sub-chains per block:
+//
+//   A  ibwt_hist     per 16 Ki-symbol tile: 256-bin histogram of L (Radix::gather, bwt/mod.rs:95-99)
+//   B  ibwt_scan     per block: exclusive scan over symbols and tiles (Radix::accumulate, :102-109)
+//   C  ibwt_scatter  per tile: stable 256-way partition (match_any ranking inside each warp, smem-staged so
+//                    that every (tile, symbol) run leaves the SM as one contiguous store) ->
+//                    P[slot] = (position-in-L << 8) | symbol, with the `origin`-first rule of :230-236
+//                    (origin's entry is the END marker; the reference stores index+1 and 0)
+//   D  ibwt_walk     sampled list ranking, pass 1: every 2^k-th row starts a sub-chain that hops
+//                    cur = P[cur]>>8 until it meets the next sampled row (or END), packing the emitted bytes
+//                    16 at a time into a chain-local scratch slot; over-long chains are split on the fly
+//                    (continuation slots come from an atomic ticket) so no chain is walked twice
+//   E  ibwt_rank     per block: Wyllie pointer jumping over the <= 24 K chain descriptors in shared memory
+//                    (dist and next packed in one 64-bit word) -> output offset of every chain
+//   F  ibwt_compact  chain-local bytes -> final positions (coalesced copies)
+//
+// The walk starts at `origin`, emits F[cur] (== L[table[cur]-1], bwt/mod.rs:270-279) per hop, and ends at the END
+// entry — exactly the reference's iterator, so a block that is not a valid BWT yields the same (shorter) output.
+#include "rcz_internal.h"
+#include <algorithm>
+
+namespace ibwt {
+
+constexpr int TB = 16384;                 // symbols per tile (kernels A, C)
+constexpr int NT_TILE = 512;
+constexpr unsigned END24 = 0xFFFFFFu;     // "next" field of the origin entry
+constexpr unsigned SUCC_END = 0xFFFFFFFFu;
+constexpr unsigned OFF_INVALID = 0xFFFFFFFFu;
+constexpr unsigned MAX_N = 0xFFFFFEu;     // positions must fit the 24-bit field
+constexpr int RANK_NT = 1024;
+constexpr unsigned RANK_MAX_CHAINS = 24832;   // 8 B each -> 194 KiB of shared memory
+
+struct Blk {
+    unsigned long long in_off, out_off, scratch_off;   // bytes
+    unsigned n, origin;
+    unsigned p_off;        // element offset of this block's P table
+    unsigned tile0, ntiles;
+    unsigned stride_log2;  // sampled rows are multiples of 1 << stride_log2
+    unsigned K;            // number of sampled rows; chain K is the origin chain
+    unsigned cap;          // bytes per chain slot (2 * stride)
+    unsigned chain0;       // global id of this block's first chain descriptor
+    unsigned max_chains;
+    unsigned work0;        // first index of this block's initial work items (K + 1 of them)
+    unsigned skip;         // block rejected on the host (status already set)
+};
+
+// ------------------------------------------------------------------------------------------ A: histogram
+__global__ void __launch_bounds__(NT_TILE)
+ibwt_hist_kernel(const uint8_t* __restrict__ in_base, const Blk* __restrict__ blks, const unsigned* __restrict__ tile2blk,
+                 unsigned* __restrict__ tile_hist) {
+    __shared__ unsigned h[NT_TILE / 32][256];
+    const unsigned tile = blockIdx.x, tid = threadIdx.x, w = tid >> 5;
+    const Blk bk = blks[tile2blk[tile]];
+    const unsigned t = tile - bk.tile0;
+    const uint8_t* L = in_base + bk.in_off;
+    const unsigned lo = t * TB, hi = min(bk.n, lo + TB);
+    for (unsigned i = tid; i < (NT_TILE / 32) * 256; i += NT_TILE) (&h[0][0])[i] = 0;
+    __syncthreads();
+    for (unsigned i = lo + tid; i < hi; i += NT_TILE) atomicAdd(&h[w][L[i]], 1u);
+    __syncthreads();
+    if (tid < 256) {
+        unsigned s = 0;
+#pragma unroll
+        for (int k = 0; k < NT_TILE / 32; ++k) s += h[k][tid];
+        tile_hist[(size_t)tile * 256 + tid] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ B: scan
+// tile_hist[tile][c] becomes the number of c's in earlier tiles of the block; cbase[blk][c] = #symbols < c.
+__global__ void __launch_bounds__(256)
+ibwt_scan_kernel(const Blk* __restrict__ blks, unsigned* __restrict__ tile_hist, unsigned* __restrict__ cbase) {
+    __shared__ unsigned scratch[40];
+    const unsigned b = blockIdx.x, c = threadIdx.x;
+    const Blk bk = blks[b];
+    unsigned run = 0;
+    if (!bk.skip)
+        for (unsigned t = 0; t < bk.ntiles; ++t) {
+            const size_t idx = (size_t)(bk.tile0 + t) * 256 + c;
+            const unsigned hcnt = tile_hist[idx];
+            tile_hist[idx] = run;
+            run += hcnt;
+        }
+    unsigned total;
+    const unsigned ex = block_excl_scan_add<256>(run, scratch, &total);
+    cbase[(size_t)b * 256 + c] = ex;
+}
+
+// ------------------------------------------------------------------------------------------ C: stable partition
+struct ScatterSmem {
+    unsigned sorted[TB];
+    unsigned wcnt[NT_TILE / 32][256];
+    unsigned symbase[256];
+    unsigned gbase[256];
+    unsigned scratch[40];
+};
+
+__global__ void __launch_bounds__(NT_TILE, 2)
+ibwt_scatter_kernel(const uint8_t* __restrict__ in_base, const Blk* __restrict__ blks, const unsigned* __restrict__ tile2blk,
+                    const unsigned* __restrict__ tile_hist, const unsigned* __restrict__ cbase, unsigned* __restrict__ P_base) {
+    RCZ_DYN_SMEM(raw);
+    ScatterSmem& sm = *reinterpret_cast<ScatterSmem*>(raw);
+    const unsigned tile = blockIdx.x, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const unsigned bi = tile2blk[tile];
+    const Blk bk = blks[bi];
+    const unsigned t = tile - bk.tile0;
+    const uint8_t* L = in_base + bk.in_off;
+    unsigned* P = P_base + bk.p_off;
+    const unsigned lo = t * TB, hi = min(bk.n, lo + TB), tlen = hi - lo;
+    constexpr unsigned WSPAN = TB / (NT_TILE / 32);   // 1024 consecutive symbols per warp
+
+    for (unsigned i = tid; i < (NT_TILE / 32) * 256; i += NT_TILE) (&sm.wcnt[0][0])[i] = 0;
+    __syncthreads();
+    // pass A: per-warp symbol counts
+    for (unsigned g = 0; g < WSPAN / 32; ++g) {
+        const unsigned i = lo + w * WSPAN + g * 32 + lane;
+        if (i < hi) atomicAdd(&sm.wcnt[w][L[i]], 1u);
+    }
+    __syncthreads();
+    // pass B: exclusive scan over warps (per symbol), then over symbols
+    unsigned tot = 0;
+    if (tid < 256) {
+#pragma unroll
+        for (int k = 0; k < NT_TILE / 32; ++k) { const unsigned x = sm.wcnt[k][tid]; sm.wcnt[k][tid] = tot; tot += x; }
+    }
+    unsigned dummy;
+    const unsigned sb = block_excl_scan_add<NT_TILE>(tot, sm.scratch, &dummy);
+    if (tid < 256) {
+        sm.symbase[tid] = sb;
+        // destination of local sorted index j with symbol c:  gbase[c] + j
+        sm.gbase[tid] = cbase[(size_t)bi * 256 + tid] + tile_hist[(size_t)tile * 256 + tid] - sb;
+    }
+    __syncthreads();
+    // pass C: stable ranking, 32 symbols at a time per warp (match_any groups equal symbols)
+    for (unsigned g = 0; g < WSPAN / 32; ++g) {
+        const unsigned i = lo + w * WSPAN + g * 32 + lane;
+        const bool valid = i < hi;
+        const unsigned s = valid ? (unsigned)L[i] : 256u + lane;     // invalid lanes get unique keys
+        const unsigned m = __match_any_sync(RCZ_FULL, s);
+        const unsigned r = __popc(m & ((1u << lane) - 1u));
+        unsigned base = 0;
+        if (valid) base = sm.wcnt[w][s];
+        __syncwarp();
+        if (valid && r == 0) sm.wcnt[w][s] = base + __popc(m);
+        __syncwarp();
+        if (valid) sm.sorted[sm.symbase[s] + base + r] = (i << 8) | s;
+    }
+    __syncthreads();
+    // pass D: write out; runs of equal symbols are contiguous in P. origin-first rule of bwt/mod.rs:230-236.
+    const unsigned origin = bk.origin;
+    const unsigned c0 = L[origin];
+    const unsigned slot0 = cbase[(size_t)bi * 256 + c0];
+    for (unsigned j = tid; j < tlen; j += NT_TILE) {
+        const unsigned v = sm.sorted[j];
+        const unsigned s = v & 255u, pos = v >> 8;
+        unsigned slot = sm.gbase[s] + j;
+        unsigned val = v;
+        if (s == c0) {
+            if (pos == origin) { slot = slot0; val = (END24 << 8) | s; }
+            else if (pos < origin) slot += 1;
+        }
+        P[slot] = val;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ D: walk
+struct Desc { unsigned len, succ; };
+
+__global__ void __launch_bounds__(256)
+ibwt_walk_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned total_work, const unsigned* __restrict__ P_base,
+                 uint8_t* __restrict__ scratch_base, Desc* __restrict__ desc_base, unsigned* __restrict__ chain_ctr,
+                 unsigned* __restrict__ queue) {
+    const unsigned lane = threadIdx.x & 31;
+    bool active = false, done = false;
+    // per-chain state
+    const unsigned* P = nullptr; uint8_t* slotp = nullptr; Desc* desc = nullptr; unsigned* ctr = nullptr;
+    unsigned cur = 0, count = 0, chain = 0, mask = 0, slog = 0, cap = 0, hops = 0, nmax = 0, maxch = 0;
+    unsigned long long scratch_off = 0;
+    unsigned b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+
+    for (;;) {
+        // ---- refill idle lanes with new chains (warp-aggregated ticket)
+        const unsigned need = __ballot_sync(RCZ_FULL, !active && !done);
+        if (need) {
+            unsigned base = 0;
+            const unsigned leader = (unsigned)__ffs((int)need) - 1;
+            if (lane == leader) base = atomicAdd(queue, (unsigned)__popc(need));
+            base = __shfl_sync(RCZ_FULL, base, (int)leader);
+            if (!active && !done) {
+                const unsigned wi = base + __popc(need & ((1u << lane) - 1u));
+                if (wi >= total_work) done = true;
+                else {
+                    unsigned lo = 0, hi = nblocks;            // last block with work0 <= wi
+                    while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (blks[mid].work0 <= wi) lo = mid; else hi = mid; }
+                    const Blk bk = blks[lo];
+                    chain = wi - bk.work0;
+                    P = P_base + bk.p_off;
+                    desc = desc_base + bk.chain0;
+                    ctr = chain_ctr + lo;
+                    scratch_off = bk.scratch_off;
+                    slog = bk.stride_log2; mask = (1u << slog) - 1u; cap = bk.cap; nmax = bk.n; maxch = bk.max_chains;
+                    cur = chain < bk.K ? (chain << slog) : bk.origin;
+                    slotp = scratch_base + scratch_off + (size_t)chain * cap;
+                    count = 0; hops = 0;
+                    active = true;
+                    if (chain < bk.K && cur == bk.origin) {   // no row links to `origin`: this sampled chain is unreachable,
+                        Desc d; d.len = 0; d.succ = SUCC_END;  // and the origin chain (id K) walks the same rows
+                        desc[chain] = d;
+                        active = false;
+                    }
+                }
+            }
+        }
+        if (__all_sync(RCZ_FULL, done)) break;
+        // ---- a burst of hops between refill checks
+#pragma unroll 1
+        for (int it = 0; it < 16; ++it) {
+            if (active) {
+                const unsigned e = __ldg(P + cur);
+                const unsigned byte = e & 255u, nxt = e >> 8;
+                // append to the 16-byte register buffer
+                const unsigned k = count & 15u;
+                const unsigned sh = (k & 3u) * 8u;
+                if (k < 4) b0 = (k == 0 ? 0u : b0) | (byte << sh);
+                else if (k < 8) b1 = (k == 4 ? 0u : b1) | (byte << sh);
+                else if (k < 12) b2 = (k == 8 ? 0u : b2) | (byte << sh);
+                else b3 = (k == 12 ? 0u : b3) | (byte << sh);
+                ++count; ++hops;
+                if ((count & 15u) == 0) *reinterpret_cast<uint4*>(slotp + count - 16) = make_uint4(b0, b1, b2, b3);
+                const bool at_end = (nxt == END24) || hops > nmax;
+                const bool at_sample = !at_end && (nxt & mask) == 0;
+                if (at_end || at_sample) {
+                    if (count & 15u) {
+                        if ((count & 15u) <= 4) { b1 = 0; b2 = 0; b3 = 0; } else if ((count & 15u) <= 8) { b2 = 0; b3 = 0; } else if ((count & 15u) <= 12) b3 = 0;
+                        *reinterpret_cast<uint4*>(slotp + (count & ~15u)) = make_uint4(b0, b1, b2, b3);
+                    }
+                    Desc d; d.len = count; d.succ = at_end ? SUCC_END : (nxt >> slog);
+                    desc[chain] = d;
+                    active = false;
+                } else {
+                    cur = nxt;
+                    if (count == cap) {                       // slot full: continue in a fresh chain slot
+                        const unsigned nc = atomicAdd(ctr, 1u);
+                        Desc d; d.len = count; d.succ = nc < maxch ? nc : SUCC_END;
+                        desc[chain] = d;
+                        if (nc >= maxch) active = false;      // cannot happen (see max_chains); never write out of bounds
+                        chain = nc;
+                        slotp = scratch_base + scratch_off + (size_t)chain * cap;
+                        count = 0;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ E: rank chains
+__global__ void __launch_bounds__(RANK_NT, 1)
+ibwt_rank_kernel(const Blk* __restrict__ blks, const Desc* __restrict__ desc_base, const unsigned* __restrict__ chain_ctr,
+                 unsigned* __restrict__ chain_off, uint64_t* __restrict__ out_len, int32_t* __restrict__ status) {
+    RCZ_DYN_SMEM(raw);
+    unsigned long long* node = reinterpret_cast<unsigned long long*>(raw);   // (dist << 32) | next
+    volatile unsigned long long* vnode = node;
+    const unsigned b = blockIdx.x, tid = threadIdx.x;
+    const Blk bk = blks[b];
+    if (bk.skip) return;
+    const Desc* desc = desc_base + bk.chain0;
+    unsigned nch = chain_ctr[b];
+    if (nch > bk.max_chains) nch = bk.max_chains;
+    const unsigned SENT = nch;                                // absorbing node for END
+    for (unsigned i = tid; i < nch; i += RANK_NT) {
+        const Desc d = desc[i];
+        unsigned s = d.succ == SUCC_END ? SENT : d.succ;
+        if (s > nch) s = i;                                   // defensive: dangling link becomes a self-loop (never reaches END)
+        node[i] = ((unsigned long long)d.len << 32) | s;
+    }
+    if (tid == 0) node[SENT] = SENT;
+    __syncthreads();
+    unsigned rounds = 2;
+    for (unsigned v = nch; v; v >>= 1) ++rounds;
+    for (unsigned r = 0; r < rounds; ++r) {
+        int pend = 0;
+        for (unsigned i = tid; i < nch; i += RANK_NT) {
+            const unsigned long long a = vnode[i];
+            const unsigned s = (unsigned)a;
+            if (s != SENT) {
+                const unsigned long long q = vnode[s];
+                vnode[i] = (((a >> 32) + (q >> 32)) << 32) | (unsigned)q;
+                pend = 1;
+            }
+        }
+        if (!__syncthreads_or(pend)) break;
+    }
+    const unsigned long long org = node[bk.K];
+    const unsigned total = (unsigned)(org >> 32);             // the origin chain always reaches END
+    unsigned* coff = chain_off + bk.chain0;
+    for (unsigned i = tid; i < nch; i += RANK_NT) {
+        const unsigned long long a = node[i];
+        coff[i] = ((unsigned)a == SENT) ? total - (unsigned)(a >> 32) : OFF_INVALID;
+    }
+    if (tid == 0) { out_len[b] = total; status[b] = 0; }
+}
+
+// ------------------------------------------------------------------------------------------ F: compact
+__global__ void __launch_bounds__(256)
+ibwt_compact_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned total_chains, const uint8_t* __restrict__ scratch_base,
+                    const Desc* __restrict__ desc_base, const unsigned* __restrict__ chain_ctr, const unsigned* __restrict__ chain_off,
+                    uint8_t* __restrict__ out_base) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned wpb = blockDim.x >> 5;
+    for (unsigned g = blockIdx.x * wpb + (threadIdx.x >> 5); g < total_chains; g += gridDim.x * wpb) {
+        unsigned lo = 0, hi = nblocks;
+        while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (blks[mid].chain0 <= g) lo = mid; else hi = mid; }
+        const Blk bk = blks[lo];
+        const unsigned chain = g - bk.chain0;
+        if (bk.skip || chain >= chain_ctr[lo]) continue;
+        const unsigned off = chain_off[g];
+        if (off == OFF_INVALID) continue;
+        const unsigned len = desc_base[g].len;
+        const uint8_t* src = scratch_base + bk.scratch_off + (size_t)chain * bk.cap;
+        uint8_t* dst = out_base + bk.out_off + off;
+        for (unsigned i = lane; i < len; i += 32) dst[i] = src[i];
+    }
+}
+
+__global__ void ibwt_init_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned* __restrict__ chain_ctr, unsigned* __restrict__ queue,
+                                 uint64_t* __restrict__ out_len, int32_t* __restrict__ status, const int32_t* __restrict__ host_status) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *queue = 0;
+    if (i < nblocks) {
+        chain_ctr[i] = blks[i].K + 1;
+        if (blks[i].skip) { out_len[i] = 0; status[i] = host_status[i]; }
+    }
+}
+
+}  // namespace ibwt
+
+extern "C" int rcz_bwt_decode_blocks(rcz_ctx* c, const void* in_base, const uint64_t* in_off, const uint64_t* n_arr,
+                                     const uint32_t* origin, void* out_base, const uint64_t* out_off,
+                                     uint64_t* out_len, int32_t* status, size_t nblocks, int mem_kind) {
+    using namespace ibwt;
+    if (!c || rcz_bad_kind(mem_kind)) return RCZ_E_ARG;
+    if (nblocks == 0) return RCZ_OK;
+    if (!in_base || !in_off || !n_arr || !origin || !out_base || !out_off || !out_len || !status) return RCZ_E_ARG;
+    if (nblocks > 0x3fffffu) return RCZ_E_ARG;
+    rt_set_device(c->device);
+
+    // ---- host-side geometry
+    std::vector<Blk> blks(nblocks);
+    std::vector<int32_t> hstatus(nblocks, 0);
+    std::vector<unsigned> tile2blk;
+    unsigned long long p_elems = 0, scratch_bytes = 0;
+    unsigned long long chains = 0, work = 0;
+    for (size_t i = 0; i < nblocks; ++i) {
+        Blk& b = blks[i];
+        memset(&b, 0, sizeof b);
+        b.in_off = in_off[i]; b.out_off = out_off[i];
+        const unsigned long long n = n_arr[i];
+        b.tile0 = (unsigned)tile2blk.size();
+        b.chain0 = (unsigned)chains; b.work0 = (unsigned)work;
+        b.p_off = (unsigned)p_elems; b.scratch_off = scratch_bytes;
+        if (n == 0 || origin[i] >= n) { b.skip = 1; hstatus[i] = RCZ_E_MALFORMED; continue; }   // bwt/mod.rs:230 index panic
+        if (n > MAX_N) { b.skip = 1; hstatus[i] = RCZ_E_UNSUPPORTED; continue; }
+        b.n = (unsigned)n; b.origin = origin[i];
+        unsigned slog = 8;
+        while ((n >> slog) > 16384) ++slog;                   // keep <= 16 Ki sampled rows per block
+        b.stride_log2 = slog;
+        b.K = (unsigned)((n + (1ull << slog) - 1) >> slog);
+        b.cap = 2u << slog;
+        b.max_chains = b.K + 1 + (unsigned)(n / b.cap) + 1;   // every row is walked at most once => <= n/cap continuations
+        if (b.max_chains + 1 > RANK_MAX_CHAINS) { b.skip = 1; hstatus[i] = RCZ_E_UNSUPPORTED; continue; }
+        b.ntiles = (unsigned)((n + TB - 1) / TB);
+        for (unsigned t = 0; t < b.ntiles; ++t) tile2blk.push_back((unsigned)i);
+        p_elems += (n + 63) & ~63ull;
+        scratch_bytes += (unsigned long long)b.max_chains * b.cap;
+        chains += b.max_chains;
+        work += b.K + 1;
+        if (p_elems > 0xffffffffull || chains > 0xffffffffull) return RCZ_E_ARG;   // split the batch
+    }
+    const unsigned ntiles = (unsigned)tile2blk.size();
+
+    DescStager ds(c, mem_kind, nblocks);
+    const size_t i_blk = ds.add_in(blks.data(), nblocks * sizeof(Blk));
+    const size_t i_t2b = ds.add_in(tile2blk.data(), (size_t)ntiles * 4);
+    const size_t i_hst = ds.add_in(hstatus.data(), nblocks * 4);
+    const size_t o_len = ds.add_out(out_len, nblocks * 8);
+    const size_t o_st = ds.add_out(status, nblocks * 4);
+    int st = ds.upload(); if (st) return st;
+
+    const uint8_t* din = (const uint8_t*)in_base; uint8_t* dout = (uint8_t*)out_base;
+    if (mem_kind == RCZ_MEM_HOST) {
+        st = stage_span_in(c, WS_IN, in_base, in_off, n_arr, nblocks, 1, &din); if (st) return st;
+        st = stage_span_out(c, WS_OUT, out_off, n_arr, nblocks, 1, &dout); if (st) return st;
+    }
+    void *wP, *wS, *wM;
+    st = ctx_ws(c, WS_A, (size_t)p_elems * 4 + 256, &wP); if (st) return st;
+    st = ctx_ws(c, WS_B, (size_t)scratch_bytes + 256, &wS); if (st) return st;
+    // misc: tile_hist | cbase | desc | chain_off | chain_ctr | queue
+    const size_t sz_hist = (size_t)ntiles * 256 * 4, sz_cb = nblocks * 256 * 4, sz_desc = (size_t)chains * 8, sz_coff = (size_t)chains * 4,
+                 sz_ctr = nblocks * 4;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    st = ctx_ws(c, WS_C, al(sz_hist) + al(sz_cb) + al(sz_desc) + al(sz_coff) + al(sz_ctr) + 512, &wM); if (st) return st;
+    uint8_t* m = (uint8_t*)wM;
+    unsigned* tile_hist = (unsigned*)m; m += al(sz_hist);
+    unsigned* cbase = (unsigned*)m; m += al(sz_cb);
+    Desc* desc = (Desc*)m; m += al(sz_desc);
+    unsigned* chain_off = (unsigned*)m; m += al(sz_coff);
+    unsigned* chain_ctr = (unsigned*)m; m += al(sz_ctr);
+    unsigned* queue = (unsigned*)m;
+
+    const Blk* dblk = ds.in_ptr<Blk>(i_blk);
+    const unsigned* dt2b = ds.in_ptr<unsigned>(i_t2b);
+    uint64_t* d_len = ds.out_ptr<uint64_t>(o_len);
+    int32_t* d_st = ds.out_ptr<int32_t>(o_st);
+
+    st = ctx_timer_begin(c); if (st) return st;
+    RCZ_KLAUNCH(c, ibwt_init_kernel, (unsigned)((nblocks + 255) / 256), 256, 0, dblk, (unsigned)nblocks, chain_ctr, queue, d_len, d_st,
+                ds.in_ptr<int32_t>(i_hst));
+    if (ntiles) {
+        RCZ_KLAUNCH(c, ibwt_hist_kernel, ntiles, NT_TILE, 0, din, dblk, dt2b, tile_hist);
+        RCZ_KLAUNCH(c, ibwt_scan_kernel, (unsigned)nblocks, 256, 0, dblk, tile_hist, cbase);
+        RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(ibwt_scatter_kernel, sizeof(ScatterSmem)));
+        RCZ_KLAUNCH(c, ibwt_scatter_kernel, ntiles, NT_TILE, sizeof(ScatterSmem), din, dblk, dt2b, tile_hist, cbase, (unsigned*)wP);
+        const unsigned walk_grid = (unsigned)std::min<unsigned long long>((work + 255) / 256, (unsigned long long)c->sm_count * 8);
+        RCZ_KLAUNCH(c, ibwt_walk_kernel, walk_grid, 256, 0, dblk, (unsigned)nblocks, (unsigned)work, (const unsigned*)wP, (uint8_t*)wS, desc,
+                    chain_ctr, queue);
+        const size_t rank_smem = (size_t)RANK_MAX_CHAINS * 8;
+        RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(ibwt_rank_kernel, rank_smem));
+        RCZ_KLAUNCH(c, ibwt_rank_kernel, (unsigned)nblocks, RANK_NT, rank_smem, dblk, desc, chain_ctr, chain_off, d_len, d_st);
+        const unsigned cgrid = (unsigned)std::min<unsigned long long>((chains + 7) / 8, (unsigned long long)c->sm_count * 16);
+        RCZ_KLAUNCH(c, ibwt_compact_kernel, cgrid, 256, 0, dblk, (unsigned)nblocks, (unsigned)chains, (const uint8_t*)wS, desc, chain_ctr,
+                    chain_off, dout);
+    }
+    st = ctx_timer_end(c); if (st) return st;
+    st = ds.download(); if (st) return st;
+    if (mem_kind == RCZ_MEM_HOST) { st = unstage_span_out(c, out_base, dout, out_off, out_len, nblocks, 1); if (st) return st; }
+    return RCZ_OK;
+}

@@ -1,0 +1,427 @@
+// lz4_decode.cu — K1: LZ4 block decode, one CTA per block with intra-block parallelism.
+//
+// Replaces the serial loop `BlockDecoder::decode` (/root/reference/src/lz4.rs:64-162: token, literal run,
+// u16 offset, match with the offset<4 DECR dance, byte-forward copy) — same bytes out, different shape:
+//
+//   per batch (one 8 KiB window of the compressed block, staged in shared memory by a TMA bulk copy):
+//     P1  every window position speculatively parses "the token that would start here" -> nxt1[]
+//     P2  pointer doubling (5 rounds) gives nxt32[]; one thread hops 32 tokens at a time, 32 chains are
+//         then filled in parallel -> the true token list (sequence boundaries) of the window
+//     P3  per-token field parse + block-wide warp-shuffle prefix scan of (literals+match) lengths
+//         -> output offset of every sequence (literal/match boundary resolution)
+//   per 16 KiB output tile:
+//     P4  sequence heads are scattered into the tile, a per-warp max-scan labels every output byte with
+//         its sequence; every byte becomes a literal value, a value gathered from already-final output,
+//         or a 15-bit pointer to an earlier byte of the same tile
+//     P5  in-tile pointers are resolved by pointer doubling in shared memory (<= log2(tile) rounds,
+//         usually 1-2) — this is what makes overlapping / chained matches order-independent
+//     P6  the tile is written to HBM with coalesced stores
+//
+// Offsets < match length (incl. 1..3, the reference's DECR path lz4.rs:100-102) are folded analytically:
+// byte k of a match with offset `off` equals byte (k mod off) of the `off` bytes before the match.
+// Malformed input (truncated fields, offset 0, offset before block start — the cases on which the
+// reference panics) yields RCZ_E_MALFORMED for that block.
+#include "rcz_internal.h"
+
+namespace lz4k {
+
+constexpr int NT = 512;             // threads per CTA (2 CTAs / SM)
+constexpr int CH = 8192;            // compressed window bytes in shared memory
+constexpr int SMAX = 1024;          // sequences per batch
+constexpr int NCHAIN = SMAX / 32;
+constexpr int TILE = 16384;         // output tile bytes (pointer field is 15 bits)
+constexpr int EXT_MAX = 8;          // 0xFF-continuation bytes parsed in-window before deferring to the slow path
+constexpr unsigned SINK = CH;
+constexpr unsigned NX_EXIT = 0xFFFE, NX_END = 0xFFFD, NX_SLOW = 0xFFFC, NX_BAD = 0xFFFB, NX_CONT = 0xFFFA;
+
+struct __align__(16) SeqEnt { uint32_t out_start, L, lit_abs, off; };
+
+struct Smem {
+    __align__(16) uint8_t chunk[CH + 16];
+    __align__(16) uint16_t nxt1[CH + 8];
+    __align__(16) uint16_t pp[2][CH + 8];   // ping-pong doubling tables; reused as ent[TILE] in the copy phase
+    SeqEnt seq[SMAX];
+    uint16_t tok[SMAX];
+    uint16_t W[NCHAIN + 8];
+    unsigned scan[40];
+    unsigned nchains, K, term_kind, term_idx, next_idx_last, blk;
+    unsigned slow_next, slow_tot;
+    int slow_err;
+    rcz_mbar bar;
+};
+static_assert(2 * (CH + 8) >= TILE, "ent alias");
+
+struct Tok { uint32_t L, M, off, lit_idx, next_idx, kind; };   // kind: 0 regular, else NX_END / NX_SLOW / NX_BAD
+
+// Speculative parse of the token at window index j. `lim` = valid window bytes, `e` = window index of the
+// end of the block's input (may lie far beyond the window).
+__device__ __forceinline__ Tok parse_token(const uint8_t* c, uint32_t j, uint32_t lim, uint32_t e) {
+    Tok t; t.M = 0; t.off = 0; t.kind = 0; t.next_idx = 0;
+    const uint32_t tk = c[j];
+    uint32_t L = tk >> 4, p = j + 1;
+    t.L = 0; t.lit_idx = p;
+    if (L == 15) {                                              // lz4.rs:112-122 length()
+        int cnt = 0;
+        for (;;) {
+            if (p >= e) { t.kind = NX_BAD; return t; }
+            if (p >= lim || cnt >= EXT_MAX) { t.kind = NX_SLOW; return t; }
+            uint32_t b = c[p++]; L += b; ++cnt;
+            if (b != 255) break;
+        }
+    }
+    t.L = L; t.lit_idx = p;
+    if (L > e - p) { t.kind = NX_BAD; return t; }               // literal run past the input end
+    p += L;
+    if (p == e) { t.kind = NX_END; t.next_idx = p; return t; }  // lz4.rs:87: last sequence has literals only
+    if (e - p < 2) { t.kind = NX_BAD; return t; }               // truncated offset
+    if (p + 2 > lim) { t.kind = NX_SLOW; return t; }
+    t.off = (uint32_t)c[p] | ((uint32_t)c[p + 1] << 8);         // lz4.rs:91
+    p += 2;
+    uint32_t M = tk & 15;
+    if (M == 15) {
+        int cnt = 0;
+        for (;;) {
+            if (p >= e) { t.kind = NX_BAD; return t; }
+            if (p >= lim || cnt >= EXT_MAX) { t.kind = NX_SLOW; return t; }
+            uint32_t b = c[p++]; M += b; ++cnt;
+            if (b != 255) break;
+        }
+    }
+    t.M = M + 4;                                                // lz4.rs:99-106: always 4 + len bytes in total
+    t.next_idx = p;
+    if (p == e) t.kind = NX_END;                                // block ends right after a match: loop at lz4.rs:68 exits
+    return t;
+}
+
+// warp-parallel scan of a 0xFF-continued length starting at absolute position p (slow path only)
+__device__ __forceinline__ bool ext_scan(const uint8_t* in, unsigned n, unsigned& p, unsigned long long& acc) {
+    const unsigned lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned idx = p + lane;
+        unsigned b = idx < n ? in[idx] : 0u;
+        unsigned m = __ballot_sync(RCZ_FULL, b != 255u);
+        if (m == 0) { acc += 255ull * 32; p += 32; if (acc > 0xffffffffull) return false; continue; }
+        unsigned f = (unsigned)__ffs((int)m) - 1;
+        unsigned bf = __shfl_sync(RCZ_FULL, b, (int)f);
+        if (p + f >= n) return false;                           // ran off the end of the input: bump() panic
+        acc += 255ull * f + bf;
+        p += f + 1;
+        return true;
+    }
+}
+
+__global__ void __launch_bounds__(NT, 2)
+lz4_decode_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off,
+                  const uint64_t* __restrict__ in_len, uint8_t* __restrict__ out_base,
+                  const uint64_t* __restrict__ out_off, const uint64_t* __restrict__ out_cap,
+                  uint64_t* __restrict__ out_len, int32_t* __restrict__ status, unsigned nblocks,
+                  unsigned* __restrict__ ticket) {
+    RCZ_DYN_SMEM(raw);
+    Smem& sm = *reinterpret_cast<Smem*>(raw);
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint16_t* const ent = &sm.pp[0][0];
+    volatile uint16_t* const vent = ent;
+    unsigned phase = 0;
+
+    if (tid == 0) { mbar_init(&sm.bar, 1); mbar_fence_init(); }
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) sm.blk = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const unsigned b = sm.blk;
+        if (b >= nblocks) break;
+
+        const uint8_t* in = in_base + in_off[b];
+        const unsigned n = (unsigned)in_len[b];
+        uint8_t* out = out_base + out_off[b];
+        const unsigned long long cap64 = out_cap[b];
+        const unsigned cap = cap64 > 0x7fffffffull ? 0x7fffffffu : (unsigned)cap64;
+        unsigned cpos = 0, opos = 0;
+        int err = 0;
+
+        while (cpos < n && !err) {
+            // ---------------- P0: stage the compressed window (TMA bulk copy, 16-byte aligned source) ------------
+            const uintptr_t a = (uintptr_t)(in + cpos);
+            const unsigned lead = (unsigned)(a & 15);
+            const uint8_t* src = (const uint8_t*)(a - lead);
+            const unsigned avail = lead + (n - cpos);            // window index of the input end
+            const unsigned lim = avail < (unsigned)CH ? avail : (unsigned)CH;
+            const unsigned load_bytes = (lim + 15u) & ~15u;
+            __syncthreads();                                     // everyone is done with chunk / ent of the previous batch
+            if (tid == 0) {
+                fence_proxy_async_smem();
+                mbar_expect_tx(&sm.bar, load_bytes);
+                tma_load_1d(sm.chunk, src, load_bytes, &sm.bar);
+                if (avail > (unsigned)CH) {                      // warm L2 with the next window
+                    unsigned more = avail - CH; more = more > (unsigned)CH ? (unsigned)CH : more;
+                    prefetch_l2(src + CH, (more + 15u) & ~15u);
+                }
+            }
+            mbar_wait(&sm.bar, phase);
+            phase ^= 1;
+
+            // ---------------- P1: speculative next-token table ------------------------------------------------------
+            for (unsigned j = tid; j <= (unsigned)CH; j += NT) {
+                unsigned nx = NX_BAD;
+                if (j >= lead && j < lim) {
+                    Tok t = parse_token(sm.chunk, j, lim, avail);
+                    nx = t.kind ? t.kind : (t.next_idx < lim ? t.next_idx : NX_EXIT);
+                }
+                sm.nxt1[j] = (uint16_t)nx;
+                sm.pp[0][j] = (uint16_t)(nx < (unsigned)CH ? nx : SINK);
+            }
+            __syncthreads();
+            // ---------------- P2: pointer doubling nxt1 -> nxt32, hop, fill in ---------------------------------------
+#pragma unroll 1
+            for (int r = 0; r < 5; ++r) {
+                const uint16_t* s = sm.pp[r & 1];
+                uint16_t* d = sm.pp[(r & 1) ^ 1];
+                for (unsigned j = tid; j <= (unsigned)CH; j += NT) d[j] = s[s[j]];
+                __syncthreads();
+            }
+            if (tid == 0) {
+                const uint16_t* f32 = sm.pp[1];
+                unsigned nch = 1, t = lead;
+                sm.W[0] = (uint16_t)t;
+                while (nch < (unsigned)NCHAIN) {
+                    t = f32[t];
+                    if (t == SINK) break;
+                    sm.W[nch++] = (uint16_t)t;
+                }
+                sm.nchains = nch;
+            }
+            __syncthreads();
+            {
+                const unsigned nch = sm.nchains;
+                if (tid < nch) {
+                    unsigned t = sm.W[tid], cnt = 0;
+                    const unsigned base = tid * 32;
+                    const bool last = (tid == nch - 1);
+                    for (int i = 0; i < 32; ++i) {
+                        const unsigned nx = sm.nxt1[t];
+                        if (nx == NX_SLOW || nx == NX_BAD) { sm.term_kind = nx; sm.term_idx = t; break; }
+                        sm.tok[base + i] = (uint16_t)t; ++cnt;
+                        if (nx >= (unsigned)CH) { sm.term_kind = nx; sm.term_idx = t; break; }
+                        t = nx;
+                        if (i == 31 && last) { sm.term_kind = NX_CONT; sm.term_idx = t; }
+                    }
+                    if (last) sm.K = base + cnt;
+                }
+            }
+            __syncthreads();
+            unsigned K = sm.K;
+            const unsigned term_kind = sm.term_kind, term_idx = sm.term_idx;
+            unsigned batch_end, next_cpos;
+
+            if (K == 0) {
+                if (term_kind == NX_BAD) { err = RCZ_E_MALFORMED; break; }
+                // ------------ slow path: the first token of the window has fields that do not fit the window ---------
+                if (warp == 0) {
+                    int serr = 0;
+                    unsigned p = cpos;
+                    const unsigned tk = in[p]; ++p;
+                    unsigned long long L = tk >> 4, M = 0;
+                    unsigned off = 0, lit_abs = 0;
+                    if (L == 15 && !ext_scan(in, n, p, L)) serr = RCZ_E_MALFORMED;
+                    if (!serr) {
+                        lit_abs = p;
+                        if (L > (unsigned long long)(n - p)) serr = RCZ_E_MALFORMED;
+                        else p += (unsigned)L;
+                    }
+                    if (!serr && p < n) {
+                        if (n - p < 2) serr = RCZ_E_MALFORMED;
+                        else {
+                            off = (unsigned)in[p] | ((unsigned)in[p + 1] << 8); p += 2;
+                            M = tk & 15;
+                            if (M == 15 && !ext_scan(in, n, p, M)) serr = RCZ_E_MALFORMED;
+                            M += 4;
+                        }
+                    }
+                    if (!serr && M > 0 && (off == 0 || (unsigned long long)off > (unsigned long long)opos + L)) serr = RCZ_E_MALFORMED;
+                    if (!serr && L + M > (unsigned long long)(cap - opos)) serr = RCZ_E_OUTPUT_FULL;
+                    if (lane == 0) {
+                        sm.slow_err = serr;
+                        if (!serr) {
+                            SeqEnt s; s.out_start = opos; s.L = (unsigned)L; s.lit_abs = lit_abs; s.off = off;
+                            sm.seq[0] = s;
+                            sm.slow_next = p; sm.slow_tot = (unsigned)(L + M);
+                        }
+                    }
+                }
+                __syncthreads();
+                if (sm.slow_err) { err = sm.slow_err; break; }
+                K = 1;
+                batch_end = opos + sm.slow_tot;
+                next_cpos = sm.slow_next;
+            } else {
+                // ------------ P3: fields of every real token + prefix scan of sequence lengths -------------------------
+                Tok tk[2]; unsigned len[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const unsigned i = 2 * tid + q;
+                    len[q] = 0;
+                    if (i < K) { tk[q] = parse_token(sm.chunk, sm.tok[i], lim, avail); len[q] = tk[q].L + tk[q].M; }
+                }
+                unsigned tot;
+                const unsigned ex = block_excl_scan_add<NT>(len[0] + len[1], sm.scan, &tot);
+                int bad = 0;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const unsigned i = 2 * tid + q;
+                    if (i < K) {
+                        SeqEnt s;
+                        s.out_start = opos + ex + (q ? len[0] : 0u);
+                        s.L = tk[q].L;
+                        s.lit_abs = cpos + (tk[q].lit_idx - lead);
+                        s.off = tk[q].off;
+                        if (tk[q].M > 0 && (s.off == 0 || s.off > s.out_start + s.L)) bad = 1;   // lz4.rs:93 underflow / App. B #9
+                        sm.seq[i] = s;
+                        if (i == K - 1) sm.next_idx_last = tk[q].next_idx;
+                    }
+                }
+                bad = __syncthreads_or(bad);
+                if (bad) { err = RCZ_E_MALFORMED; break; }
+                if (tot > cap - opos) { err = RCZ_E_OUTPUT_FULL; break; }
+                batch_end = opos + tot;
+                if (term_kind == NX_END) next_cpos = n;
+                else if (term_kind == NX_EXIT) next_cpos = cpos + (sm.next_idx_last - lead);
+                else next_cpos = cpos + (term_idx - lead);           // NX_CONT / NX_SLOW / NX_BAD: resume at that token
+            }
+
+            // ---------------- P4-P6: materialise the batch's output, one tile at a time -----------------------------
+            for (unsigned t0 = opos; t0 < batch_end; t0 += TILE) {
+                const unsigned tlen = (batch_end - t0) < (unsigned)TILE ? (batch_end - t0) : (unsigned)TILE;
+                const unsigned tlen8 = (tlen + 7u) & ~7u;
+                {   // zero the label array
+                    uint32_t* e32 = reinterpret_cast<uint32_t*>(ent);
+                    for (unsigned i = tid; i < tlen8 / 2; i += NT) e32[i] = 0;
+                }
+                __syncthreads();
+                for (unsigned i = tid; i < K; i += NT) {
+                    const unsigned s = sm.seq[i].out_start;
+                    if (s >= t0 && s - t0 < tlen) ent[s - t0] = (uint16_t)(i + 1);
+                }
+                __syncthreads();
+                {   // per-warp inclusive max-scan: every byte learns (index+1) of the sequence covering it
+                    constexpr unsigned WSPAN = TILE / (NT / 32);
+                    const unsigned wbase = warp * WSPAN;
+                    if (wbase < tlen) {
+                        // carry-in = number of sequences that start before this warp's range
+                        const unsigned x = t0 + wbase;
+                        unsigned lo = 0, hi = K;
+                        while (lo < hi) { unsigned mid = (lo + hi) >> 1; if (sm.seq[mid].out_start < x) lo = mid + 1; else hi = mid; }
+                        unsigned carry = lo;
+                        for (unsigned it = 0; it < WSPAN / 256; ++it) {
+                            const unsigned base = wbase + it * 256 + lane * 8;
+                            if (wbase + it * 256 >= tlen8) break;
+                            unsigned v[8];
+                            if (base < tlen8) {
+                                const uint4 q = *reinterpret_cast<const uint4*>(&ent[base]);
+                                v[0] = q.x & 0xffff; v[1] = q.x >> 16; v[2] = q.y & 0xffff; v[3] = q.y >> 16;
+                                v[4] = q.z & 0xffff; v[5] = q.z >> 16; v[6] = q.w & 0xffff; v[7] = q.w >> 16;
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) v[k] = 0;
+                            }
+#pragma unroll
+                            for (int k = 1; k < 8; ++k) v[k] = max(v[k], v[k - 1]);
+                            const unsigned incl = warp_incl_scan_max(v[7]);
+                            unsigned pre = __shfl_up_sync(RCZ_FULL, incl, 1);
+                            pre = lane == 0 ? carry : max(pre, carry);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) v[k] = max(v[k], pre);
+                            if (base < tlen8) {
+                                uint4 q;
+                                q.x = v[0] | (v[1] << 16); q.y = v[2] | (v[3] << 16);
+                                q.z = v[4] | (v[5] << 16); q.w = v[6] | (v[7] << 16);
+                                *reinterpret_cast<uint4*>(&ent[base]) = q;
+                            }
+                            carry = max(carry, __shfl_sync(RCZ_FULL, incl, 31));
+                        }
+                    }
+                }
+                __syncthreads();
+                int anyptr = 0;
+                for (unsigned i = tid; i < tlen; i += NT) {
+                    const unsigned si = (unsigned)ent[i] - 1u;
+                    const SeqEnt s = sm.seq[si];
+                    const unsigned pos = t0 + i, rel = pos - s.out_start;
+                    unsigned e;
+                    if (rel < s.L) {                                         // literal byte (lz4.rs:75-85)
+                        const unsigned la = s.lit_abs + rel;
+                        const unsigned wi = (la - cpos) + lead;
+                        e = wi < lim ? (unsigned)sm.chunk[wi] : (unsigned)__ldg(in + la);
+                    } else {                                                 // match byte (lz4.rs:96-107, cp lz4.rs:131-140)
+                        const unsigned k = rel - s.L, off = s.off;
+                        const unsigned srcp = k < off ? pos - off : (s.out_start + s.L - off) + (k % off);
+                        if (srcp < t0) e = out[srcp];                        // already final in HBM/L2
+                        else { e = 0x8000u | (srcp - t0); anyptr = 1; }
+                    }
+                    ent[i] = (uint16_t)e;
+                }
+                int pend = __syncthreads_or(anyptr);
+                while (pend) {                                               // P5: pointer doubling inside the tile
+                    int p2 = 0;
+                    for (unsigned i = tid; i < tlen; i += NT) {
+                        const unsigned e = vent[i];
+                        if (e & 0x8000u) {
+                            const unsigned f = vent[e & 0x7fffu];
+                            vent[i] = (uint16_t)f;
+                            p2 |= (int)(f >> 15);
+                        }
+                    }
+                    pend = __syncthreads_or(p2);
+                }
+                for (unsigned i = tid; i < tlen; i += NT) out[t0 + i] = (uint8_t)ent[i];   // P6
+                __syncthreads();
+            }
+            opos = batch_end;
+            cpos = next_cpos;
+        }
+        __syncthreads();
+        if (tid == 0) { out_len[b] = opos; status[b] = err; }
+    }
+}
+
+}  // namespace lz4k
+
+static int lz4_launch(rcz_ctx* c, const uint8_t* in, const uint64_t* in_off, const uint64_t* in_len, uint8_t* out,
+                      const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len, int32_t* status, size_t nblocks) {
+    void* tk;
+    int st = ctx_ws(c, WS_A, 256, &tk); if (st) return st;
+    RCZ_CK(c, rt_memset(tk, 0, 256, c->stream));
+    const size_t smem = sizeof(lz4k::Smem);
+    RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(lz4k::lz4_decode_kernel, smem));
+    size_t grid = nblocks < (size_t)2 * c->sm_count ? nblocks : (size_t)2 * c->sm_count;
+    st = ctx_timer_begin(c); if (st) return st;
+    RCZ_KLAUNCH(c, lz4k::lz4_decode_kernel, (unsigned)grid, lz4k::NT, smem, in, in_off, in_len, out, out_off, out_cap, out_len, status,
+                (unsigned)nblocks, (unsigned*)tk);
+    return ctx_timer_end(c);
+}
+
+extern "C" int rcz_lz4_decode_blocks(rcz_ctx* c, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                                     void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
+                                     uint64_t* out_len, int32_t* status, size_t nblocks, int mem_kind) {
+    if (!c || rcz_bad_kind(mem_kind)) return RCZ_E_ARG;
+    if (nblocks == 0) return RCZ_OK;
+    if (!in_base || !in_off || !in_len || !out_base || !out_off || !out_cap || !out_len || !status) return RCZ_E_ARG;
+    if (nblocks > 0x7fffffffu) return RCZ_E_ARG;
+    rt_set_device(c->device);
+    for (size_t i = 0; i < nblocks; ++i) if (in_len[i] >= (1ull << 31)) return RCZ_E_ARG;
+    DescStager ds(c, mem_kind, nblocks);
+    ds.add_in(in_off, nblocks * 8); ds.add_in(in_len, nblocks * 8); ds.add_in(out_off, nblocks * 8); ds.add_in(out_cap, nblocks * 8);
+    ds.add_out(out_len, nblocks * 8); ds.add_out(status, nblocks * 4);
+    int st = ds.upload(); if (st) return st;
+    const uint8_t* din = (const uint8_t*)in_base; uint8_t* dout = (uint8_t*)out_base;
+    if (mem_kind == RCZ_MEM_HOST) {
+        st = stage_span_in(c, WS_IN, in_base, in_off, in_len, nblocks, 1, &din); if (st) return st;
+        st = stage_span_out(c, WS_OUT, out_off, out_cap, nblocks, 1, &dout); if (st) return st;
+    }
+    st = lz4_launch(c, din, ds.in_ptr<uint64_t>(0), ds.in_ptr<uint64_t>(1), dout, ds.in_ptr<uint64_t>(2), ds.in_ptr<uint64_t>(3),
+                    ds.out_ptr<uint64_t>(0), ds.out_ptr<int32_t>(1), nblocks);
+    if (st) return st;
+    st = ds.download(); if (st) return st;
+    if (mem_kind == RCZ_MEM_HOST) { st = unstage_span_out(c, out_base, dout, out_off, out_len, nblocks, 1); if (st) return st; }
+    return RCZ_OK;
+}

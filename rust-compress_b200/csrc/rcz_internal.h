@@ -1,0 +1,146 @@
+// rcz_internal.h — context, workspace and batch staging shared by all librcz ops.
+#pragma once
+#include "../../include/rcz.h"
+#include "rt.h"
+#include <stdio.h>
+#include <vector>
+
+enum { WS_IN = 0, WS_OUT = 1, WS_DESC = 2, WS_A = 3, WS_B = 4, WS_C = 5, WS_D = 6, WS_E = 7, WS_COUNT = 8 };
+
+struct rcz_ctx {
+    int device = 0;
+    int sm_count = 148;
+    rt_stream_t stream = 0;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    rt_event_t ev0 = 0, ev1 = 0;
+    bool ev_valid = false;
+    char err[256] = {0};
+    struct { void* p; size_t cap; } ws[WS_COUNT] = {};
+    void* pinned = nullptr;
+    size_t pinned_cap = 0;
+};
+
+#define RCZ_CK(ctx, expr)                                                                              \
+    do {                                                                                               \
+        int e__ = (expr);                                                                              \
+        if (e__ != 0) {                                                                                \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,     \
+                     rt_error_string(e__));                                                            \
+            return RCZ_E_CUDA;                                                                         \
+        }                                                                                              \
+    } while (0)
+
+#define RCZ_KLAUNCH(ctx, kern, grid, block, smem, ...)                   \
+    do {                                                                 \
+        RCZ_LAUNCH(kern, grid, block, smem, (ctx)->stream, __VA_ARGS__); \
+        (ctx)->launches++;                                               \
+        RCZ_CK(ctx, rt_last_error());                                    \
+    } while (0)
+
+// grow-only device workspace slot
+inline int ctx_ws(rcz_ctx* c, int slot, size_t bytes, void** out) {
+    if (c->ws[slot].cap < bytes) {
+        if (c->ws[slot].p) { RCZ_CK(c, rt_stream_sync(c->stream)); RCZ_CK(c, rt_free(c->ws[slot].p)); c->ws[slot].p = nullptr; c->ws[slot].cap = 0; }
+        size_t cap = (bytes + (bytes >> 3) + 4095) & ~(size_t)4095;
+        RCZ_CK(c, rt_malloc(&c->ws[slot].p, cap));
+        c->ws[slot].cap = cap;
+    }
+    *out = c->ws[slot].p;
+    return RCZ_OK;
+}
+inline int ctx_pinned(rcz_ctx* c, size_t bytes, void** out) {
+    if (c->pinned_cap < bytes) {
+        if (c->pinned) { RCZ_CK(c, rt_stream_sync(c->stream)); RCZ_CK(c, rt_host_free(c->pinned)); c->pinned = nullptr; c->pinned_cap = 0; }
+        size_t cap = (bytes * 2 + 4095) & ~(size_t)4095;
+        RCZ_CK(c, rt_host_alloc(&c->pinned, cap));
+        c->pinned_cap = cap;
+    }
+    *out = c->pinned;
+    return RCZ_OK;
+}
+inline int ctx_timer_begin(rcz_ctx* c) { c->ev_valid = false; RCZ_CK(c, rt_event_record(c->ev0, c->stream)); return RCZ_OK; }
+inline int ctx_timer_end(rcz_ctx* c) { RCZ_CK(c, rt_event_record(c->ev1, c->stream)); c->ev_valid = true; return RCZ_OK; }
+
+// ------------------------------------------------------------------------------------------------
+// Descriptor staging.  Every batch op has a few per-unit input arrays (offsets, lengths, ...) — always HOST
+// arrays, in every mem_kind, so that the host can size grids — and a few per-unit result arrays (out_len,
+// status, ...).  Inputs are packed and uploaded with one H2D from pageable memory (the driver stages it
+// before returning, so the call may return before the copy executes).  Results live in a device arena and
+// come back with one D2H in HOST / DEVICE mode; in DEVICE_ASYNC mode the caller's device arrays are written
+// directly and nothing is synchronised.
+// ------------------------------------------------------------------------------------------------
+struct DescStager {
+    rcz_ctx* c; int kind; size_t n;
+    struct In { const void* host; size_t bytes; size_t off; };
+    struct Out { void* host; size_t bytes; size_t off; };
+    std::vector<In> ins; std::vector<Out> outs;
+    std::vector<uint8_t> pack;
+    size_t in_bytes = 0, out_bytes = 0;
+    uint8_t* dev = nullptr;
+    DescStager(rcz_ctx* c_, int kind_, size_t n_) : c(c_), kind(kind_), n(n_) {}
+    size_t add_in(const void* host, size_t bytes) { ins.push_back({host, bytes, in_bytes}); in_bytes += (bytes + 15) & ~(size_t)15; return ins.size() - 1; }
+    size_t add_out(void* host, size_t bytes) { outs.push_back({host, bytes, out_bytes}); out_bytes += (bytes + 15) & ~(size_t)15; return outs.size() - 1; }
+    int upload(int slot = WS_DESC) {
+        void* d;
+        int st = ctx_ws(c, slot, in_bytes + out_bytes + 256, &d); if (st) return st;
+        dev = (uint8_t*)d;
+        pack.assign(in_bytes + 16, 0);
+        for (auto& i : ins) if (i.bytes) memcpy(pack.data() + i.off, i.host, i.bytes);
+        RCZ_CK(c, rt_h2d(dev, pack.data(), in_bytes, c->stream));
+        return RCZ_OK;
+    }
+    template <class T> const T* in_ptr(size_t idx) const { return (const T*)(dev + ins[idx].off); }
+    template <class T> T* out_ptr(size_t idx) const {
+        if (kind == RCZ_MEM_DEVICE_ASYNC) return (T*)outs[idx].host;
+        return (T*)(dev + in_bytes + outs[idx].off);
+    }
+    // download results + synchronise (no-op in async mode)
+    int download() {
+        if (kind == RCZ_MEM_DEVICE_ASYNC) return RCZ_OK;
+        pack.assign(out_bytes + 16, 0);
+        RCZ_CK(c, rt_d2h(pack.data(), dev + in_bytes, out_bytes, c->stream));
+        RCZ_CK(c, rt_stream_sync(c->stream));
+        for (auto& o : outs) if (o.bytes && o.host) memcpy(o.host, pack.data() + o.off, o.bytes);
+        return RCZ_OK;
+    }
+};
+
+// Host-resident data staging: upload the byte span covered by (off[i], len[i]) and return a virtual device
+// base such that base + off[i] addresses block i (offsets keep their low 8 bits => same 16-byte phase).
+inline int stage_span_in(rcz_ctx* c, int slot, const void* host_base, const uint64_t* off, const uint64_t* len, size_t n,
+                         size_t elem, const uint8_t** dev_base) {
+    uint64_t lo = UINT64_MAX, hi = 0;
+    for (size_t i = 0; i < n; ++i) { if (len[i] == 0) continue; lo = off[i] < lo ? off[i] : lo; hi = off[i] + len[i] > hi ? off[i] + len[i] : hi; }
+    if (lo == UINT64_MAX) { lo = 0; hi = 0; }
+    uint64_t lo_al = (lo * elem) & ~(uint64_t)255;
+    void* d; int st = ctx_ws(c, slot, (size_t)(hi * elem - lo_al) + 512, &d); if (st) return st;
+    RCZ_CK(c, rt_h2d((uint8_t*)d + (lo * elem - lo_al), (const uint8_t*)host_base + lo * elem, (size_t)((hi - lo) * elem), c->stream));
+    *dev_base = (const uint8_t*)d - lo_al;
+    return RCZ_OK;
+}
+inline int stage_span_out(rcz_ctx* c, int slot, const uint64_t* off, const uint64_t* cap, size_t n, size_t elem, uint8_t** dev_base) {
+    uint64_t lo = UINT64_MAX, hi = 0;
+    for (size_t i = 0; i < n; ++i) { if (cap[i] == 0) continue; lo = off[i] < lo ? off[i] : lo; hi = off[i] + cap[i] > hi ? off[i] + cap[i] : hi; }
+    if (lo == UINT64_MAX) { lo = 0; hi = 0; }
+    uint64_t lo_al = (lo * elem) & ~(uint64_t)255;
+    void* d; int st = ctx_ws(c, slot, (size_t)(hi * elem - lo_al) + 512, &d); if (st) return st;
+    *dev_base = (uint8_t*)d - lo_al;
+    return RCZ_OK;
+}
+// copy back out_len[i] elements of every unit (adjacent units are merged into one copy); call after download()
+inline int unstage_span_out(rcz_ctx* c, void* host_base, const uint8_t* dev_base, const uint64_t* off, const uint64_t* len, size_t n,
+                            size_t elem) {
+    size_t i = 0;
+    while (i < n) {
+        if (len[i] == 0) { ++i; continue; }
+        uint64_t s = off[i], e = off[i] + len[i];
+        size_t j = i + 1;
+        while (j < n && (len[j] == 0 || off[j] == e)) { e += len[j]; ++j; }
+        RCZ_CK(c, rt_d2h((uint8_t*)host_base + s * elem, dev_base + s * elem, (size_t)((e - s) * elem), c->stream));
+        i = j;
+    }
+    RCZ_CK(c, rt_stream_sync(c->stream));
+    return RCZ_OK;
+}
+inline bool rcz_bad_kind(int k) { return k != RCZ_MEM_HOST && k != RCZ_MEM_DEVICE && k != RCZ_MEM_DEVICE_ASYNC; }

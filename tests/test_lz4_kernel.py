@@ -1,0 +1,128 @@
+"""LZ4 block-decode kernel (csrc/lz4_decode.cu) against the oracle: bit-exact output, identical status.
+
+The cases run twice: on the CPU SIMT emulation build (no GPU needed; catches logic errors here) and, marked
+`gpu`, on the real sm_100a library through the C ABI with device-resident and host-resident buffers."""
+import random
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from util import run_batch
+
+TXT = golden("ref_test.txt")
+
+
+def _cases(oracle, gen):
+    c = gen.lz4_compress(TXT)
+    cases = {
+        "empty": ([b""], [16]),
+        "tiny": ([bytes([0x10, 0x41])], [16]),
+        "txt_ref_encoder": ([oracle.lz4_encode_block(TXT)], [4096]),
+        "txt_liblz4": ([c], [3050]),
+        "txt_liblz4_hc": ([gen.lz4_compress(TXT, hc=True)], [3050]),
+        "zeros_long_match": ([gen.lz4_compress(bytes(300000))], [300000]),
+        "zeros_ref_encoder": ([oracle.lz4_encode_block(bytes(300000))], [300000]),
+        "incompressible_long_literals": ([gen.lz4_compress(gen.one("random", 7, 100000))], [100000]),
+        "lzsyn_512k": ([gen.lz4_compress(gen.one("lzsyn", gen.unit_seed(2, 0), 1 << 19))], [1 << 19]),
+        "lzsyn_ref_encoder": ([oracle.lz4_encode_block(gen.one("lzsyn", gen.unit_seed(2, 1), 1 << 18))], [1 << 18]),
+        "hextext": ([gen.lz4_compress(gen.one("hextext", 3, 200000))], [200000]),
+        "runs": ([gen.lz4_compress(gen.one("runs", 4, 150000))], [150000]),
+        "batch_ragged": ([gen.lz4_compress(gen.one("lzsyn", 100 + i, 20000 + i * 777)) for i in range(7)] + [b"", c],
+                         [20000 + i * 777 for i in range(7)] + [0, 3050]),
+        "output_full": ([c], [3000]),
+        "truncated_half": ([c[: len(c) // 2]], [4096]),
+        "truncated_1": ([c[:-1]], [4096]),
+        "offset_zero": ([bytes([0x10, 0x41, 0, 0, 0x00])], [64]),
+        "offset_before_start": ([bytes([0x10, 0x41, 5, 0, 0x00])], [64]),
+        "literal_overrun": ([bytes([0xF0, 0xFF, 0xFF])], [100000]),
+        "ends_after_match": ([bytes([0x14, 0x41, 1, 0])], [64]),
+    }
+    for per in (1, 2, 3, 4, 5, 7, 13, 255, 256, 65535):     # offsets 1..3 exercise the DECR path (lz4.rs:100-102)
+        d = (bytes((i * 37 + 11) & 255 for i in range(per)) * (140000 // per + 2))[:140001]
+        cases["period_%d" % per] = ([gen.lz4_compress(d)], [len(d)])
+    rnd = random.Random(1)
+    for k in range(8):
+        bb = bytearray(c)
+        for _ in range(3):
+            bb[rnd.randrange(len(bb))] = rnd.randrange(256)
+        cases["fuzz_%d" % k] = ([bytes(bb)], [8192])
+    return cases
+
+
+CASE_NAMES = ["empty", "tiny", "txt_ref_encoder", "txt_liblz4", "txt_liblz4_hc", "zeros_long_match", "zeros_ref_encoder",
+              "incompressible_long_literals", "lzsyn_512k", "lzsyn_ref_encoder", "hextext", "runs", "batch_ragged", "output_full",
+              "truncated_half", "truncated_1", "offset_zero", "offset_before_start", "literal_overrun", "ends_after_match"] + \
+             ["period_%d" % p for p in (1, 2, 3, 4, 5, 7, 13, 255, 256, 65535)] + ["fuzz_%d" % k for k in range(8)]
+
+
+def _check(ctx, oracle, units, caps, **kw):
+    got, _ = run_batch(ctx, "lz4_decode_blocks", units, caps, **kw)
+    for i, (u, cap) in enumerate(zip(units, caps)):
+        st, ref = oracle.lz4_decode_block(u, cap)
+        assert got[i][0] == st, (i, got[i][0], st)
+        if st == 0:
+            assert got[i][1] == ref, "block %d differs" % i
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_lz4_emu(emu_ctx, oracle, gen, name):
+    units, caps = _cases(oracle, gen)[name]
+    _check(emu_ctx, oracle, units, caps, pad_front=5, gap=3)
+
+
+def test_lz4_emu_frame_fixtures(emu_ctx, oracle):
+    """The nine reference frames (lz4.rs:647-659): one compressed block each, FLG 0x64 / BD 0x70."""
+    for i in range(1, 10):
+        f = golden("ref_test.lz4.%d" % i)
+        size = int.from_bytes(f[7:11], "little")
+        got, _ = run_batch(emu_ctx, "lz4_decode_blocks", [f[11: 11 + size]], [4096])
+        assert got[0] == (0, TXT)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("device", [True, False])
+def test_lz4_gpu_cases(gpu_ctx, oracle, gen, device):
+    cases = _cases(oracle, gen)
+    for name in CASE_NAMES:
+        units, caps = cases[name]
+        _check(gpu_ctx, oracle, units, caps, device=device, pad_front=5, gap=3)
+    for i in range(1, 10):
+        f = golden("ref_test.lz4.%d" % i)
+        size = int.from_bytes(f[7:11], "little")
+        got, _ = run_batch(gpu_ctx, "lz4_decode_blocks", [f[11: 11 + size]], [4096], device=device)
+        assert got[0] == (0, TXT)
+
+
+@pytest.mark.gpu
+def test_lz4_gpu_4mib_blocks(gpu_ctx, oracle, gen):
+    """BASELINE config 2 shape at reduced count: 16 x 4 MiB lzsyn blocks, liblz4-compressed, vs the oracle."""
+    import torch
+    unit, count = 4 << 20, 16
+    raw = gen.units("lzsyn", gen.unit_seed(2, 0), unit, count)
+    packed, off, lens = gen.lz4_compress_units(raw, unit, count)
+    d_in = torch.from_numpy(packed).cuda()
+    d_out = torch.zeros(unit * count, dtype=torch.uint8, device="cuda")
+    out_off = np.arange(count, dtype=np.uint64) * unit
+    out_len, status = gpu_ctx.lz4_decode_blocks(d_in, off, lens, d_out, out_off, np.full(count, unit, dtype=np.uint64))
+    assert (status == 0).all() and (out_len == unit).all()
+    assert bytes(d_out.cpu().numpy()) == raw.tobytes()
+    ref_len, ref_st = oracle.lz4_decode_blocks_mt(packed, off, lens, np.zeros(unit * count, np.uint8), out_off, np.full(count, unit, np.uint64), 4)
+    assert (ref_st == 0).all() and (ref_len == out_len).all()
+
+
+@pytest.mark.gpu
+def test_lz4_gpu_full_config_roundtrip(gpu_ctx, gen):
+    """BASELINE config 2 at full size (256 x 4 MiB) via a size-independent property: decode(compress(x)) == x,
+    checked on the device by comparing against the uploaded original."""
+    import torch
+    unit, count = 4 << 20, 256
+    raw = gen.units("lzsyn", gen.unit_seed(2, 0), unit, count)
+    packed, off, lens = gen.lz4_compress_units(raw, unit, count)
+    d_in = torch.from_numpy(packed).cuda()
+    d_raw = torch.from_numpy(raw).cuda()
+    d_out = torch.zeros(unit * count, dtype=torch.uint8, device="cuda")
+    out_off = np.arange(count, dtype=np.uint64) * unit
+    out_len, status = gpu_ctx.lz4_decode_blocks(d_in, off, lens, d_out, out_off, np.full(count, unit, dtype=np.uint64))
+    assert (status == 0).all() and (out_len == unit).all()
+    assert torch.equal(d_out, d_raw)
