@@ -26,20 +26,23 @@
 namespace lz4k {
 
 constexpr int NT = 512;             // threads per CTA (2 CTAs / SM)
-constexpr int CH = 8192;            // compressed window bytes in shared memory
+constexpr int CH = 8192;            // compressed window bytes in shared memory (= 16 * NT)
 constexpr int SMAX = 1024;          // sequences per batch
-constexpr int NCHAIN = SMAX / 32;
-constexpr int TILE = 16384;         // output tile bytes (pointer field is 15 bits)
+constexpr int HOP = 8;              // tokens per walker hop (3 doubling rounds)
+constexpr int NCHAIN = SMAX / HOP;
+constexpr int TILE = 16384;         // output tile entries (pointer field is 15 bits)
 constexpr int EXT_MAX = 8;          // 0xFF-continuation bytes parsed in-window before deferring to the slow path
 constexpr unsigned SINK = CH;
 constexpr unsigned NX_EXIT = 0xFFFE, NX_END = 0xFFFD, NX_SLOW = 0xFFFC, NX_BAD = 0xFFFB, NX_CONT = 0xFFFA;
+static_assert(CH == 16 * NT, "P1 assigns 16 consecutive window bytes to every thread");
+static_assert(NCHAIN <= NT, "one thread per chain");
 
 struct __align__(16) SeqEnt { uint32_t out_start, L, lit_abs, off; };
 
 struct Smem {
-    __align__(16) uint8_t chunk[CH + 16];
+    __align__(16) uint8_t chunk[2][CH + 16];   // double-buffered compressed window (TMA destination)
     __align__(16) uint16_t nxt1[CH + 8];
-    __align__(16) uint16_t pp[2][CH + 8];   // ping-pong doubling tables; reused as ent[TILE] in the copy phase
+    __align__(16) uint16_t pp[2][CH + 8];      // ping-pong doubling tables; reused as ent[TILE] in the copy phase
     SeqEnt seq[SMAX];
     uint16_t tok[SMAX];
     uint16_t W[NCHAIN + 8];
@@ -47,7 +50,7 @@ struct Smem {
     unsigned nchains, K, term_kind, term_idx, next_idx_last, blk;
     unsigned slow_next, slow_tot;
     int slow_err;
-    rcz_mbar bar;
+    rcz_mbar bar[2];
 };
 static_assert(2 * (CH + 8) >= TILE, "ent alias");
 
@@ -93,6 +96,23 @@ __device__ __forceinline__ Tok parse_token(const uint8_t* c, uint32_t j, uint32_
     return t;
 }
 
+// next-token code of window position j whose token byte is tk (same result as parse_token, but the common
+// case — neither length nibble is 15 — needs no further loads)
+__device__ __forceinline__ unsigned next_code(const uint8_t* c, uint32_t tk, uint32_t j, uint32_t lim, uint32_t e) {
+    const uint32_t L = tk >> 4, M = tk & 15;
+    if (L != 15 && M != 15) {
+        const uint32_t p = j + 1 + L;
+        if (p > e) return NX_BAD;
+        if (p == e) return NX_END;
+        if (e - p < 2) return NX_BAD;
+        if (p + 2 > lim) return NX_SLOW;
+        if (p + 2 == e) return NX_END;
+        return p + 2 < lim ? p + 2 : NX_EXIT;
+    }
+    const Tok t = parse_token(c, j, lim, e);
+    return t.kind ? t.kind : (t.next_idx < lim ? t.next_idx : NX_EXIT);
+}
+
 // warp-parallel scan of a 0xFF-continued length starting at absolute position p (slow path only)
 __device__ __forceinline__ bool ext_scan(const uint8_t* in, unsigned n, unsigned& p, unsigned long long& acc) {
     const unsigned lane = threadIdx.x & 31;
@@ -110,6 +130,28 @@ __device__ __forceinline__ bool ext_scan(const uint8_t* in, unsigned n, unsigned
     }
 }
 
+__device__ __forceinline__ void unpack8(const uint4 q, unsigned* v) {
+    v[0] = q.x & 0xffff; v[1] = q.x >> 16; v[2] = q.y & 0xffff; v[3] = q.y >> 16;
+    v[4] = q.z & 0xffff; v[5] = q.z >> 16; v[6] = q.w & 0xffff; v[7] = q.w >> 16;
+}
+__device__ __forceinline__ uint4 pack8(const unsigned* v) {
+    uint4 q;
+    q.x = v[0] | (v[1] << 16); q.y = v[2] | (v[3] << 16); q.z = v[4] | (v[5] << 16); q.w = v[6] | (v[7] << 16);
+    return q;
+}
+
+// issue the TMA bulk copy of the window that starts at compressed offset cpos into buffer `buf`
+__device__ __forceinline__ void issue_window(Smem& sm, int buf, const uint8_t* in, unsigned n, unsigned cpos) {
+    const uintptr_t a = (uintptr_t)(in + cpos);
+    const unsigned lead = (unsigned)(a & 15);
+    const unsigned avail = lead + (n - cpos);
+    const unsigned lim = avail < (unsigned)CH ? avail : (unsigned)CH;
+    const unsigned load_bytes = (lim + 15u) & ~15u;
+    fence_proxy_async_smem();
+    mbar_expect_tx(&sm.bar[buf], load_bytes);
+    tma_load_1d(sm.chunk[buf], (const uint8_t*)(a - lead), load_bytes, &sm.bar[buf]);
+}
+
 __global__ void __launch_bounds__(NT, 2)
 lz4_decode_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off,
                   const uint64_t* __restrict__ in_len, uint8_t* __restrict__ out_base,
@@ -121,9 +163,9 @@ lz4_decode_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restric
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint16_t* const ent = &sm.pp[0][0];
     volatile uint16_t* const vent = ent;
-    unsigned phase = 0;
+    unsigned phase[2] = {0, 0};
 
-    if (tid == 0) { mbar_init(&sm.bar, 1); mbar_fence_init(); }
+    if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); mbar_fence_init(); }
     __syncthreads();
 
     for (;;) {
@@ -138,54 +180,78 @@ lz4_decode_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restric
         const unsigned long long cap64 = out_cap[b];
         const unsigned cap = cap64 > 0x7fffffffull ? 0x7fffffffu : (unsigned)cap64;
         unsigned cpos = 0, opos = 0;
-        int err = 0;
+        int err = 0, buf = 0;
+        bool loaded = false;                                     // window for `cpos` already in flight in chunk[buf]?
 
         while (cpos < n && !err) {
-            // ---------------- P0: stage the compressed window (TMA bulk copy, 16-byte aligned source) ------------
-            const uintptr_t a = (uintptr_t)(in + cpos);
-            const unsigned lead = (unsigned)(a & 15);
-            const uint8_t* src = (const uint8_t*)(a - lead);
+            // ---------------- P0: compressed window in shared memory (TMA bulk copy, 16-byte aligned source) ------
+            const unsigned lead = (unsigned)((uintptr_t)(in + cpos) & 15);
             const unsigned avail = lead + (n - cpos);            // window index of the input end
             const unsigned lim = avail < (unsigned)CH ? avail : (unsigned)CH;
-            const unsigned load_bytes = (lim + 15u) & ~15u;
-            __syncthreads();                                     // everyone is done with chunk / ent of the previous batch
-            if (tid == 0) {
-                fence_proxy_async_smem();
-                mbar_expect_tx(&sm.bar, load_bytes);
-                tma_load_1d(sm.chunk, src, load_bytes, &sm.bar);
-                if (avail > (unsigned)CH) {                      // warm L2 with the next window
-                    unsigned more = avail - CH; more = more > (unsigned)CH ? (unsigned)CH : more;
-                    prefetch_l2(src + CH, (more + 15u) & ~15u);
-                }
-            }
-            mbar_wait(&sm.bar, phase);
-            phase ^= 1;
+            const uint8_t* chunk = sm.chunk[buf];
+            __syncthreads();                                     // everyone is done with ent / seq of the previous batch
+            if (!loaded && tid == 0) issue_window(sm, buf, in, n, cpos);
+            mbar_wait(&sm.bar[buf], phase[buf]);
+            phase[buf] ^= 1;
+            loaded = false;
 
-            // ---------------- P1: speculative next-token table ------------------------------------------------------
-            for (unsigned j = tid; j <= (unsigned)CH; j += NT) {
-                unsigned nx = NX_BAD;
-                if (j >= lead && j < lim) {
-                    Tok t = parse_token(sm.chunk, j, lim, avail);
-                    nx = t.kind ? t.kind : (t.next_idx < lim ? t.next_idx : NX_EXIT);
+            // ---------------- P1: speculative next-token table (16 consecutive positions per thread) ---------------
+            {
+                const unsigned j0 = tid * 16;
+                const uint4 q = *reinterpret_cast<const uint4*>(chunk + j0);
+                const unsigned w4[4] = {q.x, q.y, q.z, q.w};
+                unsigned nx[16];
+                // interior threads: every field of a short token (no 0xF nibble) provably lies inside the window,
+                // so the next-token index is pure arithmetic on the token byte
+                const bool interior = (j0 >= lead) && (j0 + 16 + 17 < lim);
+                unsigned slowmask = 0;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const unsigned tk = (w4[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+                    const unsigned L = tk >> 4;
+                    nx[k] = j0 + k + 3 + L;
+                    if (L == 15 || (tk & 15u) == 15u) slowmask |= 1u << k;
                 }
-                sm.nxt1[j] = (uint16_t)nx;
-                sm.pp[0][j] = (uint16_t)(nx < (unsigned)CH ? nx : SINK);
+                if (!interior) slowmask = 0xffffu;
+                *reinterpret_cast<uint4*>(&sm.nxt1[j0]) = pack8(nx);
+                *reinterpret_cast<uint4*>(&sm.nxt1[j0 + 8]) = pack8(nx + 8);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) nx[k] = nx[k] < (unsigned)CH ? nx[k] : SINK;
+                *reinterpret_cast<uint4*>(&sm.pp[0][j0]) = pack8(nx);
+                *reinterpret_cast<uint4*>(&sm.pp[0][j0 + 8]) = pack8(nx + 8);
+#pragma unroll 1
+                while (slowmask) {                                   // ~12 % of positions: 0xF nibbles, window edges
+                    const int k = __ffs((int)slowmask) - 1;
+                    slowmask &= slowmask - 1;
+                    const unsigned j = j0 + k;
+                    const unsigned v = (j >= lead && j < lim) ? next_code(chunk, chunk[j], j, lim, avail) : NX_BAD;
+                    sm.nxt1[j] = (uint16_t)v;
+                    sm.pp[0][j] = (uint16_t)(v < (unsigned)CH ? v : SINK);
+                }
+                if (tid == 0) { sm.nxt1[CH] = (uint16_t)NX_BAD; sm.pp[0][CH] = (uint16_t)SINK; sm.pp[1][CH] = (uint16_t)SINK; }
             }
             __syncthreads();
-            // ---------------- P2: pointer doubling nxt1 -> nxt32, hop, fill in ---------------------------------------
+            // ---------------- P2: pointer doubling nxt1 -> nxt8, hop, fill in ----------------------------------------
 #pragma unroll 1
-            for (int r = 0; r < 5; ++r) {
+            for (int r = 0; r < 3; ++r) {
                 const uint16_t* s = sm.pp[r & 1];
                 uint16_t* d = sm.pp[(r & 1) ^ 1];
-                for (unsigned j = tid; j <= (unsigned)CH; j += NT) d[j] = s[s[j]];
+                const unsigned j0 = tid * 16;
+                unsigned v[16];
+                unpack8(*reinterpret_cast<const uint4*>(&s[j0]), v);
+                unpack8(*reinterpret_cast<const uint4*>(&s[j0 + 8]), v + 8);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[k] = s[v[k]];
+                *reinterpret_cast<uint4*>(&d[j0]) = pack8(v);
+                *reinterpret_cast<uint4*>(&d[j0 + 8]) = pack8(v + 8);
                 __syncthreads();
             }
             if (tid == 0) {
-                const uint16_t* f32 = sm.pp[1];
+                const uint16_t* f8 = sm.pp[1];
                 unsigned nch = 1, t = lead;
                 sm.W[0] = (uint16_t)t;
                 while (nch < (unsigned)NCHAIN) {
-                    t = f32[t];
+                    t = f8[t];
                     if (t == SINK) break;
                     sm.W[nch++] = (uint16_t)t;
                 }
@@ -196,15 +262,15 @@ lz4_decode_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restric
                 const unsigned nch = sm.nchains;
                 if (tid < nch) {
                     unsigned t = sm.W[tid], cnt = 0;
-                    const unsigned base = tid * 32;
+                    const unsigned base = tid * HOP;
                     const bool last = (tid == nch - 1);
-                    for (int i = 0; i < 32; ++i) {
+                    for (int i = 0; i < HOP; ++i) {
                         const unsigned nx = sm.nxt1[t];
                         if (nx == NX_SLOW || nx == NX_BAD) { sm.term_kind = nx; sm.term_idx = t; break; }
                         sm.tok[base + i] = (uint16_t)t; ++cnt;
                         if (nx >= (unsigned)CH) { sm.term_kind = nx; sm.term_idx = t; break; }
                         t = nx;
-                        if (i == 31 && last) { sm.term_kind = NX_CONT; sm.term_idx = t; }
+                        if (i == HOP - 1 && last) { sm.term_kind = NX_CONT; sm.term_idx = t; }
                     }
                     if (last) sm.K = base + cnt;
                 }
@@ -261,7 +327,7 @@ lz4_decode_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restric
                 for (int q = 0; q < 2; ++q) {
                     const unsigned i = 2 * tid + q;
                     len[q] = 0;
-                    if (i < K) { tk[q] = parse_token(sm.chunk, sm.tok[i], lim, avail); len[q] = tk[q].L + tk[q].M; }
+                    if (i < K) { tk[q] = parse_token(chunk, sm.tok[i], lim, avail); len[q] = tk[q].L + tk[q].M; }
                 }
                 unsigned tot;
                 const unsigned ex = block_excl_scan_add<NT>(len[0] + len[1], sm.scan, &tot);
@@ -288,98 +354,107 @@ lz4_decode_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restric
                 else if (term_kind == NX_EXIT) next_cpos = cpos + (sm.next_idx_last - lead);
                 else next_cpos = cpos + (term_idx - lead);           // NX_CONT / NX_SLOW / NX_BAD: resume at that token
             }
+            // the next window is known: start its TMA now, it lands while this batch's output is materialised
+            if (next_cpos < n) {
+                if (tid == 0) issue_window(sm, buf ^ 1, in, n, next_cpos);
+                loaded = true;
+            }
 
             // ---------------- P4-P6: materialise the batch's output, one tile at a time -----------------------------
-            for (unsigned t0 = opos; t0 < batch_end; t0 += TILE) {
-                const unsigned tlen = (batch_end - t0) < (unsigned)TILE ? (batch_end - t0) : (unsigned)TILE;
-                const unsigned tlen8 = (tlen + 7u) & ~7u;
-                {   // zero the label array
-                    uint32_t* e32 = reinterpret_cast<uint32_t*>(ent);
-                    for (unsigned i = tid; i < tlen8 / 2; i += NT) e32[i] = 0;
+            // Entry i of a tile corresponds to global address (out + tbase + i); tbase is chosen so that entry 0 is
+            // 16-byte aligned in HBM, so full vectors leave the SM as 16-byte stores.
+            for (unsigned t0 = opos; t0 < batch_end;) {
+                const unsigned h = (unsigned)((uintptr_t)(out + t0) & 15);
+                const unsigned room = (unsigned)TILE - h;
+                const unsigned tlen = (batch_end - t0) < room ? (batch_end - t0) : room;
+                const unsigned t1 = t0 + tlen;
+                const unsigned tend = h + tlen;                          // entries [h, tend) are live
+                const unsigned tend8 = (tend + 7u) & ~7u;
+                const unsigned tbase = t0 - h;                           // may wrap below zero; only used as pos - tbase, pos >= t0
+                // first / one-past-last sequence overlapping [t0, t1)
+                unsigned ja, jb;
+                {
+                    unsigned lo = 0, hi = K;                              // ja = (#seq with out_start <= t0) - 1
+                    while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (sm.seq[mid].out_start <= t0) lo = mid + 1; else hi = mid; }
+                    ja = lo - 1;
+                    lo = ja; hi = K;                                      // jb = #seq with out_start < t1
+                    while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (sm.seq[mid].out_start < t1) lo = mid + 1; else hi = mid; }
+                    jb = lo;
                 }
-                __syncthreads();
-                for (unsigned i = tid; i < K; i += NT) {
-                    const unsigned s = sm.seq[i].out_start;
-                    if (s >= t0 && s - t0 < tlen) ent[s - t0] = (uint16_t)(i + 1);
-                }
-                __syncthreads();
-                {   // per-warp inclusive max-scan: every byte learns (index+1) of the sequence covering it
-                    constexpr unsigned WSPAN = TILE / (NT / 32);
-                    const unsigned wbase = warp * WSPAN;
-                    if (wbase < tlen) {
-                        // carry-in = number of sequences that start before this warp's range
-                        const unsigned x = t0 + wbase;
-                        unsigned lo = 0, hi = K;
-                        while (lo < hi) { unsigned mid = (lo + hi) >> 1; if (sm.seq[mid].out_start < x) lo = mid + 1; else hi = mid; }
-                        unsigned carry = lo;
-                        for (unsigned it = 0; it < WSPAN / 256; ++it) {
-                            const unsigned base = wbase + it * 256 + lane * 8;
-                            if (wbase + it * 256 >= tlen8) break;
-                            unsigned v[8];
-                            if (base < tlen8) {
-                                const uint4 q = *reinterpret_cast<const uint4*>(&ent[base]);
-                                v[0] = q.x & 0xffff; v[1] = q.x >> 16; v[2] = q.y & 0xffff; v[3] = q.y >> 16;
-                                v[4] = q.z & 0xffff; v[5] = q.z >> 16; v[6] = q.w & 0xffff; v[7] = q.w >> 16;
-                            } else {
-#pragma unroll
-                                for (int k = 0; k < 8; ++k) v[k] = 0;
-                            }
-#pragma unroll
-                            for (int k = 1; k < 8; ++k) v[k] = max(v[k], v[k - 1]);
-                            const unsigned incl = warp_incl_scan_max(v[7]);
-                            unsigned pre = __shfl_up_sync(RCZ_FULL, incl, 1);
-                            pre = lane == 0 ? carry : max(pre, carry);
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) v[k] = max(v[k], pre);
-                            if (base < tlen8) {
-                                uint4 q;
-                                q.x = v[0] | (v[1] << 16); q.y = v[2] | (v[3] << 16);
-                                q.z = v[4] | (v[5] << 16); q.w = v[6] | (v[7] << 16);
-                                *reinterpret_cast<uint4*>(&ent[base]) = q;
-                            }
-                            carry = max(carry, __shfl_sync(RCZ_FULL, incl, 31));
+                if (tid < 16) { if (tid < h) ent[tid] = 0; if (tend + tid < tend8 + 8) ent[tend + tid] = 0; }   // dead head / tail entries
+                // ---- P4: one warp per sequence: literal bytes, bytes gathered from final output, or in-tile pointers
+                int anyptr = 0;
+                for (unsigned j = ja + warp; j < jb; j += NT / 32) {
+                    const SeqEnt s = sm.seq[j];
+                    const unsigned nstart = (j + 1 < K) ? sm.seq[j + 1].out_start : batch_end;
+                    const unsigned ms = s.out_start + s.L;               // match part starts here
+                    {   // literal run (lz4.rs:75-85)
+                        const unsigned lo = s.out_start > t0 ? s.out_start : t0, hi = ms < t1 ? ms : t1;
+#pragma unroll 1
+                        for (unsigned pos = lo + lane; pos < hi; pos += 32) {
+                            const unsigned la = s.lit_abs + (pos - s.out_start);
+                            const unsigned wi = (la - cpos) + lead;
+                            ent[pos - tbase] = wi < lim ? (uint16_t)chunk[wi] : (uint16_t)__ldg(in + la);
                         }
                     }
-                }
-                __syncthreads();
-                int anyptr = 0;
-                for (unsigned i = tid; i < tlen; i += NT) {
-                    const unsigned si = (unsigned)ent[i] - 1u;
-                    const SeqEnt s = sm.seq[si];
-                    const unsigned pos = t0 + i, rel = pos - s.out_start;
-                    unsigned e;
-                    if (rel < s.L) {                                         // literal byte (lz4.rs:75-85)
-                        const unsigned la = s.lit_abs + rel;
-                        const unsigned wi = (la - cpos) + lead;
-                        e = wi < lim ? (unsigned)sm.chunk[wi] : (unsigned)__ldg(in + la);
-                    } else {                                                 // match byte (lz4.rs:96-107, cp lz4.rs:131-140)
-                        const unsigned k = rel - s.L, off = s.off;
-                        const unsigned srcp = k < off ? pos - off : (s.out_start + s.L - off) + (k % off);
-                        if (srcp < t0) e = out[srcp];                        // already final in HBM/L2
-                        else { e = 0x8000u | (srcp - t0); anyptr = 1; }
+                    {   // match (lz4.rs:96-107, cp lz4.rs:131-140): byte k equals byte (k mod off) of the `off` bytes before it
+                        const unsigned lo = ms > t0 ? ms : t0, hi = nstart < t1 ? nstart : t1;
+                        const unsigned off = s.off;
+#pragma unroll 1
+                        for (unsigned pos = lo + lane; pos < hi; pos += 32) {
+                            const unsigned k = pos - ms;
+                            const unsigned srcp = k < off ? pos - off : (ms - off) + (k % off);
+                            unsigned e;
+                            if (srcp < t0) e = out[srcp];                // already final in HBM/L2
+                            else { e = 0x8000u | (srcp - tbase); anyptr = 1; }
+                            ent[pos - tbase] = (uint16_t)e;
+                        }
                     }
-                    ent[i] = (uint16_t)e;
                 }
                 int pend = __syncthreads_or(anyptr);
-                while (pend) {                                               // P5: pointer doubling inside the tile
+                while (pend) {                                           // P5: pointer doubling inside the tile
                     int p2 = 0;
-                    for (unsigned i = tid; i < tlen; i += NT) {
-                        const unsigned e = vent[i];
-                        if (e & 0x8000u) {
-                            const unsigned f = vent[e & 0x7fffu];
-                            vent[i] = (uint16_t)f;
-                            p2 |= (int)(f >> 15);
-                        }
+                    for (unsigned i8 = tid * 8; i8 < tend8; i8 += NT * 8) {
+                        const uint4 q = lds128_volatile(&ent[i8]);
+                        if (((q.x | q.y | q.z | q.w) & 0x80008000u) == 0) continue;
+                        unsigned e[8], f[8];
+                        unpack8(q, e);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) f[u] = (e[u] & 0x8000u) ? (unsigned)vent[e[u] & 0x7fffu] : e[u];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) p2 |= (int)(f[u] >> 15);
+                        sts128_volatile(&ent[i8], pack8(f));
                     }
                     pend = __syncthreads_or(p2);
                 }
-                for (unsigned i = tid; i < tlen; i += NT) out[t0 + i] = (uint8_t)ent[i];   // P6
+                // ---- P6: 16 entries -> one aligned 16-byte store (byte stores only for the ragged head / tail vector)
+                for (unsigned vi = tid; vi * 16 < tend; vi += NT) {
+                    const unsigned i = vi * 16;
+                    unsigned v[16];
+                    unpack8(*reinterpret_cast<const uint4*>(&ent[i]), v);
+                    unpack8(*reinterpret_cast<const uint4*>(&ent[i + 8]), v + 8);
+                    uint8_t* dst = out + t0 - h + i;
+                    if (i >= h && i + 16 <= tend) {
+                        uint4 q;
+                        q.x = (v[0] & 255) | ((v[1] & 255) << 8) | ((v[2] & 255) << 16) | (v[3] << 24);
+                        q.y = (v[4] & 255) | ((v[5] & 255) << 8) | ((v[6] & 255) << 16) | (v[7] << 24);
+                        q.z = (v[8] & 255) | ((v[9] & 255) << 8) | ((v[10] & 255) << 16) | (v[11] << 24);
+                        q.w = (v[12] & 255) | ((v[13] & 255) << 8) | ((v[14] & 255) << 16) | (v[15] << 24);
+                        *reinterpret_cast<uint4*>(dst) = q;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) if (i + k >= h && i + k < tend) dst[k] = (uint8_t)v[k];
+                    }
+                }
                 __syncthreads();
+                t0 += tlen;
             }
             opos = batch_end;
             cpos = next_cpos;
+            buf ^= 1;
         }
         __syncthreads();
+        if (loaded) { mbar_wait(&sm.bar[buf], phase[buf]); phase[buf] ^= 1; }   // drain a window issued before an error exit
         if (tid == 0) { out_len[b] = opos; status[b] = err; }
     }
 }

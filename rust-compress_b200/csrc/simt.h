@@ -33,6 +33,8 @@ __device__ inline void tma_load_1d(void* dst, const void* src, unsigned bytes, r
 __device__ inline void mbar_wait(rcz_mbar* b, unsigned parity) { while ((b->v & 1) == parity) emu::yield(); }
 __device__ inline void fence_proxy_async_smem() {}
 __device__ inline void prefetch_l2(const void*, unsigned) {}
+__device__ inline uint4 lds128_volatile(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ inline void sts128_volatile(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
 #else
 struct rcz_mbar { unsigned long long v; };
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -63,6 +65,15 @@ __device__ __forceinline__ void mbar_wait(rcz_mbar* b, unsigned phase) {
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// 16-byte shared-memory accesses that the compiler may neither cache nor reorder (racy-by-design pointer doubling)
+__device__ __forceinline__ uint4 lds128_volatile(const void* p) {
+    uint4 r;
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)) : "memory");
+    return r;
+}
+__device__ __forceinline__ void sts128_volatile(void* p, uint4 v) {
+    asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 #endif
 
