@@ -51,7 +51,7 @@ def build_emu(force=False):
     bdir = os.path.join(HERE, "build_emu")
     os.makedirs(bdir, exist_ok=True)
     flags = ["-O2", "-g", "-std=c++17", "-fPIC", "-DRCZ_EMU", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function",
-             "-fno-omit-frame-pointer"]
+             "-fno-omit-frame-pointer", "-fno-strict-aliasing"]
     procs = []
     for s in _sources() + [os.path.join(CSRC, "emu_rt.cpp")]:
         o = os.path.join(bdir, os.path.basename(s) + ".o")

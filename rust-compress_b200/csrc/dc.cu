@@ -1,0 +1,334 @@
+// dc.cu — K9/K10: distance coding of BWT blocks.
+//
+// Encode replaces /root/reference/src/bwt/dc.rs:110-149 `encode` + :88-104 `EncodeIterator` (+ MTF::encode,
+// bwt/mtf.rs:63-79).  The reference walks the block left to right with a move-to-front list; what it emits is,
+// for every run end p (p == n-1 or in[p+1] != in[p]) in position order,
+//        d[p] = q - p - r - 1,   q = next position > p holding in[p] (n if none),
+//                                r = number of distinct symbols in (p, q)   (== the MTF rank, dc.rs:131-136,
+//                                                                             and the final sweep dc.rs:139-144)
+// and init[c] = first position of c (n when absent).  That form has no carried list, so it is computed right to
+// left from a per-symbol "next occurrence" table nxt[256]: r = #{s != in[p] : nxt[s] < q}.  Blocks are cut into
+// 16 KiB segments (one warp each); a first pass records the first occurrence of every symbol per segment and the
+// number of run ends, a per-block suffix-min / prefix-sum turns those into each segment's starting nxt[] table
+// and output offset, and the last pass emits the distances.
+//
+// Decode replaces dc.rs:162-233 `decode` fed by `decode_simple`'s closure (dc.rs:236-252).  It is inherently
+// serial in the run index (every distance re-sorts the symbol list), so one warp decodes one block: ranks 0..31
+// of the (symbol, next position) list live in registers (one per lane; the slide of dc.rs:215-218 is a ballot +
+// one shuffle), ranks >= 32 in shared memory; run filling is a warp-wide store.
+#include "rcz_internal.h"
+#include <algorithm>
+
+namespace dck {
+
+constexpr unsigned SEG = 16384;          // bytes per encode segment
+constexpr int NT = 128;                  // 4 warps per CTA
+constexpr int WPB = NT / 32;
+
+struct Blk {
+    unsigned long long in_off;           // bytes
+    unsigned long long out_off, out_cap; // u32 elements
+    unsigned n, seg0, nseg, skip;
+};
+
+// ---------------------------------------------------------------------------------------------- encode, pass 1
+// first[seg][c] = first position of c inside the segment (n if none); nruns[seg] = run ends inside the segment
+__global__ void __launch_bounds__(NT)
+dc_first_kernel(const uint8_t* __restrict__ in_base, const Blk* __restrict__ blks, const unsigned* __restrict__ seg2blk,
+                unsigned nsegs, unsigned* __restrict__ first, unsigned* __restrict__ nruns) {
+    __shared__ unsigned sfirst[WPB][256];
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned seg = blockIdx.x * WPB + w;
+    if (seg >= nsegs) return;
+    const Blk bk = blks[seg2blk[seg]];
+    const uint8_t* in = in_base + bk.in_off;
+    const unsigned n = bk.n, lo = (seg - bk.seg0) * SEG, hi = min(n, lo + SEG);
+    for (unsigned i = lane; i < 256; i += 32) sfirst[w][i] = n;
+    __syncwarp();
+    unsigned runs = 0;
+    for (unsigned p = lo + lane; p < hi; p += 32) {
+        const unsigned c = in[p];
+        if (p == lo || in[p - 1] != c) atomicMin(&sfirst[w][c], p);          // only run heads can be first occurrences
+        if (p + 1 == n || in[p + 1] != c) ++runs;
+    }
+    runs = warp_reduce_add(runs);
+    __syncwarp();
+    for (unsigned i = lane; i < 256; i += 32) first[(size_t)seg * 256 + i] = sfirst[w][i];
+    if (lane == 0) nruns[seg] = runs;
+}
+
+// ---------------------------------------------------------------------------------------------- encode, pass 2
+// per block: first[seg][c] <- first occurrence of c at or after the END of seg (suffix min over later segments),
+// nruns[seg] <- number of run ends before seg; writes init[256] (dc.rs:153-159) and out_len.
+__global__ void __launch_bounds__(256)
+dc_scan_kernel(const Blk* __restrict__ blks, unsigned* __restrict__ first, unsigned* __restrict__ nruns, uint32_t* __restrict__ out_base,
+               uint64_t* __restrict__ out_len, int32_t* __restrict__ status, const int32_t* __restrict__ host_status) {
+    const unsigned b = blockIdx.x, c = threadIdx.x;
+    const Blk bk = blks[b];
+    if (bk.skip) { if (c == 0) { out_len[b] = 0; status[b] = host_status[b]; } return; }
+    unsigned run = bk.n;
+    for (unsigned s = bk.nseg; s-- > 0;) {
+        const size_t idx = (size_t)(bk.seg0 + s) * 256 + c;
+        const unsigned f = first[idx];
+        first[idx] = run;
+        run = min(run, f);
+    }
+    __shared__ unsigned total;
+    if (c == 0) {
+        unsigned acc = 0;
+        for (unsigned s = 0; s < bk.nseg; ++s) { const unsigned r = nruns[bk.seg0 + s]; nruns[bk.seg0 + s] = acc; acc += r; }
+        total = acc;
+    }
+    __syncthreads();
+    const bool fits = 256ull + total <= bk.out_cap;
+    if (fits) out_base[bk.out_off + c] = run;                                // init[c]: first position or n
+    if (c == 0) { out_len[b] = 256ull + total; status[b] = fits ? RCZ_OK : RCZ_E_OUTPUT_FULL; }
+}
+
+// ---------------------------------------------------------------------------------------------- encode, pass 3
+__global__ void __launch_bounds__(NT)
+dc_emit_kernel(const uint8_t* __restrict__ in_base, const Blk* __restrict__ blks, const unsigned* __restrict__ seg2blk, unsigned nsegs,
+               const unsigned* __restrict__ first, const unsigned* __restrict__ nruns, uint32_t* __restrict__ out_base,
+               const int32_t* __restrict__ status) {
+    __align__(16) __shared__ unsigned snxt[WPB][256];
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned seg = blockIdx.x * WPB + w;
+    if (seg >= nsegs) return;
+    const unsigned bi = seg2blk[seg];
+    const Blk bk = blks[bi];
+    if (bk.skip || status[bi] != RCZ_OK) return;
+    const uint8_t* in = in_base + bk.in_off;
+    const unsigned n = bk.n, lo = (seg - bk.seg0) * SEG, hi = min(n, lo + SEG);
+    unsigned* nxt = snxt[w];
+    for (unsigned i = lane; i < 256; i += 32) nxt[i] = first[(size_t)seg * 256 + i];
+    __syncwarp();
+    // distances of this segment's run ends go to dst[0 .. runs_here); we walk right to left, so count first
+    uint32_t* dst = out_base + bk.out_off + 256 + nruns[seg];
+    unsigned runs_here = 0;
+    for (unsigned p = lo + lane; p < hi; p += 32) runs_here += (p + 1 == n || in[p + 1] != in[p]) ? 1u : 0u;
+    runs_here = warp_reduce_add(runs_here);
+    unsigned idx = runs_here;                                                 // index after the next run end to emit
+    for (unsigned base = (hi - 1) & ~31u;; base -= 32) {                      // 32 positions per step, high to low
+        const unsigned p = base + lane;
+        const bool valid = p >= lo && p < hi;
+        const unsigned c = valid ? (unsigned)in[p] : 0u;
+        const unsigned cn = (valid && p + 1 < n) ? (unsigned)in[p + 1] : 256u;
+        unsigned m = __ballot_sync(RCZ_FULL, valid && c != cn);
+        while (m) {
+            const int l = 31 - __clz((int)m);
+            m &= ~(1u << l);
+            const unsigned pp = base + (unsigned)l;
+            const unsigned cc = __shfl_sync(RCZ_FULL, c, l), cnn = __shfl_sync(RCZ_FULL, cn, l);
+            if (lane == 0 && cnn < 256u) nxt[cnn] = pp + 1;                   // the run to the right starts at pp+1
+            __syncwarp();
+            const unsigned q = nxt[cc];
+            const uint4 a = *reinterpret_cast<const uint4*>(&nxt[lane * 8]);
+            const uint4 b = *reinterpret_cast<const uint4*>(&nxt[lane * 8 + 4]);
+            unsigned r = (a.x < q) + (a.y < q) + (a.z < q) + (a.w < q) + (b.x < q) + (b.y < q) + (b.z < q) + (b.w < q);
+            r = __reduce_add_sync(RCZ_FULL, r);                               // nxt[cc] == q is never < q
+            --idx;
+            if (lane == 0) dst[idx] = q - pp - r - 1;                         // dc.rs:136 / :143
+            __syncwarp();
+        }
+        if (base <= lo) break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- decode
+struct DecSmem { unsigned long long tail[WPB][256]; };                        // ranks >= 32 of every warp's list
+
+__device__ __forceinline__ unsigned long long ent_pack(unsigned long long next, unsigned sym) { return (next << 8) | sym; }
+
+__global__ void __launch_bounds__(NT)
+dc_decode_kernel(const uint32_t* __restrict__ in_base, const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ in_len,
+                 uint8_t* __restrict__ out_base, const uint64_t* __restrict__ out_off, const uint64_t* __restrict__ n_arr,
+                 int32_t* __restrict__ status, unsigned nblocks) {
+    __shared__ DecSmem sm;
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned long long* tail = sm.tail[w];
+    for (unsigned b = blockIdx.x * WPB + w; b < nblocks; b += gridDim.x * WPB) {
+        const uint32_t* in = in_base + in_off[b];
+        const unsigned long long len = in_len[b], n = n_arr[b];
+        uint8_t* out = out_base + out_off[b];
+        if (len < 256 || n >= (1ull << 31)) { if (lane == 0) status[b] = len < 256 ? RCZ_E_UNEXPECTED_EOF : RCZ_E_ARG; continue; }
+        const uint32_t* dist = in + 256;
+        const unsigned long long ndist = len - 256;
+        // ---- dc.rs:169-179: present symbols ordered by first position (stable in the symbol value)
+        unsigned init[8]; unsigned rk[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { init[k] = in[lane * 8 + k]; rk[k] = 0; }
+        unsigned present = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) present += init[k] < n ? 1u : 0u;
+        const unsigned A = __reduce_add_sync(RCZ_FULL, present);
+        for (int src = 0; src < 32; ++src) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const unsigned v = __shfl_sync(RCZ_FULL, init[j], src);
+                const unsigned t = (unsigned)src * 8 + j;
+                if (v < n) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) rk[k] += (v < init[k] || (v == init[k] && t < lane * 8 + k)) ? 1u : 0u;
+                }
+            }
+        }
+        __syncwarp();
+        unsigned long long my = ~0ull;                                        // list entry of rank == lane
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (init[k] < n) tail[rk[k]] = ent_pack(init[k], lane * 8 + k);   // ranks are a permutation of 0..A-1
+        __syncwarp();
+        if (lane < A) my = tail[lane];
+        __syncwarp();
+        if (A <= 1) {                                                         // dc.rs:180-187
+            const unsigned sym = A ? (unsigned)(__shfl_sync(RCZ_FULL, my, 0) & 255u) : 0u;
+            for (unsigned long long i = lane; i < n; i += 32) out[i] = (uint8_t)sym;
+            if (lane == 0) status[b] = RCZ_OK;
+            continue;
+        }
+        // ---- dc.rs:199-229
+        unsigned long long i = 0, di = 0;
+        int err = 0;
+        unsigned dreg = 0; unsigned long long dbase = ~0ull;                  // 32 distances at a time
+        while (i < n) {
+            const unsigned long long e0 = __shfl_sync(RCZ_FULL, my, 0), e1 = __shfl_sync(RCZ_FULL, my, 1);
+            const unsigned sym = (unsigned)(e0 & 255u);
+            const unsigned long long stop = e1 >> 8;
+            if (stop > n) { err = RCZ_E_MALFORMED; break; }                   // output[i] index panic
+            for (unsigned long long k = i + lane; k < stop; k += 32) out[k] = (uint8_t)sym;
+            if (stop > i) i = stop;
+            if (di >= ndist) { err = RCZ_E_UNEXPECTED_EOF; break; }           // dc.rs:245-246
+            if ((di & ~31ull) != dbase) { dbase = di & ~31ull; dreg = dbase + lane < ndist ? dist[dbase + lane] : 0u; }
+            const unsigned long long future = stop + __shfl_sync(RCZ_FULL, dreg, (int)(di & 31u));
+            ++di;
+            if (future > n) { err = RCZ_E_MALFORMED; break; }                 // dc.rs:213 assert!
+            // rank = 1 + #{leading r in [1, A) : future + r > next(L[r])}  (dc.rs:215-218)
+            // (the reference stops at the first rank that fails the test: count LEADING hits, not all hits)
+            const unsigned bal = __ballot_sync(RCZ_FULL, lane >= 1 && lane < A && future + lane > (my >> 8)) >> 1;
+            unsigned rank = 1 + ((unsigned)__ffs((int)~bal) - 1u);            // bal has at most 31 bits set
+            if (rank == 32 && A > 32) {
+                for (unsigned r0 = 32; r0 < A; r0 += 32) {
+                    const unsigned r = r0 + lane;
+                    const unsigned bb = __ballot_sync(RCZ_FULL, r < A && future + r > (tail[r] >> 8));
+                    if (bb == RCZ_FULL) { rank += 32; continue; }
+                    rank += (unsigned)__ffs((int)~bb) - 1u;
+                    break;
+                }
+            }
+            const unsigned long long fresh = ent_pack(future + rank - 1, sym);
+            const unsigned long long up = __shfl_down_sync(RCZ_FULL, my, 1);
+            if (rank <= 32) {
+                if (lane + 1 < rank) my = up; else if (lane + 1 == rank) my = fresh;
+            } else {
+                const unsigned long long v32 = tail[32];
+                my = lane < 31 ? up : v32;
+                __syncwarp();                                                 // tail[32] is read before anyone rewrites it
+                for (unsigned r0 = 32; r0 + 1 < rank; r0 += 32) {             // tail[r] = tail[r+1] for r in [32, rank-1)
+                    const unsigned r = r0 + lane;
+                    const unsigned long long t = (r + 1 < rank) ? tail[r + 1] : 0ull;
+                    __syncwarp();
+                    if (r + 1 < rank) tail[r] = t;
+                    __syncwarp();
+                }
+                if (lane == 0) tail[rank - 1] = fresh;
+                __syncwarp();
+            }
+        }
+        if (!err) {                                                           // dc.rs:230-231 assert_eq!
+            bool bad = lane < A && lane < 32 && ((my >> 8) < n || (my >> 8) >= n + A);
+            for (unsigned r = 32 + lane; r < A; r += 32) bad |= (tail[r] >> 8) < n || (tail[r] >> 8) >= n + A;
+            if (__any_sync(RCZ_FULL, bad) || i != n) err = RCZ_E_MALFORMED;
+        }
+        __syncwarp();
+        if (lane == 0) status[b] = err;
+    }
+}
+
+}  // namespace dck
+
+extern "C" int rcz_dc_encode_blocks(rcz_ctx* c, const void* in_base, const uint64_t* in_off, const uint64_t* n_arr, uint32_t* out_base,
+                                    const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len, int32_t* status, size_t nblocks,
+                                    int mem_kind) {
+    using namespace dck;
+    if (!c || rcz_bad_kind(mem_kind)) return RCZ_E_ARG;
+    if (nblocks == 0) return RCZ_OK;
+    if (!in_base || !in_off || !n_arr || !out_base || !out_off || !out_cap || !out_len || !status || nblocks > 0x3fffffu) return RCZ_E_ARG;
+    rt_set_device(c->device);
+    std::vector<Blk> blks(nblocks);
+    std::vector<int32_t> hstatus(nblocks, 0);
+    std::vector<unsigned> seg2blk;
+    for (size_t i = 0; i < nblocks; ++i) {
+        Blk& b = blks[i];
+        memset(&b, 0, sizeof b);
+        b.in_off = in_off[i]; b.out_off = out_off[i]; b.out_cap = out_cap[i];
+        b.seg0 = (unsigned)seg2blk.size();
+        if (n_arr[i] >= (1ull << 31)) { b.skip = 1; hstatus[i] = RCZ_E_ARG; continue; }
+        b.n = (unsigned)n_arr[i];
+        b.nseg = (b.n + SEG - 1) / SEG;
+        for (unsigned s = 0; s < b.nseg; ++s) seg2blk.push_back((unsigned)i);
+        if (seg2blk.size() > 0x3fffffffu) return RCZ_E_ARG;
+    }
+    const unsigned nsegs = (unsigned)seg2blk.size();
+    DescStager ds(c, mem_kind, nblocks);
+    const size_t i_blk = ds.add_in(blks.data(), nblocks * sizeof(Blk));
+    const size_t i_s2b = ds.add_in(seg2blk.data(), (size_t)nsegs * 4);
+    const size_t i_hst = ds.add_in(hstatus.data(), nblocks * 4);
+    const size_t o_len = ds.add_out(out_len, nblocks * 8);
+    const size_t o_st = ds.add_out(status, nblocks * 4);
+    int st = ds.upload(); if (st) return st;
+    const uint8_t* din = (const uint8_t*)in_base; uint8_t* dout = (uint8_t*)out_base;
+    if (mem_kind == RCZ_MEM_HOST) {
+        st = stage_span_in(c, WS_IN, in_base, in_off, n_arr, nblocks, 1, &din); if (st) return st;
+        st = stage_span_out(c, WS_OUT, out_off, out_cap, nblocks, 4, &dout); if (st) return st;
+    }
+    void* wf;
+    const size_t sz_first = ((size_t)nsegs * 256 * 4 + 255) & ~(size_t)255;
+    st = ctx_ws(c, WS_A, sz_first + (size_t)nsegs * 4 + 256, &wf); if (st) return st;
+    unsigned* first = (unsigned*)wf;
+    unsigned* nruns = (unsigned*)((uint8_t*)wf + sz_first);
+    const Blk* dblk = ds.in_ptr<Blk>(i_blk);
+    const unsigned* ds2b = ds.in_ptr<unsigned>(i_s2b);
+    st = ctx_timer_begin(c); if (st) return st;
+    const unsigned sgrid = (nsegs + WPB - 1) / WPB;
+    if (nsegs) RCZ_KLAUNCH(c, dc_first_kernel, sgrid, NT, 0, din, dblk, ds2b, nsegs, first, nruns);
+    RCZ_KLAUNCH(c, dc_scan_kernel, (unsigned)nblocks, 256, 0, dblk, first, nruns, (uint32_t*)dout, ds.out_ptr<uint64_t>(o_len), ds.out_ptr<int32_t>(o_st),
+                ds.in_ptr<int32_t>(i_hst));
+    if (nsegs) RCZ_KLAUNCH(c, dc_emit_kernel, sgrid, NT, 0, din, dblk, ds2b, nsegs, first, nruns, (uint32_t*)dout, ds.out_ptr<int32_t>(o_st));
+    st = ctx_timer_end(c); if (st) return st;
+    st = ds.download(); if (st) return st;
+    if (mem_kind == RCZ_MEM_HOST) {
+        std::vector<uint64_t> clipped(nblocks);
+        for (size_t i = 0; i < nblocks; ++i) clipped[i] = status[i] == RCZ_OK ? out_len[i] : 0;
+        st = unstage_span_out(c, out_base, dout, out_off, clipped.data(), nblocks, 4); if (st) return st;
+    }
+    return RCZ_OK;
+}
+
+extern "C" int rcz_dc_decode_blocks(rcz_ctx* c, const uint32_t* in_base, const uint64_t* in_off, const uint64_t* in_len, void* out_base,
+                                    const uint64_t* out_off, const uint64_t* n_arr, int32_t* status, size_t nblocks, int mem_kind) {
+    if (!c || rcz_bad_kind(mem_kind)) return RCZ_E_ARG;
+    if (nblocks == 0) return RCZ_OK;
+    if (!in_base || !in_off || !in_len || !out_base || !out_off || !n_arr || !status || nblocks > 0x7fffffffu) return RCZ_E_ARG;
+    rt_set_device(c->device);
+    DescStager ds(c, mem_kind, nblocks);
+    ds.add_in(in_off, nblocks * 8); ds.add_in(in_len, nblocks * 8); ds.add_in(out_off, nblocks * 8); ds.add_in(n_arr, nblocks * 8);
+    ds.add_out(status, nblocks * 4);
+    int st = ds.upload(); if (st) return st;
+    const uint8_t* din = (const uint8_t*)in_base; uint8_t* dout = (uint8_t*)out_base;
+    if (mem_kind == RCZ_MEM_HOST) {
+        st = stage_span_in(c, WS_IN, in_base, in_off, in_len, nblocks, 4, &din); if (st) return st;
+        st = stage_span_out(c, WS_OUT, out_off, n_arr, nblocks, 1, &dout); if (st) return st;
+    }
+    const unsigned grid = (unsigned)std::min<size_t>((nblocks + dck::WPB - 1) / dck::WPB, (size_t)c->sm_count * 16);
+    st = ctx_timer_begin(c); if (st) return st;
+    RCZ_KLAUNCH(c, dck::dc_decode_kernel, grid, dck::NT, 0, (const uint32_t*)din, ds.in_ptr<uint64_t>(0), ds.in_ptr<uint64_t>(1), dout,
+                ds.in_ptr<uint64_t>(2), ds.in_ptr<uint64_t>(3), ds.out_ptr<int32_t>(0), (unsigned)nblocks);
+    st = ctx_timer_end(c); if (st) return st;
+    st = ds.download(); if (st) return st;
+    if (mem_kind == RCZ_MEM_HOST) {
+        std::vector<uint64_t> lens(nblocks);
+        for (size_t i = 0; i < nblocks; ++i) lens[i] = n_arr[i] < (1ull << 31) ? n_arr[i] : 0;
+        st = unstage_span_out(c, out_base, dout, out_off, lens.data(), nblocks, 1); if (st) return st;
+    }
+    return RCZ_OK;
+}

@@ -1,0 +1,124 @@
+"""Distance-coding kernels (csrc/dc.cu) against the oracle (bwt/dc.rs:110-233): init[256] + distances bit-exact on
+encode, bytes and status on decode.  SURVEY Appendix C vectors included (the reference pins DC by roundtrip only)."""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+TXT = golden("ref_test.txt")
+
+
+def _layout(sizes, gap=3):
+    off, cur = [], 5
+    for s in sizes:
+        off.append(cur)
+        cur += s + gap
+    return np.array(off, dtype=np.uint64), cur + 64
+
+
+def _encode(ctx, blocks, device=False, cap_slack=0):
+    in_off, total = _layout([len(b) for b in blocks])
+    inb = np.full(total, 0xAA, dtype=np.uint8)
+    for o, b in zip(in_off, blocks):
+        inb[int(o): int(o) + len(b)] = np.frombuffer(b, dtype=np.uint8)
+    caps = [256 + len(b) + cap_slack for b in blocks]
+    out_off, ototal = _layout(caps)
+    n = np.array([len(b) for b in blocks], dtype=np.uint64)
+    if device:
+        import torch
+        d_out = torch.zeros(ototal, dtype=torch.int32, device="cuda")
+        out_len, status = ctx.dc_encode_blocks(torch.from_numpy(inb).cuda(), in_off, n, d_out, out_off, np.array(caps, dtype=np.uint64))
+        outb = d_out.cpu().numpy().view(np.uint32)
+    else:
+        outb = np.zeros(ototal, dtype=np.uint32)
+        out_len, status = ctx.dc_encode_blocks(inb, in_off, n, outb, out_off, np.array(caps, dtype=np.uint64))
+    return [(int(s), outb[int(o): int(o) + int(l)].copy()) for s, o, l in zip(status, out_off, out_len)]
+
+
+def _decode(ctx, streams, ns, device=False):
+    in_off, total = _layout([len(s) for s in streams])
+    inb = np.zeros(total, dtype=np.uint32)
+    for o, s in zip(in_off, streams):
+        inb[int(o): int(o) + len(s)] = s
+    out_off, ototal = _layout(ns)
+    in_len = np.array([len(s) for s in streams], dtype=np.uint64)
+    n = np.array(ns, dtype=np.uint64)
+    if device:
+        import torch
+        d_out = torch.zeros(ototal, dtype=torch.uint8, device="cuda")
+        status = ctx.dc_decode_blocks(torch.from_numpy(inb.view(np.int32)).cuda(), in_off, in_len, d_out, out_off, n)
+        outb = d_out.cpu().numpy()
+    else:
+        outb = np.zeros(ototal, dtype=np.uint8)
+        status = ctx.dc_decode_blocks(inb, in_off, in_len, outb, out_off, n)
+    return [(int(s), outb[int(o): int(o) + int(k)].tobytes()) for s, o, k in zip(status, out_off, ns)]
+
+
+def _blocks(oracle, gen, big):
+    def bw(d):
+        return oracle.bwt_encode(d)[1]
+    return [b"teeesst_dc", b"abracadabra", b"", b"a", b"aaaaaaa", b"ab", TXT, b"../data/test.txt", bw(TXT), bytes(range(256)) * 3,
+            bytes(range(255, -1, -1)) + bytes(range(256)), bw(gen.one("hextext", 4, big)), gen.one("random", 5, big // 2),
+            gen.one("runs", 6, big), bytes(40000), bw(gen.one("lzsyn", 7, big // 2))]
+
+
+def _check(ctx, oracle, gen, big, device=False):
+    blocks = _blocks(oracle, gen, big)
+    got = _encode(ctx, blocks, device=device)
+    streams = []
+    for i, b in enumerate(blocks):
+        st, init, dist = oracle.dc_encode(b)
+        assert st == 0 and got[i][0] == 0, i
+        ref = np.concatenate([init, dist]).astype(np.uint32)
+        assert np.array_equal(got[i][1], ref), "dc encode block %d differs" % i
+        streams.append(ref)
+    dec = _decode(ctx, streams, [len(b) for b in blocks], device=device)
+    for i, b in enumerate(blocks):
+        assert dec[i] == (0, b), "dc decode block %d differs" % i
+    # error parity: truncated distance list (dc.rs:245-246), corrupted distances / init (asserts at dc.rs:213, :230)
+    rs = np.random.RandomState(3)
+    bad, ns = [], []
+    for src in (6, 8, 11):
+        s = streams[src]
+        bad.append(s[:-1].copy()); ns.append(len(blocks[src]))
+        bad.append(s[: 256 + (len(s) - 256) // 2].copy()); ns.append(len(blocks[src]))
+        for _ in range(4):
+            t = s.copy()
+            t[256 + rs.randint(0, len(t) - 256)] += np.uint32(rs.randint(1, 50))
+            bad.append(t); ns.append(len(blocks[src]))
+        t = s.copy()
+        t[rs.randint(0, 256)] = 3
+        bad.append(t); ns.append(len(blocks[src]))
+    bad.append(streams[0][:100].copy()); ns.append(10)
+    dec = _decode(ctx, bad, ns, device=device)
+    for i, (s, k) in enumerate(zip(bad, ns)):
+        if len(s) < 256:
+            assert dec[i][0] == oracle.E_UNEXPECTED_EOF
+            continue
+        ost, oout, used = oracle.dc_decode(k, s[:256], s[256:])
+        assert dec[i][0] == ost, (i, dec[i][0], ost)
+        if ost == 0:
+            assert dec[i][1] == oout
+    # output too small on encode
+    small = _encode(ctx, [TXT], device=device, cap_slack=-3000)
+    assert small[0][0] == oracle.E_OUTPUT_FULL
+
+
+def test_dc_emu(emu_ctx, oracle, gen):
+    _check(emu_ctx, oracle, gen, 70000)
+
+
+def test_dc_emu_appendix_c(emu_ctx):
+    got = _encode(emu_ctx, [b"teeesst_dc", b"abracadabra"])
+    init = got[0][1][:256]
+    assert [int(init[ord(c)]) for c in "tes_dc"] == [0, 1, 4, 7, 8, 9] and int(init[0]) == 10
+    assert got[0][1][256:].tolist() == [3, 1, 0, 0, 0, 0, 0]
+    init = got[1][1][:256]
+    assert [int(init[ord(c)]) for c in "abrcd"] == [0, 1, 2, 4, 6]
+    assert got[1][1][256:].tolist() == [0, 2, 2, 0, 2, 0, 1, 0, 0, 0, 0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("device", [True, False])
+def test_dc_gpu(gpu_ctx, oracle, gen, device):
+    _check(gpu_ctx, oracle, gen, 1 << 20, device=device)
