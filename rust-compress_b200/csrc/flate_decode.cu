@@ -1,0 +1,362 @@
+// flate_decode.cu — K6: raw-DEFLATE decode, one warp per independent stream.
+//
+// Replaces /root/reference/src/flate.rs: `Decoder::block` (:195-206), `statik` (:237-246), `fixed` (:343-395),
+// `dynamic` (:397-450), `codes` (:262-341) and the bit-serial `HuffmanTree::decode` (:129-146), driven to BFINAL
+// for every stream (what repeated `Read::read` calls deliver, :468-488).
+//
+// Shape on the GPU: DEFLATE blocks inside a stream are bit-aligned and share a 32 KiB history, so the parallel
+// unit is the stream (BASELINE config 4: 131,072 of them).  All 32 lanes of a warp track the same bit-reader
+// state; canonical codes are decoded through per-warp look-up tables in shared memory (10 bits literal/length,
+// 9 bits distance) built cooperatively from the code lengths — results identical to the reference's one-bit-
+// per-iteration canonical decode, including its acceptance of incomplete codes (:92-103), rejection of
+// over-subscribed ones, and `NotEnoughBits` after 15 unmatched bits (:145); longer or unmatched codes take the
+// bit-serial path over the same count[]/symbol[] arrays.  Literals are queued 32 at a time and leave as one
+// warp-wide store; LZ77 copies are warp-wide, with the overlap rule of :325-334 folded as
+// byte j <- byte (j mod dist) of the `dist` bytes before the match.
+#include "rcz_internal.h"
+#include <algorithm>
+
+namespace flk {
+
+constexpr int NT = 128, WPB = NT / 32;
+constexpr int LB = 10, DB = 9;                       // primary LUT bits
+constexpr int MAXBITS = 15, MAXLCODES = 286, MAXDCODES = 30, MAXCODES = 316;   // flate.rs:36-39
+constexpr unsigned HISTORY = 32 * 1024;              // flate.rs:40
+
+struct Tree { unsigned count[16]; unsigned offs[16]; unsigned first[16]; unsigned run[16]; };
+struct WarpSmem {
+    __align__(16) uint16_t llut[1 << LB];
+    __align__(16) uint16_t dlut[1 << DB];
+    uint16_t lsym[288], dsym[32], csym[20];
+    Tree lt, dt, ct;
+    uint8_t lens[MAXCODES + 4];
+    uint8_t clen[20];
+};
+
+__constant__ uint16_t EXTRALENS[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t EXTRABITS[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t EXTRADIST[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097,
+                                       6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t EXTRADBITS[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__constant__ uint8_t CL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+// LSB-first bit reader (flate.rs:250-260).  The reference refills one byte at a time, so its byte position is
+// always ceil(bitpos / 8); `bitpos > endbits` here is its UnexpectedEof.
+struct Bits {
+    const uint8_t* in; const uint8_t* end;
+    const uint32_t* wp;
+    unsigned long long bb; unsigned bc;
+    unsigned long long bitpos, endbits;
+    __device__ __forceinline__ unsigned word() { const unsigned w = ((const uint8_t*)wp < end) ? __ldg(wp) : 0u; ++wp; return w; }
+    __device__ __forceinline__ void seek(unsigned long long bytepos) {
+        const uint8_t* p = in + bytepos;
+        const unsigned mis = (unsigned)((uintptr_t)p & 3);
+        wp = reinterpret_cast<const uint32_t*>(p - mis);
+        bb = (unsigned long long)word() >> (8 * mis);
+        bc = 32 - 8 * mis;
+        bitpos = bytepos * 8;
+    }
+    __device__ __forceinline__ void init(const uint8_t* p, unsigned long long n) { in = p; end = p + n; endbits = n * 8; seek(0); }
+    __device__ __forceinline__ void refill() { if (bc <= 32) { bb |= (unsigned long long)word() << bc; bc += 32; } }   // bc >= 33 afterwards
+    __device__ __forceinline__ unsigned peek(unsigned k) const { return (unsigned)bb & ((1u << k) - 1u); }
+    __device__ __forceinline__ void consume(unsigned k) { bb >>= k; bc -= k; bitpos += k; }
+    __device__ __forceinline__ bool eof() const { return bitpos > endbits; }
+    // bits(cnt) with cnt <= 16; caller has refilled
+    __device__ __forceinline__ unsigned take(unsigned k) { const unsigned v = peek(k); consume(k); return v; }
+    __device__ __forceinline__ unsigned long long bytepos() const { return (bitpos + 7) >> 3; }
+};
+
+enum { F_OK = 0, F_EOF = 1, F_INVALID = 2, F_MALFORMED = 3, F_FULL = 4 };
+
+// flate.rs:83-120 HuffmanTree::construct, warp-cooperative.  lens[0..n) in shared memory.  Returns false when the
+// set is over-subscribed (:98-103).  lutbits == 0 builds only count[]/symbol[].
+__device__ bool build_tree(Tree& t, uint16_t* symtab, uint16_t* lut, int lutbits, const uint8_t* lens, unsigned n) {
+    const unsigned lane = threadIdx.x & 31;
+    __syncwarp();
+    if (lane < 16) t.count[lane] = 0;
+    if (lutbits) {
+        uint4* l4 = reinterpret_cast<uint4*>(lut);
+        for (unsigned i = lane; i < (2u << lutbits) / 16; i += 32) l4[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    for (unsigned s = lane; s < n; s += 32) atomicAdd(&t.count[lens[s]], 1u);
+    __syncwarp();
+    if (t.count[0] == n) { __syncwarp(); if (lane < 16) t.count[lane] = 0; __syncwarp(); return true; }   // :93 no codes: every decode fails
+    int left = 1; unsigned off = 0, first = 0;
+    bool over = false;
+    for (int len = 1; len <= MAXBITS; ++len) {
+        const unsigned cnt = t.count[len];
+        left = left * 2 - (int)cnt;
+        if (left < 0) over = true;
+        if (lane == 0) { t.offs[len] = off; t.run[len] = off; t.first[len] = first; }
+        off += cnt;
+        first = (first + cnt) << 1;
+    }
+    if (over) return false;
+    __syncwarp();
+    for (unsigned base = 0; base < n; base += 32) {
+        const unsigned s = base + lane;
+        const unsigned l = s < n ? (unsigned)lens[s] : 0u;
+        const bool act = l != 0;
+        const unsigned m = __match_any_sync(RCZ_FULL, act ? l : 100u + lane);
+        const unsigned r = __popc(m & ((1u << lane) - 1u));
+        const unsigned idx = act ? t.run[l] : 0u;
+        __syncwarp();
+        if (act && r == 0) t.run[l] = idx + __popc(m);
+        __syncwarp();
+        if (act) {
+            const unsigned pos = idx + r;
+            symtab[pos] = (uint16_t)s;
+            if ((int)l <= lutbits) {
+                const unsigned code = t.first[l] + (pos - t.offs[l]);
+                const unsigned rev = __brev(code) >> (32 - l);
+                const uint16_t e = (uint16_t)((s << 4) | l);
+                for (unsigned j = rev; j < (1u << lutbits); j += 1u << l) lut[j] = e;
+            }
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
+// flate.rs:129-146 on the next (up to) 15 bits; -1: no code within 15 bits
+__device__ __forceinline__ int slow_decode(const Tree& t, const uint16_t* symtab, unsigned bits15, unsigned& len_out) {
+    unsigned code = 0, first = 0, index = 0;
+    for (unsigned len = 1; len <= (unsigned)MAXBITS; ++len) {
+        code |= (bits15 >> (len - 1)) & 1u;
+        const unsigned cnt = t.count[len];
+        if (code - first < cnt) { len_out = len; return (int)symtab[index + (code - first)]; }
+        index += cnt; first += cnt; first <<= 1; code <<= 1;
+    }
+    return -1;
+}
+
+struct St {
+    Bits br;
+    uint8_t* out; unsigned long long cap, o;
+    int detail;
+    unsigned qn, qv;                  // literal queue: lane k holds literal k
+};
+
+__device__ __forceinline__ void flush_lits(St& s, unsigned lane) {
+    if (s.qn) { if (lane < s.qn) s.out[s.o - s.qn + lane] = (uint8_t)s.qv; s.qn = 0; }
+}
+
+// one Huffman symbol: LUT, else the bit-serial path.  Returns F_* ; symbol in `sym`.
+__device__ __forceinline__ int huff(St& s, const Tree& t, const uint16_t* symtab, const uint16_t* lut, int lutbits, unsigned& sym) {
+    s.br.refill();
+    const unsigned e = lut[s.br.peek(lutbits)];
+    unsigned l = e & 15u;
+    if (l) sym = e >> 4;
+    else {
+        const int v = slow_decode(t, symtab, s.br.peek(15), l);
+        if (v < 0) {
+            if (s.br.bitpos + 15 > s.br.endbits) return F_EOF;
+            s.detail = RCZ_FL_NOT_ENOUGH_BITS; return F_INVALID;
+        }
+        sym = (unsigned)v;
+    }
+    s.br.consume(l);
+    return s.br.eof() ? F_EOF : F_OK;
+}
+
+// flate.rs:262-341 codes
+__device__ int codes(St& s, WarpSmem& w, unsigned lane) {
+    for (;;) {
+        unsigned sym;
+        int r = huff(s, w.lt, w.lsym, w.llut, LB, sym);
+        if (r) return r;
+        if (sym < 256u) {
+            if (s.o >= s.cap) return F_FULL;
+            if (lane == s.qn) s.qv = sym;
+            ++s.qn; ++s.o;
+            if (s.qn == 32) flush_lits(s, lane);
+        } else if (sym == 256u) return F_OK;
+        else if (sym < 290u) {
+            const unsigned k = sym - 257u;
+            if (k > 29u) { s.detail = RCZ_FL_INVALID_HUFFMAN_CODE; return F_INVALID; }   // flate.rs:294 (off-by-one kept)
+            if (k == 29u) return F_MALFORMED;                                           // EXTRALENS[29] index panic
+            const unsigned eb = EXTRABITS[k];
+            unsigned len = EXTRALENS[k] + s.br.take(eb);                                // bc >= 33 - 15 after the code: enough for 5 bits
+            if (s.br.eof()) return F_EOF;
+            unsigned ds;
+            r = huff(s, w.dt, w.dsym, w.dlut, DB, ds);
+            if (r) return r;
+            if (ds >= 30u) return F_MALFORMED;                                          // EXTRADIST index panic
+            const unsigned dbits = EXTRADBITS[ds];
+            const unsigned d = EXTRADIST[ds] + s.br.take(dbits);                        // bc >= 18 after the code: enough for 13 bits
+            if (s.br.eof()) return F_EOF;
+            const unsigned long long hist = s.o < HISTORY ? s.o : HISTORY;              // flate.rs:314
+            if (d > hist) { s.detail = RCZ_FL_INVALID_HUFFMAN_CODE; return F_INVALID; }
+            if (len > s.cap - s.o) return F_FULL;
+            flush_lits(s, lane);
+            __syncwarp();
+            const uint8_t* src = s.out + s.o - d;
+            uint8_t* dst = s.out + s.o;
+            for (unsigned j = lane; j < len; j += 32) dst[j] = src[j < d ? j : j % d];   // flate.rs:325-334
+            __syncwarp();
+            s.o += len;
+        } else { s.detail = RCZ_FL_INVALID_HUFFMAN_CODE; return F_INVALID; }
+    }
+}
+
+// flate.rs:237-246 statik
+__device__ int stored(St& s, unsigned lane) {
+    const unsigned long long n = (unsigned long long)(s.br.end - s.br.in);
+    unsigned long long p = s.br.bytepos();
+    if (p + 2 > n) return F_EOF;
+    const unsigned len = (unsigned)s.br.in[p] | ((unsigned)s.br.in[p + 1] << 8);
+    p += 2;
+    if (p + 2 > n) return F_EOF;
+    const unsigned nlen = (unsigned)s.br.in[p] | ((unsigned)s.br.in[p + 1] << 8);
+    p += 2;
+    if (((~nlen) & 0xffffu) != len) { s.br.bitpos = p * 8; s.detail = RCZ_FL_INVALID_STATIC_SIZE; return F_INVALID; }
+    if (p + len > n) return F_EOF;
+    if (len > s.cap - s.o) { s.br.bitpos = p * 8; return F_FULL; }
+    flush_lits(s, lane);
+    for (unsigned j = lane; j < len; j += 32) s.out[s.o + j] = s.br.in[p + j];
+    __syncwarp();
+    s.o += len;
+    s.br.seek(p + len);
+    return F_OK;
+}
+
+__device__ int fixed_block(St& s, WarpSmem& w, unsigned lane) {                          // flate.rs:343-395
+    __syncwarp();
+    for (unsigned i = lane; i < 288; i += 32) w.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+    __syncwarp();
+    build_tree(w.lt, w.lsym, w.llut, LB, w.lens, 288);
+    __syncwarp();
+    if (lane < 30) w.lens[lane] = 5;
+    __syncwarp();
+    build_tree(w.dt, w.dsym, w.dlut, DB, w.lens, 30);
+    return codes(s, w, lane);
+}
+
+__device__ int dynamic_block(St& s, WarpSmem& w, unsigned lane) {                        // flate.rs:397-450
+    s.br.refill();
+    const unsigned hlit = s.br.take(5) + 257; if (s.br.eof()) return F_EOF;
+    const unsigned hdist = s.br.take(5) + 1; if (s.br.eof()) return F_EOF;
+    const unsigned hclen = s.br.take(4) + 4; if (s.br.eof()) return F_EOF;
+    if (hlit > (unsigned)MAXLCODES || hdist > (unsigned)MAXDCODES) { s.detail = RCZ_FL_HUFFMAN_TREE_TOO_LARGE; return F_INVALID; }
+    __syncwarp();
+    if (lane < 19) w.clen[lane] = 0;
+    for (unsigned i = lane; i < (unsigned)MAXCODES; i += 32) w.lens[i] = 0;
+    __syncwarp();
+    for (unsigned i = 0; i < hclen; ++i) {
+        s.br.refill();
+        const unsigned v = s.br.take(3);
+        if (s.br.eof()) return F_EOF;
+        if (lane == 0) w.clen[CL_ORDER[i]] = (uint8_t)v;
+    }
+    __syncwarp();
+    if (!build_tree(w.ct, w.csym, nullptr, 0, w.clen, 19)) { s.detail = RCZ_FL_INVALID_HUFFMAN_TREE; return F_INVALID; }
+    const unsigned total = hlit + hdist;
+    unsigned i = 0, prev = 0;
+    while (i < total) {
+        s.br.refill();
+        unsigned l;
+        const int v = slow_decode(w.ct, w.csym, s.br.peek(15), l);
+        if (v < 0) {
+            if (s.br.bitpos + 15 > s.br.endbits) return F_EOF;
+            s.detail = RCZ_FL_NOT_ENOUGH_BITS; return F_INVALID;
+        }
+        s.br.consume(l);
+        if (s.br.eof()) return F_EOF;
+        if (v < 16) { if (lane == 0) w.lens[i] = (uint8_t)v; prev = (unsigned)v; ++i; }
+        else if (v == 16) {
+            if (i == 0) { s.detail = RCZ_FL_INVALID_HUFFMAN_HEADER_SYMBOL; return F_INVALID; }
+            const unsigned rep = s.br.take(2) + 3;
+            if (s.br.eof()) return F_EOF;
+            for (unsigned k = 0; k < rep; ++k) {
+                if (i >= (unsigned)MAXCODES) return F_MALFORMED;                         // lengths[i] index panic
+                if (lane == 0) w.lens[i] = (uint8_t)prev;
+                ++i;
+            }
+        } else if (v == 17) { const unsigned z = s.br.take(3); if (s.br.eof()) return F_EOF; i += z + 3; prev = 0; }
+        else if (v == 18) { const unsigned z = s.br.take(7); if (s.br.eof()) return F_EOF; i += z + 11; prev = 0; }
+        else { s.detail = RCZ_FL_INVALID_HUFFMAN_HEADER_SYMBOL; return F_INVALID; }
+    }
+    if (i > total) { s.detail = RCZ_FL_INVALID_HUFFMAN_TREE_HEADER; return F_INVALID; }
+    __syncwarp();
+    if (!build_tree(w.lt, w.lsym, w.llut, LB, w.lens, hlit)) { s.detail = RCZ_FL_INVALID_HUFFMAN_TREE; return F_INVALID; }
+    if (!build_tree(w.dt, w.dsym, w.dlut, DB, w.lens + hlit, hdist)) { s.detail = RCZ_FL_INVALID_HUFFMAN_TREE; return F_INVALID; }
+    return codes(s, w, lane);
+}
+
+__global__ void __launch_bounds__(NT)
+inflate_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ in_len,
+               uint8_t* __restrict__ out_base, const uint64_t* __restrict__ out_off, const uint64_t* __restrict__ out_cap,
+               uint64_t* __restrict__ out_len, uint64_t* __restrict__ in_used, int32_t* __restrict__ status, int32_t* __restrict__ detail,
+               unsigned nstreams) {
+    RCZ_DYN_SMEM(raw);
+    const unsigned lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    WarpSmem& w = reinterpret_cast<WarpSmem*>(raw)[wi];
+    for (unsigned sidx = blockIdx.x * WPB + wi; sidx < nstreams; sidx += gridDim.x * WPB) {
+        St s;
+        const unsigned long long n = in_len[sidx];
+        s.br.init(in_base + in_off[sidx], n);
+        s.out = out_base + out_off[sidx];
+        s.cap = out_cap[sidx]; s.o = 0; s.detail = 0; s.qn = 0; s.qv = 0;
+        int r = F_OK;
+        for (;;) {                                                                   // flate.rs:195-206 block
+            s.br.refill();
+            const unsigned bfinal = s.br.take(1);
+            if (s.br.eof()) { r = F_EOF; break; }
+            const unsigned type = s.br.take(2);
+            if (s.br.eof()) { r = F_EOF; break; }
+            if (type == 0) r = stored(s, lane);
+            else if (type == 1) r = fixed_block(s, w, lane);
+            else if (type == 2) r = dynamic_block(s, w, lane);
+            else { s.detail = RCZ_FL_INVALID_BLOCK_CODE; r = F_INVALID; }
+            if (r != F_OK || bfinal) break;
+        }
+        flush_lits(s, lane);
+        __syncwarp();
+        if (lane == 0) {
+            out_len[sidx] = s.o;
+            status[sidx] = r == F_OK ? RCZ_OK : r == F_EOF ? RCZ_E_UNEXPECTED_EOF : r == F_INVALID ? RCZ_E_INVALID_INPUT
+                           : r == F_MALFORMED ? RCZ_E_MALFORMED : RCZ_E_OUTPUT_FULL;
+            if (detail) detail[sidx] = r == F_INVALID ? s.detail : 0;
+            if (in_used) { const unsigned long long bp = s.br.bytepos(); in_used[sidx] = (r == F_EOF || bp > n) ? n : bp; }
+        }
+    }
+}
+
+}  // namespace flk
+
+extern "C" int rcz_flate_decode_streams(rcz_ctx* c, const void* in_base, const uint64_t* in_off, const uint64_t* in_len, void* out_base,
+                                        const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len, uint64_t* in_used,
+                                        int32_t* status, int32_t* detail, size_t n, int mem_kind) {
+    if (!c || rcz_bad_kind(mem_kind)) return RCZ_E_ARG;
+    if (n == 0) return RCZ_OK;
+    if (!in_base || !in_off || !in_len || !out_base || !out_off || !out_cap || !out_len || !status || n > 0x7fffffffu) return RCZ_E_ARG;
+    rt_set_device(c->device);
+    for (size_t i = 0; i < n; ++i) if (in_len[i] >= (1ull << 31)) return RCZ_E_ARG;
+    DescStager ds(c, mem_kind, n);
+    ds.add_in(in_off, n * 8); ds.add_in(in_len, n * 8); ds.add_in(out_off, n * 8); ds.add_in(out_cap, n * 8);
+    ds.add_out(out_len, n * 8); ds.add_out(status, n * 4);
+    const size_t o_used = ds.add_out(in_used, in_used ? n * 8 : 0);
+    const size_t o_det = ds.add_out(detail, detail ? n * 4 : 0);
+    int st = ds.upload(); if (st) return st;
+    const uint8_t* din = (const uint8_t*)in_base; uint8_t* dout = (uint8_t*)out_base;
+    if (mem_kind == RCZ_MEM_HOST) {
+        st = stage_span_in(c, WS_IN, in_base, in_off, in_len, n, 1, &din); if (st) return st;
+        st = stage_span_out(c, WS_OUT, out_off, out_cap, n, 1, &dout); if (st) return st;
+    }
+    const size_t smem = sizeof(flk::WarpSmem) * flk::WPB;
+    RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(flk::inflate_kernel, smem));
+    const unsigned grid = (unsigned)std::min<size_t>((n + flk::WPB - 1) / flk::WPB, (size_t)c->sm_count * 12);
+    st = ctx_timer_begin(c); if (st) return st;
+    RCZ_KLAUNCH(c, flk::inflate_kernel, grid, flk::NT, smem, din, ds.in_ptr<uint64_t>(0), ds.in_ptr<uint64_t>(1), dout, ds.in_ptr<uint64_t>(2),
+                ds.in_ptr<uint64_t>(3), ds.out_ptr<uint64_t>(0), in_used ? ds.out_ptr<uint64_t>(o_used) : (uint64_t*)nullptr,
+                ds.out_ptr<int32_t>(1), detail ? ds.out_ptr<int32_t>(o_det) : (int32_t*)nullptr, (unsigned)n);
+    st = ctx_timer_end(c); if (st) return st;
+    st = ds.download(); if (st) return st;
+    if (mem_kind == RCZ_MEM_HOST) {
+        std::vector<uint64_t> clipped(n);
+        for (size_t i = 0; i < n; ++i) clipped[i] = out_len[i] < out_cap[i] ? out_len[i] : out_cap[i];
+        st = unstage_span_out(c, out_base, dout, out_off, clipped.data(), n, 1); if (st) return st;
+    }
+    return RCZ_OK;
+}
