@@ -1,0 +1,435 @@
+// bwt_encode.cu — K2 (suffix sort) + K3 (L-column gather) for batches of independent BWT blocks.
+//
+// Replaces /root/reference/src/bwt/mod.rs:136-166 `compute_suffixes` (bucket by first byte, then
+// `sort_by(|a,b| input[a..].cmp(&input[b..]))` — quadratic and worse on repetitive input) and :193-203
+// `TransformIterator` (L[i] = in[SA[i]-1], in[n-1] at SA[i]==0 whose i is `origin`), as called by the stream
+// encoder at bwt/mod.rs:470-475.  The suffix array is unique, so any correct sort is bit-exact; the order is the
+// reference's slice order: a suffix that is a proper prefix of another sorts first (implicit end marker below 0x00).
+//
+// Shape on the GPU — prefix doubling over LSD radix sorts, all blocks of a batch in lock step:
+//   round 0   key = first 7 symbols, 9 bits each (byte+1; 0 = past the end)           -> 8 radix passes
+//   round r   key = (rank_h[i] << b) | (i+h < n ? rank_h[i+h]+1 : 0),  h = 7 * 2^(r-1)  -> ceil(2b/8) passes
+//   after every round: group heads in the sorted keys give the new ranks; a block whose n keys are all distinct is
+//   finished and its L column / origin are gathered at once.  Random data (BASELINE config 3) finishes in round 0.
+// One radix pass = per-tile digit histogram, per-block exclusive scan, stable 256-way partition per tile
+// (match_any ranking inside each warp, shared-memory staging so every (tile, digit) run leaves as one contiguous
+// store).  No host synchronisation is needed: finished blocks are skipped on the device (state[]), so the whole
+// round schedule can be enqueued blind (DEVICE_ASYNC); the synchronous modes read one counter per round to stop early.
+#include "rcz_internal.h"
+#include <algorithm>
+
+namespace bwte {
+
+constexpr int TB = 8192;                  // elements per radix tile
+constexpr int NT = 256;                   // threads per tile CTA
+constexpr int NW = NT / 32;
+constexpr int WSPAN = TB / NW;            // 1024 consecutive elements per warp
+constexpr int SPAN = 1024;                // rank-assignment granularity (one warp)
+constexpr unsigned NONE = 0xFFFFFFFFu;
+constexpr unsigned ACTIVE = 0;
+
+struct Blk {
+    unsigned long long in_off, out_off;   // bytes
+    unsigned long long e0;                // element offset into K/V/R
+    unsigned n, tile0, ntiles, span0, nspans, skip;
+};
+
+__device__ __forceinline__ unsigned find_blk_tile(const Blk* blks, unsigned nblocks, unsigned tile) {
+    unsigned lo = 0, hi = nblocks;
+    while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (blks[mid].tile0 <= tile) lo = mid; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ unsigned find_blk_span(const Blk* blks, unsigned nblocks, unsigned span) {
+    unsigned lo = 0, hi = nblocks;
+    while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (blks[mid].span0 <= span) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------ round-0 keys
+__global__ void __launch_bounds__(NT)
+init_keys_kernel(const uint8_t* __restrict__ in_base, const Blk* __restrict__ blks, unsigned nblocks, unsigned long long* __restrict__ K,
+                 unsigned* __restrict__ V) {
+    __shared__ uint8_t s[TB + 8];
+    const unsigned tile = blockIdx.x, tid = threadIdx.x;
+    const Blk bk = blks[find_blk_tile(blks, nblocks, tile)];
+    if (bk.skip) return;
+    const uint8_t* in = in_base + bk.in_off;
+    const unsigned lo = (tile - bk.tile0) * TB, hi = min(bk.n, lo + TB);
+    for (unsigned j = tid; j < TB + 8; j += NT) s[j] = lo + j < bk.n ? in[lo + j] : 0;
+    __syncthreads();
+    for (unsigned j = tid; lo + j < hi; j += NT) {
+        const unsigned i = lo + j;
+        unsigned long long key = 0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) key = (key << 9) | (i + k < bk.n ? (unsigned long long)s[j + k] + 1ull : 0ull);
+        K[bk.e0 + i] = key;
+        V[bk.e0 + i] = i;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ round-r keys
+__global__ void __launch_bounds__(NT)
+double_keys_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* __restrict__ state, const unsigned* __restrict__ R,
+                   unsigned h, unsigned bits, unsigned long long* __restrict__ K, unsigned* __restrict__ V) {
+    const unsigned tile = blockIdx.x, tid = threadIdx.x;
+    const unsigned b = find_blk_tile(blks, nblocks, tile);
+    const Blk bk = blks[b];
+    if (bk.skip || state[b] != ACTIVE) return;
+    const unsigned lo = (tile - bk.tile0) * TB, hi = min(bk.n, lo + TB);
+    const unsigned* r = R + bk.e0;
+    for (unsigned i = lo + tid; i < hi; i += NT) {
+        const unsigned long long r2 = (i + h < bk.n && i + h >= i) ? (unsigned long long)r[i + h] + 1ull : 0ull;
+        K[bk.e0 + i] = ((unsigned long long)r[i] << bits) | r2;
+        V[bk.e0 + i] = i;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ radix pass: histogram
+__global__ void __launch_bounds__(NT)
+hist_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* __restrict__ state, const unsigned long long* __restrict__ K,
+            unsigned shift, unsigned* __restrict__ tile_hist) {
+    __shared__ unsigned hsm[256];
+    const unsigned tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const unsigned b = find_blk_tile(blks, nblocks, tile);
+    const Blk bk = blks[b];
+    if (bk.skip || state[b] != ACTIVE) return;
+    const unsigned lo = (tile - bk.tile0) * TB, hi = min(bk.n, lo + TB);
+    hsm[tid] = 0;
+    __syncthreads();
+    const unsigned long long* k = K + bk.e0;
+    for (unsigned base = lo; base < hi; base += NT) {
+        const unsigned i = base + tid;
+        const bool valid = i < hi;
+        const unsigned d = valid ? (unsigned)(k[i] >> shift) & 255u : 256u + lane;
+        const unsigned m = __match_any_sync(RCZ_FULL, d);
+        if (valid && (m & ((1u << lane) - 1u)) == 0) atomicAdd(&hsm[d], (unsigned)__popc(m));
+    }
+    __syncthreads();
+    tile_hist[(size_t)tile * 256 + tid] = hsm[tid];
+}
+
+// tile_hist[tile][d] <- number of d's in earlier tiles of the block; cbase[blk][d] <- number of digits < d
+__global__ void __launch_bounds__(256)
+scan_kernel(const Blk* __restrict__ blks, const unsigned* __restrict__ state, unsigned* __restrict__ tile_hist, unsigned* __restrict__ cbase) {
+    __shared__ unsigned scratch[40];
+    const unsigned b = blockIdx.x, c = threadIdx.x;
+    const Blk bk = blks[b];
+    if (bk.skip || state[b] != ACTIVE) return;
+    unsigned run = 0;
+    for (unsigned t = 0; t < bk.ntiles; ++t) {
+        const size_t idx = (size_t)(bk.tile0 + t) * 256 + c;
+        const unsigned hcnt = tile_hist[idx];
+        tile_hist[idx] = run;
+        run += hcnt;
+    }
+    unsigned total;
+    const unsigned ex = block_excl_scan_add<256>(run, scratch, &total);
+    cbase[(size_t)b * 256 + c] = ex;
+}
+
+// ------------------------------------------------------------------------------------------ radix pass: stable partition
+struct ScatSmem {
+    unsigned long long skey[TB];
+    unsigned sval[TB];
+    unsigned wcnt[NW][256];
+    unsigned symbase[256];
+    unsigned gbase[256];
+    unsigned scratch[40];
+};
+
+__global__ void __launch_bounds__(NT, 2)
+scatter_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* __restrict__ state, const unsigned long long* __restrict__ Kin,
+               const unsigned* __restrict__ Vin, unsigned long long* __restrict__ Kout, unsigned* __restrict__ Vout, unsigned shift,
+               const unsigned* __restrict__ tile_hist, const unsigned* __restrict__ cbase) {
+    RCZ_DYN_SMEM(raw);
+    ScatSmem& sm = *reinterpret_cast<ScatSmem*>(raw);
+    const unsigned tile = blockIdx.x, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const unsigned b = find_blk_tile(blks, nblocks, tile);
+    const Blk bk = blks[b];
+    if (bk.skip || state[b] != ACTIVE) return;
+    const unsigned lo = (tile - bk.tile0) * TB, hi = min(bk.n, lo + TB), tlen = hi - lo;
+    const unsigned long long* kin = Kin + bk.e0;
+    const unsigned* vin = Vin + bk.e0;
+
+    for (unsigned i = tid; i < NW * 256; i += NT) (&sm.wcnt[0][0])[i] = 0;
+    __syncthreads();
+    for (unsigned g = 0; g < WSPAN / 32; ++g) {                                // per-warp digit counts
+        const unsigned i = lo + w * WSPAN + g * 32 + lane;
+        const bool valid = i < hi;
+        const unsigned d = valid ? (unsigned)(kin[i] >> shift) & 255u : 256u + lane;
+        const unsigned m = __match_any_sync(RCZ_FULL, d);
+        if (valid && (m & ((1u << lane) - 1u)) == 0) sm.wcnt[w][d] += (unsigned)__popc(m);
+        __syncwarp();
+    }
+    __syncthreads();
+    unsigned tot = 0;                                                          // exclusive scan over warps, then digits
+#pragma unroll
+    for (int k = 0; k < NW; ++k) { const unsigned x = sm.wcnt[k][tid]; sm.wcnt[k][tid] = tot; tot += x; }
+    unsigned dummy;
+    const unsigned sb = block_excl_scan_add<NT>(tot, sm.scratch, &dummy);
+    sm.symbase[tid] = sb;
+    sm.gbase[tid] = cbase[(size_t)b * 256 + tid] + tile_hist[(size_t)tile * 256 + tid] - sb;   // dst of sorted index j: gbase[d] + j
+    __syncthreads();
+    for (unsigned g = 0; g < WSPAN / 32; ++g) {                                // stable ranking, 32 keys at a time per warp
+        const unsigned i = lo + w * WSPAN + g * 32 + lane;
+        const bool valid = i < hi;
+        const unsigned long long key = valid ? kin[i] : 0ull;
+        const unsigned val = valid ? vin[i] : 0u;
+        const unsigned d = valid ? (unsigned)(key >> shift) & 255u : 256u + lane;
+        const unsigned m = __match_any_sync(RCZ_FULL, d);
+        const unsigned r = __popc(m & ((1u << lane) - 1u));
+        unsigned base = 0;
+        if (valid) base = sm.wcnt[w][d];
+        __syncwarp();
+        if (valid && r == 0) sm.wcnt[w][d] = base + __popc(m);
+        __syncwarp();
+        if (valid) { const unsigned p = sm.symbase[d] + base + r; sm.skey[p] = key; sm.sval[p] = val; }
+    }
+    __syncthreads();
+    unsigned long long* kout = Kout + bk.e0;
+    unsigned* vout = Vout + bk.e0;
+    for (unsigned j = tid; j < tlen; j += NT) {
+        const unsigned long long key = sm.skey[j];
+        const unsigned dst = sm.gbase[(unsigned)(key >> shift) & 255u] + j;
+        kout[dst] = key;
+        vout[dst] = sm.sval[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------ group heads per span
+__global__ void __launch_bounds__(128)
+heads_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nspans, const unsigned* __restrict__ state,
+             const unsigned long long* __restrict__ K, unsigned* __restrict__ span_heads, unsigned* __restrict__ span_last) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned span = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (span >= nspans) return;
+    const unsigned b = find_blk_span(blks, nblocks, span);
+    const Blk bk = blks[b];
+    if (bk.skip || state[b] != ACTIVE) return;
+    const unsigned lo = (span - bk.span0) * SPAN, hi = min(bk.n, lo + SPAN);
+    const unsigned long long* k = K + bk.e0;
+    unsigned cnt = 0, last = NONE;
+    for (unsigned base = lo; base < hi; base += 32) {
+        const unsigned j = base + lane;
+        const bool head = j < hi && (j == 0 || k[j] != k[j - 1]);
+        const unsigned m = __ballot_sync(RCZ_FULL, head);
+        cnt += __popc(m);
+        if (m) last = base + 31u - (unsigned)__clz((int)m);
+    }
+    if (lane == 0) { span_heads[span] = cnt; span_last[span] = last; }
+}
+
+// per block: all keys distinct -> state = round + 1 (finished in this round); else span_last <- last head before the span
+__global__ void __launch_bounds__(256)
+block_state_kernel(const Blk* __restrict__ blks, unsigned* __restrict__ state, const unsigned* __restrict__ span_heads,
+                   unsigned* __restrict__ span_last, unsigned round, unsigned* __restrict__ nactive) {
+    __shared__ unsigned ssum[256], smax[256];
+    __shared__ unsigned done;
+    const unsigned b = blockIdx.x, t = threadIdx.x;
+    const Blk bk = blks[b];
+    if (bk.skip || state[b] != ACTIVE) return;
+    const unsigned per = (bk.nspans + 255) / 256;
+    const unsigned s0 = min(bk.nspans, t * per), s1 = min(bk.nspans, s0 + per);
+    unsigned sum = 0, mx = 0;                                                  // positions are stored +1 so that 0 == none
+    for (unsigned s = s0; s < s1; ++s) { sum += span_heads[bk.span0 + s]; const unsigned l = span_last[bk.span0 + s]; if (l != NONE) mx = l + 1; }
+    ssum[t] = sum; smax[t] = mx;
+    __syncthreads();
+    if (t == 0) {
+        unsigned total = 0, run = 0;
+        for (unsigned i = 0; i < 256; ++i) { total += ssum[i]; const unsigned m = smax[i]; smax[i] = run; if (m) run = m; }
+        done = total == bk.n;
+        if (done) state[b] = round + 1; else atomicAdd(nactive, 1u);
+    }
+    __syncthreads();
+    if (done) return;
+    unsigned run = smax[t];
+    for (unsigned s = s0; s < s1; ++s) {
+        const unsigned l = span_last[bk.span0 + s];
+        span_last[bk.span0 + s] = run ? run - 1 : 0u;                          // position 0 is always a head
+        if (l != NONE) run = l + 1;
+    }
+}
+
+// R[V[j]] = position of the head of j's group
+__global__ void __launch_bounds__(128)
+assign_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nspans, const unsigned* __restrict__ state,
+              const unsigned long long* __restrict__ K, const unsigned* __restrict__ V, const unsigned* __restrict__ span_carry,
+              unsigned* __restrict__ R) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned span = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (span >= nspans) return;
+    const unsigned b = find_blk_span(blks, nblocks, span);
+    const Blk bk = blks[b];
+    if (bk.skip || state[b] != ACTIVE) return;
+    const unsigned lo = (span - bk.span0) * SPAN, hi = min(bk.n, lo + SPAN);
+    const unsigned long long* k = K + bk.e0;
+    const unsigned* v = V + bk.e0;
+    unsigned* r = R + bk.e0;
+    unsigned carry = span_carry[span];
+    for (unsigned base = lo; base < hi; base += 32) {
+        const unsigned j = base + lane;
+        const bool head = j < hi && (j == 0 || k[j] != k[j - 1]);
+        const unsigned m = __ballot_sync(RCZ_FULL, head);
+        const unsigned below = m & (0xFFFFFFFFu >> (31 - lane));
+        const unsigned rank = below ? base + 31u - (unsigned)__clz((int)below) : carry;
+        if (j < hi) r[v[j]] = rank;
+        if (m) carry = base + 31u - (unsigned)__clz((int)m);
+    }
+}
+
+// L column + origin for the blocks that finished in this round (bwt/mod.rs:193-203)
+__global__ void __launch_bounds__(NT)
+gather_kernel(const uint8_t* __restrict__ in_base, const Blk* __restrict__ blks, unsigned nblocks, const unsigned* __restrict__ state,
+              unsigned round, const unsigned* __restrict__ V, uint8_t* __restrict__ out_base, uint32_t* __restrict__ origin,
+              int32_t* __restrict__ status) {
+    const unsigned tile = blockIdx.x, tid = threadIdx.x;
+    const unsigned b = find_blk_tile(blks, nblocks, tile);
+    const Blk bk = blks[b];
+    if (bk.skip || state[b] != round + 1) return;
+    const uint8_t* in = in_base + bk.in_off;
+    uint8_t* out = out_base + bk.out_off;
+    const unsigned* v = V + bk.e0;
+    const unsigned lo = (tile - bk.tile0) * TB, hi = min(bk.n, lo + TB);
+    for (unsigned j = lo + tid; j < hi; j += NT) {
+        const unsigned p = v[j];
+        if (p == 0) { out[j] = in[bk.n - 1]; origin[b] = j; status[b] = RCZ_OK; }
+        else out[j] = in[p - 1];
+    }
+}
+
+__global__ void init_state_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned* __restrict__ state, unsigned* __restrict__ nactive,
+                                  unsigned nrounds, uint32_t* __restrict__ origin, int32_t* __restrict__ status,
+                                  const int32_t* __restrict__ host_status) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nrounds) nactive[i] = 0;
+    if (i < nblocks) {
+        state[i] = ACTIVE;
+        origin[i] = 0;
+        status[i] = blks[i].skip ? host_status[i] : RCZ_E_CUDA;               // overwritten by gather_kernel when the block finishes
+    }
+}
+
+}  // namespace bwte
+
+extern "C" int rcz_bwt_encode_blocks(rcz_ctx* c, const void* in_base, const uint64_t* in_off, const uint64_t* n_arr, void* out_base,
+                                     const uint64_t* out_off, uint32_t* origin, int32_t* status, size_t nblocks, int mem_kind) {
+    using namespace bwte;
+    if (!c || rcz_bad_kind(mem_kind)) return RCZ_E_ARG;
+    if (nblocks == 0) return RCZ_OK;
+    if (!in_base || !in_off || !n_arr || !out_base || !out_off || !origin || !status || nblocks > 0x3fffffu) return RCZ_E_ARG;
+    rt_set_device(c->device);
+
+    // ---- geometry; big batches are cut into groups so that the sort workspace (28 B / symbol) stays bounded
+    constexpr unsigned long long GROUP_ELEMS = 1ull << 28;
+    std::vector<Blk> blks(nblocks);
+    std::vector<int32_t> hstatus(nblocks, 0);
+    struct Group { size_t b0, b1; unsigned long long elems; unsigned ntiles, nspans, nmax; };
+    std::vector<Group> groups;
+    Group cur{0, 0, 0, 0, 0, 0};
+    for (size_t i = 0; i < nblocks; ++i) {
+        Blk& b = blks[i];
+        memset(&b, 0, sizeof b);
+        b.in_off = in_off[i]; b.out_off = out_off[i];
+        const unsigned long long n = n_arr[i];
+        const bool bad = n == 0 || n >= (1ull << 31);
+        if (!bad && cur.b1 > cur.b0 && (cur.elems + n > GROUP_ELEMS || cur.ntiles > 0x3fffffffu - (unsigned)(n / TB + 1))) {
+            groups.push_back(cur);
+            cur = Group{i, i, 0, 0, 0, 0};
+        }
+        b.e0 = cur.elems; b.tile0 = cur.ntiles; b.span0 = cur.nspans;
+        if (bad) { b.skip = 1; hstatus[i] = n == 0 ? RCZ_E_MALFORMED : RCZ_E_ARG; }   // n == 0: get_origin().unwrap() on None (bwt/mod.rs:186-188)
+        else {
+            b.n = (unsigned)n;
+            b.ntiles = (b.n + TB - 1) / TB; b.nspans = (b.n + SPAN - 1) / SPAN;
+            cur.elems += (n + 63) & ~63ull; cur.ntiles += b.ntiles; cur.nspans += b.nspans;
+            cur.nmax = std::max(cur.nmax, b.n);
+        }
+        cur.b1 = i + 1;
+    }
+    groups.push_back(cur);
+    unsigned long long max_elems = 0; unsigned max_tiles = 0, max_spans = 0; size_t max_blocks = 0;
+    for (auto& g : groups) {
+        max_elems = std::max(max_elems, g.elems); max_tiles = std::max(max_tiles, g.ntiles); max_spans = std::max(max_spans, g.nspans);
+        max_blocks = std::max(max_blocks, g.b1 - g.b0);
+    }
+
+    DescStager ds(c, mem_kind, nblocks);
+    const size_t i_blk = ds.add_in(blks.data(), nblocks * sizeof(Blk));
+    const size_t i_hst = ds.add_in(hstatus.data(), nblocks * 4);
+    const size_t o_org = ds.add_out(origin, nblocks * 4);
+    const size_t o_st = ds.add_out(status, nblocks * 4);
+    int st = ds.upload(); if (st) return st;
+    const uint8_t* din = (const uint8_t*)in_base; uint8_t* dout = (uint8_t*)out_base;
+    if (mem_kind == RCZ_MEM_HOST) {
+        st = stage_span_in(c, WS_IN, in_base, in_off, n_arr, nblocks, 1, &din); if (st) return st;
+        st = stage_span_out(c, WS_OUT, out_off, n_arr, nblocks, 1, &dout); if (st) return st;
+    }
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    void *wK, *wV, *wR, *wM;
+    st = ctx_ws(c, WS_A, al((size_t)max_elems * 8) * 2 + 256, &wK); if (st) return st;
+    st = ctx_ws(c, WS_B, al((size_t)max_elems * 4) * 2 + 256, &wV); if (st) return st;
+    st = ctx_ws(c, WS_C, al((size_t)max_elems * 4) + 256, &wR); if (st) return st;
+    const size_t sz_hist = al((size_t)max_tiles * 256 * 4), sz_cb = al(max_blocks * 256 * 4), sz_sp = al((size_t)max_spans * 4), sz_state = al(max_blocks * 4);
+    st = ctx_ws(c, WS_D, sz_hist + sz_cb + 2 * sz_sp + sz_state + 1024, &wM); if (st) return st;
+    unsigned long long* K[2] = {(unsigned long long*)wK, (unsigned long long*)((uint8_t*)wK + al((size_t)max_elems * 8))};
+    unsigned* V[2] = {(unsigned*)wV, (unsigned*)((uint8_t*)wV + al((size_t)max_elems * 4))};
+    unsigned* R = (unsigned*)wR;
+    uint8_t* m = (uint8_t*)wM;
+    unsigned* tile_hist = (unsigned*)m; m += sz_hist;
+    unsigned* cbase = (unsigned*)m; m += sz_cb;
+    unsigned* span_heads = (unsigned*)m; m += sz_sp;
+    unsigned* span_last = (unsigned*)m; m += sz_sp;
+    unsigned* state = (unsigned*)m; m += sz_state;
+    unsigned* nactive = (unsigned*)m;                                          // one counter per round (<= 64)
+
+    RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(scatter_kernel, sizeof(ScatSmem)));
+    st = ctx_timer_begin(c); if (st) return st;
+    for (auto& g : groups) {
+        const unsigned nb = (unsigned)(g.b1 - g.b0);
+        const Blk* dblk = ds.in_ptr<Blk>(i_blk) + g.b0;
+        uint32_t* d_org = ds.out_ptr<uint32_t>(o_org) + g.b0;
+        int32_t* d_st = ds.out_ptr<int32_t>(o_st) + g.b0;
+        unsigned bits = 1; while ((1ull << bits) <= g.nmax) ++bits;            // rank2 takes values 0..n
+        unsigned nrounds = 1; while (7ull << (nrounds - 1) < g.nmax) ++nrounds; // after round r ranks cover 7 * 2^r symbols
+        if (nrounds > 60) nrounds = 60;
+        RCZ_KLAUNCH(c, init_state_kernel, (std::max(nb, 64u) + 255) / 256, 256, 0, dblk, nb, state, nactive, 64u, d_org, d_st,
+                    ds.in_ptr<int32_t>(i_hst) + g.b0);
+        if (g.ntiles == 0) continue;
+        const unsigned sgrid = (g.nspans + 3) / 4;
+        for (unsigned round = 0; round < nrounds; ++round) {
+            unsigned npass;
+            if (round == 0) {
+                RCZ_KLAUNCH(c, init_keys_kernel, g.ntiles, NT, 0, din, dblk, nb, K[0], V[0]);
+                npass = 8;
+            } else {
+                RCZ_KLAUNCH(c, double_keys_kernel, g.ntiles, NT, 0, dblk, nb, state, R, (unsigned)(7u << (round - 1)), bits, K[0], V[0]);
+                npass = (2 * bits + 7) / 8; npass += npass & 1;               // even: the sorted data ends up in buffer 0
+            }
+            for (unsigned p = 0; p < npass; ++p) {
+                const unsigned a = p & 1;
+                RCZ_KLAUNCH(c, hist_kernel, g.ntiles, NT, 0, dblk, nb, state, K[a], p * 8, tile_hist);
+                RCZ_KLAUNCH(c, scan_kernel, nb, 256, 0, dblk, state, tile_hist, cbase);
+                RCZ_KLAUNCH(c, scatter_kernel, g.ntiles, NT, sizeof(ScatSmem), dblk, nb, state, K[a], V[a], K[a ^ 1], V[a ^ 1], p * 8, tile_hist, cbase);
+            }
+            RCZ_KLAUNCH(c, heads_kernel, sgrid, 128, 0, dblk, nb, g.nspans, state, K[0], span_heads, span_last);
+            RCZ_KLAUNCH(c, block_state_kernel, nb, 256, 0, dblk, state, span_heads, span_last, round, nactive + round);
+            RCZ_KLAUNCH(c, gather_kernel, g.ntiles, NT, 0, din, dblk, nb, state, round, V[0], dout, d_org, d_st);
+            if (round + 1 == nrounds) break;
+            if (mem_kind != RCZ_MEM_DEVICE_ASYNC) {                            // stop as soon as every block is finished
+                unsigned left = 0;
+                RCZ_CK(c, rt_d2h(&left, nactive + round, 4, c->stream));
+                RCZ_CK(c, rt_stream_sync(c->stream));
+                if (left == 0) break;
+            }
+            RCZ_KLAUNCH(c, assign_kernel, sgrid, 128, 0, dblk, nb, g.nspans, state, K[0], V[0], span_last, R);
+        }
+    }
+    st = ctx_timer_end(c); if (st) return st;
+    st = ds.download(); if (st) return st;
+    if (mem_kind == RCZ_MEM_HOST) {
+        std::vector<uint64_t> lens(nblocks);
+        for (size_t i = 0; i < nblocks; ++i) lens[i] = status[i] == RCZ_OK ? n_arr[i] : 0;
+        st = unstage_span_out(c, out_base, dout, out_off, lens.data(), nblocks, 1); if (st) return st;
+    }
+    return RCZ_OK;
+}
