@@ -1,0 +1,235 @@
+// test_host.cpp — the reference crate's own unit tests, restated against the C++ host mirrors (rcz_stream.hpp).
+//   lz4.rs:647-726   decode (fixtures), one_byte_at_a_time, random_byte_lengths, some_roundtrips
+//   bwt/mod.rs:541-551 some_roundtrips          bwt/dc.rs:291-302 roundtrips
+//   entropy/ari/test.rs:185-212 roundtrips, roundtrips_term
+//   flate.rs:528-582 decode (fixtures), one_byte_at_a_time (+eof), random_byte_lengths
+//   rle.rs:320-361   simple/long run encoding + decoding KATs, random_roundtrips
+// Built by tests/test_host_mirrors.py against librcz_emu.so (CPU, no GPU needed) and against librcz.so (-m gpu).
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <functional>
+#include <iostream>
+#include <iterator>
+#include <random>
+#include <string>
+
+#include "rcz_stream.hpp"
+
+using bytes = std::vector<uint8_t>;
+static std::string g_dir;
+static int g_fail = 0;
+
+static bytes load(const std::string& name) {
+    std::ifstream f(g_dir + "/" + name, std::ios::binary);
+    if (!f) { std::cerr << "missing fixture " << name << "\n"; exit(2); }
+    return bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+#define CHECK(cond) do { if (!(cond)) { std::cerr << "  FAILED " << #cond << " at line " << __LINE__ << "\n"; ++g_fail; return; } } while (0)
+static void run(const char* name, const std::function<void()>& f) {
+    int before = g_fail;
+    try { f(); } catch (const std::exception& e) { std::cerr << "  exception: " << e.what() << "\n"; ++g_fail; }
+    std::cout << (g_fail == before ? "ok   " : "FAIL ") << name << std::endl;
+}
+template <class D> static bytes read_to_end(D& d, size_t chunk = 4096) {
+    bytes out, buf(chunk);
+    for (;;) { size_t k = d.read(buf.data(), chunk); if (k == 0) break; out.insert(out.end(), buf.begin(), buf.begin() + (long)k); }
+    return out;
+}
+static bytes lit(const char* s) { return bytes(s, s + strlen(s)); }
+
+int main(int argc, char** argv) {
+    if (argc < 2) { std::cerr << "usage: test_host <golden dir>\n"; return 2; }
+    g_dir = argv[1];
+    rcz::Context ctx(0);
+    const bytes txt = load("ref_test.txt");
+    std::mt19937 rng(12345);
+
+    // ------------------------------------------------------------------------------------------ lz4
+    run("lz4::decode fixtures", [&] {
+        for (int i = 1; i <= 9; ++i) {
+            bytes f = load("ref_test.lz4." + std::to_string(i));
+            rcz::lz4::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(f));
+            CHECK(read_to_end(d) == txt);
+            CHECK(d.eof());
+        }
+    });
+    run("lz4::one_byte_at_a_time", [&] {
+        bytes f = load("ref_test.lz4.1");
+        rcz::lz4::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(f));
+        bytes out; uint8_t b;
+        while (d.read(&b, 1) == 1) out.push_back(b);
+        CHECK(d.eof());
+        CHECK(out == txt);
+    });
+    run("lz4::random_byte_lengths", [&] {
+        bytes f = load("ref_test.lz4.1");
+        rcz::lz4::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(f));
+        bytes out, buf(40);
+        for (;;) { size_t want = 1 + rng() % 40; size_t k = d.read(buf.data(), want); if (k == 0) break; out.insert(out.end(), buf.begin(), buf.begin() + (long)k); }
+        CHECK(out == txt);
+    });
+    run("lz4::some_roundtrips", [&] {
+        bytes big; for (int i = 0; i < 300; ++i) big.insert(big.end(), txt.begin(), txt.end());   // > 256 KiB: several raw blocks
+        for (const bytes& input : {lit("test"), lit(""), txt, big}) {
+            rcz::lz4::Encoder<rcz::VecWriter> e{rcz::VecWriter()};
+            e.write(input.data(), input.size());
+            bytes enc = e.finish().v;
+            rcz::lz4::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(enc));
+            CHECK(read_to_end(d) == input);
+        }
+    });
+    run("lz4::decode_block + errors", [&] {
+        bytes f = load("ref_test.lz4.3");
+        uint32_t n = (uint32_t)f[7] | ((uint32_t)f[8] << 8) | ((uint32_t)f[9] << 16) | ((uint32_t)f[10] << 24);
+        bytes out;
+        CHECK(rcz::lz4::decode_block(ctx, f.data() + 11, n, out) == txt.size());
+        CHECK(out == txt);
+        CHECK(rcz::lz4::compression_bound(100) == 120 && rcz::lz4::compression_bound(0x7e000001u) < 0);
+        bytes bad = f; bad[0] ^= 1;                                            // lz4.rs:365: bad magic => InvalidInput
+        rcz::lz4::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(bad));
+        uint8_t b; bool threw = false;
+        try { d.read(&b, 1); } catch (const rcz::io_error& e) { threw = e.kind == rcz::ErrorKind::InvalidInput; }
+        CHECK(threw);
+        bytes cut(f.begin(), f.begin() + 600);                                 // truncated payload => Other "unexpected end of file"
+        rcz::lz4::Decoder<rcz::SliceReader> d2(ctx, rcz::SliceReader(cut));
+        threw = false;
+        try { read_to_end(d2); } catch (const rcz::io_error& e) { threw = e.kind == rcz::ErrorKind::Other; }
+        CHECK(threw);
+    });
+
+    // ------------------------------------------------------------------------------------------ bwt
+    run("bwt::some_roundtrips", [&] {
+        for (const bytes& input : {lit("test"), lit(""), txt}) {
+            rcz::bwt::Encoder<rcz::VecWriter> e(ctx, rcz::VecWriter(), 1 << 10);
+            e.write(input.data(), input.size());
+            bytes enc = e.finish().v;
+            rcz::bwt::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(enc), true);
+            CHECK(read_to_end(d) == input);
+        }
+    });
+    run("bwt::stream golden (SURVEY App. C)", [&] {
+        bytes in = lit("abracadabra");
+        rcz::bwt::Encoder<rcz::VecWriter> e(ctx, rcz::VecWriter(), 1024);
+        e.write(in.data(), in.size());
+        bytes enc = e.finish().v;
+        const uint8_t want[] = {0x00, 0x04, 0x00, 0x00, 0x0b, 0x00, 0x00, 0x00, 'r', 'd', 'a', 'r', 'c', 'a', 'a', 'a', 'a', 'b', 'b', 0x02, 0x00, 0x00, 0x00};
+        CHECK(enc == bytes(want, want + sizeof want));
+        auto lo = rcz::bwt::encode_simple(ctx, in.data(), in.size());
+        CHECK(lo.second == 2 && lo.first == lit("rdarcaaaabb"));
+        CHECK(rcz::bwt::decode_simple(ctx, lo.first.data(), lo.first.size(), lo.second) == in);
+        bytes cut(enc.begin(), enc.begin() + 10);                             // truncated block payload => Other
+        rcz::bwt::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(cut));
+        bool threw = false;
+        try { read_to_end(d); } catch (const rcz::io_error& er) { threw = er.kind == rcz::ErrorKind::Other; }
+        CHECK(threw);
+        bytes cut2(enc.begin(), enc.begin() + 6);                             // truncated length word => clean EOF (App. B #3)
+        rcz::bwt::Decoder<rcz::SliceReader> d2(ctx, rcz::SliceReader(cut2));
+        CHECK(read_to_end(d2).empty());
+    });
+
+    // ------------------------------------------------------------------------------------------ dc
+    run("dc::roundtrips", [&] {
+        for (const bytes& input : {lit("teeesst_dc"), lit(""), txt, lit("../data/test.txt")}) {
+            std::vector<uint32_t> dist = rcz::dc::encode_simple(ctx, input.data(), input.size());
+            CHECK(rcz::dc::decode_simple(ctx, input.size(), dist.data(), dist.size()) == input);
+        }
+    });
+
+    // ------------------------------------------------------------------------------------------ ari
+    run("ari::roundtrips", [&] {
+        for (const bytes& input : {lit("abracadabra"), lit(""), txt}) {
+            rcz::ari::ByteEncoder<rcz::VecWriter> e(ctx, rcz::VecWriter());
+            e.write(input.data(), input.size());
+            bytes enc = e.finish().v;
+            rcz::ari::ByteDecoder<rcz::SliceReader> d(ctx, rcz::SliceReader(enc));
+            CHECK(read_to_end(d) == input);
+        }
+    });
+    run("ari::roundtrips_term", [&] {                                          // two terminated streams back to back (ari/test.rs:52-89)
+        bytes a = lit("abracadabra"), b2(txt.begin(), txt.begin() + 777);
+        rcz::ari::ByteEncoder<rcz::VecWriter> e1(ctx, rcz::VecWriter());
+        e1.write(a.data(), a.size());
+        rcz::ari::ByteEncoder<rcz::VecWriter> e2(ctx, e1.finish());
+        e2.write(b2.data(), b2.size());
+        bytes enc = e2.finish().v;
+        rcz::ari::ByteDecoder<rcz::SliceReader> d1(ctx, rcz::SliceReader(enc));
+        CHECK(read_to_end(d1) == a);
+        rcz::ari::ByteDecoder<rcz::VecReader> d2(ctx, d1.finish());
+        CHECK(read_to_end(d2) == b2);
+    });
+
+    // ------------------------------------------------------------------------------------------ flate
+    auto fixup = [](bytes v) { return bytes(v.begin() + 2, v.end() - 4); };      // flate.rs:504-506
+    run("flate::decode fixtures", [&] {
+        for (int i = 0; i <= 9; ++i) {
+            bytes f = fixup(load("ref_test.z." + std::to_string(i)));
+            rcz::flate::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(f));
+            CHECK(read_to_end(d) == txt);
+        }
+        bytes g = load("ref_test.z.go");
+        rcz::flate::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(g));
+        CHECK(read_to_end(d) == txt);
+    });
+    run("flate::one_byte_at_a_time", [&] {
+        bytes f = fixup(load("ref_test.z.1"));
+        rcz::flate::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(f));
+        CHECK(!d.eof());
+        bytes out; uint8_t b;
+        while (d.read(&b, 1) == 1) out.push_back(b);
+        CHECK(d.eof());
+        CHECK(out == txt);
+    });
+    run("flate::random_byte_lengths", [&] {
+        bytes f = fixup(load("ref_test.z.1"));
+        rcz::flate::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(f));
+        bytes out, buf(40);
+        for (;;) { size_t want = 1 + rng() % 40; size_t k = d.read(buf.data(), want); if (k == 0) break; out.insert(out.end(), buf.begin(), buf.begin() + (long)k); }
+        CHECK(out == txt);
+    });
+    run("flate::zlib framing leaves the trailer unread", [&] {
+        bytes z = load("ref_test.z.5");
+        bytes body(z.begin() + 2, z.end());                                      // DEFLATE data followed by the 4-byte Adler-32
+        rcz::flate::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(body));
+        CHECK(read_to_end(d) == txt);
+        size_t rest = 0; const uint8_t* tail = d.unread(&rest);
+        CHECK(rest == 4 && tail[0] == 0xfb && tail[1] == 0x4f && tail[2] == 0xcf && tail[3] == 0xa6);   // Adler-32(test.txt) = 0xfb4fcfa6
+        bytes bad = fixup(load("ref_test.z.5")); bad[0] |= 0x06;                 // BTYPE 3 => InvalidInput
+        rcz::flate::Decoder<rcz::SliceReader> d2(ctx, rcz::SliceReader(bad));
+        bool threw = false;
+        try { read_to_end(d2); } catch (const rcz::io_error& e) { threw = e.kind == rcz::ErrorKind::InvalidInput && e.detail == RCZ_FL_INVALID_BLOCK_CODE; }
+        CHECK(threw);
+    });
+
+    // ------------------------------------------------------------------------------------------ rle
+    auto rle_enc = [&](const bytes& in) { rcz::rle::Encoder<rcz::VecWriter> e(ctx, rcz::VecWriter()); e.write(in.data(), in.size()); return e.finish().v; };
+    auto rle_dec = [&](const bytes& in) { rcz::rle::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(in)); return read_to_end(d); };
+    run("rle::simple_encoding / long_run_encoding / decoding", [&] {
+        bytes a(5, 20); a.push_back(15);
+        CHECK(rle_enc(a) == (bytes{20, 20, 5 - 2 + 128, 15}));
+        CHECK(rle_dec(bytes{20, 20, 5 - 2 + 128, 15}) == a);
+        CHECK(rle_enc(bytes{0, 0}) == (bytes{0, 0, 128}));
+        bytes c(129, 5);
+        CHECK(rle_enc(c) == (bytes{5, 5, 255}));
+        CHECK(rle_dec(bytes{5, 5, 255}) == c);
+        bytes l{1, 3, 4, 4}; l.insert(l.end(), 2 + 52 + 128, 100);
+        CHECK(rle_enc(l) == (bytes{1, 3, 4, 4, 128, 100, 100, 52, 129}));
+        CHECK(rle_dec(bytes{1, 3, 4, 4, 128, 100, 100, 52, 129}) == l);
+        CHECK(rle_enc(lit("abca123")) == lit("abca123") && rle_enc(lit("")).empty());
+        bool threw = false;
+        bytes over{7, 7, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+        try { rle_dec(over); } catch (const rcz::io_error& e) { threw = e.kind == rcz::ErrorKind::Other && std::string(e.what()) == "Overly long run"; }
+        CHECK(threw);
+    });
+    run("rle::random_roundtrips", [&] {
+        for (int it = 0; it < 20; ++it) {
+            bytes in(13579);
+            for (auto& x : in) x = (uint8_t)(rng() & (it % 2 ? 0xff : 0x03));
+            CHECK(rle_dec(rle_enc(in)) == in);
+        }
+        CHECK(rle_enc(txt).size() == 3084);
+    });
+
+    std::cout << (g_fail ? "FAILED " : "PASSED ") << g_fail << std::endl;
+    return g_fail ? 1 : 0;
+}
