@@ -30,6 +30,14 @@ UNIT = 4 << 20
 COUNT = 256
 
 
+def traffic_for(kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json), else None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(kernel)
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -110,6 +118,14 @@ def make_bwt_decode(rank, nthreads, count=COUNT):
             "name": "bwt::Decoder over %d x 4 MiB random blocks" % count}
 
 
+def config_for(w):
+    """The same `config` object on both arms (ours / --impl reference)."""
+    nb = len(w.get("in_off", w.get("off")))
+    return {"workload": w["name"], "blocks_per_gpu": nb, "block_bytes": UNIT, "compressed_bytes_per_gpu": w["C"],
+            "l2": "inputs larger than L2: %.2f GiB touched per step vs 126 MB L2, no flush needed" % ((w["C"] + w["U"]) / 2**30),
+            "parallelism": "independent blocks, %d per GPU, no data-path collective" % nb}
+
+
 # ------------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
     """The reference's own CPU implementation of the path = oracle/ (C++ restatement; no rustc in this image), all host threads."""
@@ -130,7 +146,7 @@ def run_reference(args):
     gbs = w["U"] / dt / 1e9
     line = {"impl": "reference", "metric": "lz4_decode_uncompressed_GBps", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic", "config": {"workload": w["name"], "blocks": COUNT, "block_bytes": UNIT, "compressed_bytes": w["C"]},
+            "data": "synthetic", "config": config_for(w),
             "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
                              "sample": "all 256 blocks per step, C++ restatement of lz4.rs BlockDecoder::decode, one block per thread"},
             "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -184,6 +200,7 @@ def run_ours(args):
 
         h2d, d2h = int(w["in_off"][-1] + w["in_len"][-1] - w["in_off"][0]), w["U"]
         metric = "lz4_decode_uncompressed_GBps"
+        kernel_name = "lz4_decode_kernel"
     elif args.workload == "bwt_decode":
         w = make_bwt_decode(rank, nthreads, count=args.blocks or 64)
         d_in = torch.from_numpy(w["L"]).cuda()
@@ -201,6 +218,7 @@ def run_ours(args):
 
         h2d, d2h = w["U"], w["U"]
         metric = "bwt_decode_uncompressed_GBps"
+        kernel_name = "ibwt_walk_kernel"
     else:
         raise SystemExit("unknown workload " + args.workload)
 
@@ -227,7 +245,30 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     barrier()
     ms_per_step = max_over_ranks(total_ms / args.steps)
-    kern_ms = float(np.mean(step_ms))
+    # duration of the kernel(s) alone: CUDA events recorded by librcz on the context's stream around its launches
+    kms = []
+    for _ in range(3):
+        step_dev()
+        kms.append(ctx.last_kernel_ms())
+    kern_ms = float(np.mean(kms))
+    step_ms_mean = float(np.mean(step_ms))
+    # final gather of the decoded shards (N > 1): NCCL all-gather over NVLink, timed separately from the decode
+    gather = None
+    if world > 1:
+        flat = torch.empty(w["U"] * world, dtype=torch.uint8, device="cuda")
+        for _ in range(2):
+            dist.all_gather_into_tensor(flat, d_out)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(3):
+            dist.all_gather_into_tensor(flat, d_out)
+        g1.record()
+        torch.cuda.synchronize()
+        gms = max_over_ranks(g0.elapsed_time(g1) / 3)
+        gather = {"collective": "ncclAllGather (uniform shards)", "bytes_per_rank": w["U"], "ms": gms,
+                  "busbw_GBps": w["U"] * (world - 1) / (gms * 1e-3) / 1e9}
+        del flat
     out_len, status = res[0], res[1]
     assert int((status != 0).sum().item() if hasattr(status, "sum") else 0) == 0, "decode reported errors"
     ok = torch.equal(d_out, torch.from_numpy(w["raw"]).cuda())
@@ -252,7 +293,7 @@ def run_ours(args):
         out = np.zeros(w["U"] + 64, dtype=np.uint8)
         t0 = time.perf_counter()
         reps = 0
-        while time.perf_counter() - t0 < 8.0 and reps < 8:
+        while time.perf_counter() - t0 < 12.0 and reps < 12:
             oracle.lz4_decode_blocks_mt(w["packed"], w["in_off"][:nb], w["in_len"][:nb], out, w["out_off"][:nb], w["out_cap"][:nb], 1)
             reps += 1
         dt = (time.perf_counter() - t0) / reps
@@ -266,14 +307,15 @@ def run_ours(args):
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
         line = {"metric": metric, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": w["name"], "blocks_per_gpu": len(w.get("in_off", w.get("off"))), "block_bytes": UNIT, "compressed_bytes_per_gpu": w["C"],
-                           "l2": "inputs larger than L2: %.2f GiB touched per step vs 126 MB L2, no flush needed" % (alg_bytes / 2**30),
-                           "parallelism": "independent blocks, %d per GPU, no data-path collective" % COUNT},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                             "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes, "kernel_ms": kern_ms},
+                "config": config_for(w),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": traffic_for(kernel_name), "kernel": kernel_name, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms, "step_ms_events": step_ms_mean},
                 "cpu_baseline": cpu,
                 "e2e": {"value": world * w["U"] / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},
-                "gpu_launches": launches, "clocks": clocks}
+                "gpu_launches": launches, "clocks": clocks, "host_cores": os.cpu_count()}
+        if gather:
+            line["gather"] = gather
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

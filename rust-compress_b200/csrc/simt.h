@@ -32,6 +32,11 @@ __device__ inline void mbar_expect_tx(rcz_mbar*, unsigned) {}
 __device__ inline void tma_load_1d(void* dst, const void* src, unsigned bytes, rcz_mbar* b) { memcpy(dst, src, bytes); b->v++; }
 __device__ inline void mbar_wait(rcz_mbar* b, unsigned parity) { while ((b->v & 1) == parity) emu::yield(); }
 __device__ inline void fence_proxy_async_smem() {}
+// emulation: the bulk store completes immediately
+__device__ inline void tma_store_1d(void* gdst, const void* ssrc, unsigned bytes) { memcpy(gdst, ssrc, bytes); }
+__device__ inline void bulk_commit() {}
+__device__ inline void bulk_wait_read0() {}
+__device__ inline void bulk_wait0() {}
 __device__ inline void prefetch_l2(const void*, unsigned) {}
 __device__ inline uint4 lds128_volatile(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ inline void sts128_volatile(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
@@ -63,6 +68,16 @@ __device__ __forceinline__ void mbar_wait(rcz_mbar* b, unsigned phase) {
 }
 // generic-proxy accesses to shared memory -> visible/ordered w.r.t. the async proxy (TMA) before re-filling a buffer
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// TMA 1-D bulk store shared -> global (SASS UBLKCP); both addresses 16-byte aligned, bytes a multiple of 16.
+// Writers of the shared source must have executed fence_proxy_async_smem() + a barrier before the issue.
+__device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores of this thread have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all committed bulk stores of this thread are complete (writes performed)
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }

@@ -92,10 +92,22 @@ inline void run_block(unsigned nthreads) {
         for (int i = 1; i <= 6; ++i) p[-i] = nullptr;   // rbp rbx r12 r13 r14 r15
         f.sp = (void*)(p - 6);
     }
+    // Scheduling order of the fibers inside one sweep: RCZ_EMU_ORDER=0 ascending (default), 1 descending, 2 pseudo-random
+    // per sweep.  Kernels must not depend on it; the tests run the dependency-sensitive ones under all three.
+    static const int order_mode = getenv("RCZ_EMU_ORDER") ? atoi(getenv("RCZ_EMU_ORDER")) : 0;
+    static uint64_t lcg = 0x9E3779B97F4A7C15ull;
     unsigned remaining = nthreads;
     while (remaining) {
         unsigned progressed = 0;
-        for (unsigned t = 0; t < nthreads; ++t) {
+        unsigned mul = 1, add = 0;
+        if (order_mode == 2) {                                   // t -> (t * mul + add) mod 2^k is a permutation of a power-of-two range for odd mul
+            lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+            mul = (unsigned)(lcg >> 33) | 1u; add = (unsigned)(lcg >> 13);
+        }
+        unsigned pow2 = 1; while (pow2 < nthreads) pow2 <<= 1;
+        for (unsigned tt = 0; tt < pow2; ++tt) {
+            unsigned t = order_mode == 1 ? pow2 - 1 - tt : order_mode == 2 ? ((tt * mul + add) & (pow2 - 1)) : tt;
+            if (t >= nthreads) continue;
             Fiber& f = s.fibers[t];
             if (f.done) continue;
             s.cur = &f;
