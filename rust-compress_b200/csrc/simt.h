@@ -38,6 +38,7 @@ __device__ inline void bulk_commit() {}
 __device__ inline void bulk_wait_read0() {}
 __device__ inline void bulk_wait0() {}
 __device__ inline void prefetch_l2(const void*, unsigned) {}
+__device__ inline void rcz_backoff(unsigned) {}
 __device__ inline uint4 lds128_volatile(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ inline void sts128_volatile(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
 #else
@@ -78,6 +79,8 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // all committed bulk stores of this thread are complete (writes performed)
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// polling back-off: frees the issue slots of a warp that waits on a flag in shared memory
+__device__ __forceinline__ void rcz_backoff(unsigned ns) { __nanosleep(ns); }
 __device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }

@@ -13,6 +13,31 @@ from util import run_batch
 TXT = golden("ref_test.txt")
 
 
+PERIODS = (1, 2, 3, 4, 5, 7, 13, 31, 32, 33, 255, 256, 300, 32767, 32768, 32769, 50000, 65534, 65535)
+
+
+def _lz4_raw(seqs, tail=b""):
+    """Hand-assembled LZ4 block: [(literals, offset, match_len >= 4)], then a final literal run."""
+    out = bytearray()
+    for lit, off, ml in seqs + [(tail, 0, 0)]:
+        l, m = len(lit), (ml - 4 if ml else 0)
+        out.append((min(l, 15) << 4) | (min(m, 15) if ml else 0))
+        if l >= 15:
+            r = l - 15
+            while r >= 255:
+                out.append(255); r -= 255
+            out.append(r)
+        out += lit
+        if ml:
+            out += bytes([off & 255, off >> 8])
+            if m >= 15:
+                r = m - 15
+                while r >= 255:
+                    out.append(255); r -= 255
+                out.append(r)
+    return bytes(out)
+
+
 def _cases(oracle, gen):
     c = gen.lz4_compress(TXT)
     cases = {
@@ -38,9 +63,20 @@ def _cases(oracle, gen):
         "literal_overrun": ([bytes([0xF0, 0xFF, 0xFF])], [100000]),
         "ends_after_match": ([bytes([0x14, 0x41, 1, 0])], [64]),
     }
-    for per in (1, 2, 3, 4, 5, 7, 13, 255, 256, 65535):     # offsets 1..3 exercise the DECR path (lz4.rs:100-102)
+    for per in PERIODS:     # offsets 1..3 exercise the DECR path (lz4.rs:100-102); large ones the 64 KiB ring reach
         d = (bytes((i * 37 + 11) & 255 for i in range(per)) * (140000 // per + 2))[:140001]
         cases["period_%d" % per] = ([gen.lz4_compress(d)], [len(d)])
+    # matches whose seed is (partly) the sequence's own literals, offsets <, == and > the literal run, overlapping and not
+    rl = random.Random(5)
+    seqs = []
+    for _ in range(600):
+        l = rl.choice([1, 2, 3, 5, 17, 40])
+        off = rl.choice([1, 2, l, max(1, l - 1), l + 1, l + 7]) if seqs else rl.choice([1, l])
+        seqs.append((bytes(rl.randrange(256) for _ in range(l)), off, rl.choice([4, 5, 19, 33, 70, 300])))
+    blk = _lz4_raw(seqs, b"tail!")
+    cases["own_literal_seeds"] = ([blk], [200000])
+    blk = _lz4_raw([(b"ab", 2, 4)] + [(b"", rl.choice([1, 2, 3, 4, 6]), 4) for _ in range(5000)], b"z")
+    cases["many_tiny_sequences"] = ([blk], [40000])
     rnd = random.Random(1)
     for k in range(8):
         bb = bytearray(c)
@@ -53,7 +89,7 @@ def _cases(oracle, gen):
 CASE_NAMES = ["empty", "tiny", "txt_ref_encoder", "txt_liblz4", "txt_liblz4_hc", "zeros_long_match", "zeros_ref_encoder",
               "incompressible_long_literals", "lzsyn_512k", "lzsyn_ref_encoder", "hextext", "runs", "batch_ragged", "output_full",
               "truncated_half", "truncated_1", "offset_zero", "offset_before_start", "literal_overrun", "ends_after_match"] + \
-             ["period_%d" % p for p in (1, 2, 3, 4, 5, 7, 13, 255, 256, 65535)] + ["fuzz_%d" % k for k in range(8)]
+             ["period_%d" % p for p in PERIODS] + ["fuzz_%d" % k for k in range(8)] + ["own_literal_seeds", "many_tiny_sequences"]
 
 
 def _check(ctx, oracle, units, caps, **kw):
