@@ -14,8 +14,8 @@
 //                    cur = P[cur]>>8 until it meets the next sampled row (or END), packing the emitted bytes
 //                    16 at a time into a chain-local scratch slot; over-long chains are split on the fly
 //                    (continuation slots come from an atomic ticket) so no chain is walked twice
-//   E  ibwt_rank     per block: Wyllie pointer jumping over the <= 24 K chain descriptors in shared memory
-//                    (dist and next packed in one 64-bit word) -> output offset of every chain
+//   E  ibwt_rank     per block: Wyllie pointer jumping over the chain descriptors (dist and next packed in one 64-bit
+//                    word, ping-pong arrays that stay L2 resident) -> output offset of every chain
 //   F  ibwt_compact  chain-local bytes -> final positions (coalesced copies)
 //
 // The walk starts at `origin`, emits F[cur] (== L[table[cur]-1], bwt/mod.rs:270-279) per hop, and ends at the END
@@ -32,7 +32,6 @@ constexpr unsigned SUCC_END = 0xFFFFFFFFu;
 constexpr unsigned OFF_INVALID = 0xFFFFFFFFu;
 constexpr unsigned MAX_N = 0xFFFFFEu;     // positions must fit the 24-bit field
 constexpr int RANK_NT = 1024;
-constexpr unsigned RANK_MAX_CHAINS = 24832;   // 8 B each -> 194 KiB of shared memory
 
 struct Blk {
     unsigned long long in_off, out_off, scratch_off;   // bytes
@@ -220,7 +219,7 @@ ibwt_walk_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned total_
 #pragma unroll 1
         for (int it = 0; it < 16; ++it) {
             if (active) {
-                const unsigned e = __ldg(P + cur);
+                const unsigned e = __ldcg(P + cur);             // L2 only: an L1 miss would pull the whole 128-byte line for one 4-byte entry
                 const unsigned byte = e & 255u, nxt = e >> 8;
                 // append to the 16-byte register buffer
                 const unsigned k = count & 15u;
@@ -259,12 +258,11 @@ ibwt_walk_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned total_
 }
 
 // ------------------------------------------------------------------------------------------ E: rank chains
+// node[i] = (distance to END << 32) | next; two arrays per block (ping-pong), one CTA per block.
 __global__ void __launch_bounds__(RANK_NT, 1)
 ibwt_rank_kernel(const Blk* __restrict__ blks, const Desc* __restrict__ desc_base, const unsigned* __restrict__ chain_ctr,
-                 unsigned* __restrict__ chain_off, uint64_t* __restrict__ out_len, int32_t* __restrict__ status) {
-    RCZ_DYN_SMEM(raw);
-    unsigned long long* node = reinterpret_cast<unsigned long long*>(raw);   // (dist << 32) | next
-    volatile unsigned long long* vnode = node;
+                 unsigned long long* __restrict__ node_base, unsigned* __restrict__ chain_off, uint64_t* __restrict__ out_len,
+                 int32_t* __restrict__ status) {
     const unsigned b = blockIdx.x, tid = threadIdx.x;
     const Blk bk = blks[b];
     if (bk.skip) return;
@@ -272,34 +270,44 @@ ibwt_rank_kernel(const Blk* __restrict__ blks, const Desc* __restrict__ desc_bas
     unsigned nch = chain_ctr[b];
     if (nch > bk.max_chains) nch = bk.max_chains;
     const unsigned SENT = nch;                                // absorbing node for END
+    const size_t stride = (size_t)bk.max_chains + 1;
+    unsigned long long* cur = node_base + 2 * ((size_t)bk.chain0 + b);   // 2 * (max_chains + 1) words per block
+    unsigned long long* nxt = cur + stride;
     for (unsigned i = tid; i < nch; i += RANK_NT) {
         const Desc d = desc[i];
         unsigned s = d.succ == SUCC_END ? SENT : d.succ;
         if (s > nch) s = i;                                   // defensive: dangling link becomes a self-loop (never reaches END)
-        node[i] = ((unsigned long long)d.len << 32) | s;
+        cur[i] = ((unsigned long long)d.len << 32) | s;
     }
-    if (tid == 0) node[SENT] = SENT;
+    if (tid == 0) { cur[SENT] = SENT; nxt[SENT] = SENT; }
     __syncthreads();
     unsigned rounds = 2;
     for (unsigned v = nch; v; v >>= 1) ++rounds;
     for (unsigned r = 0; r < rounds; ++r) {
         int pend = 0;
-        for (unsigned i = tid; i < nch; i += RANK_NT) {
-            const unsigned long long a = vnode[i];
-            const unsigned s = (unsigned)a;
-            if (s != SENT) {
-                const unsigned long long q = vnode[s];
-                vnode[i] = (((a >> 32) + (q >> 32)) << 32) | (unsigned)q;
-                pend = 1;
+        for (unsigned i0 = tid; i0 < nch; i0 += RANK_NT * 4) {     // 4 independent node updates in flight per thread
+            unsigned long long a[4], q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const unsigned i = i0 + u * RANK_NT; a[u] = i < nch ? __ldcg(cur + i) : (unsigned long long)SENT; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = (unsigned)a[u] != SENT ? __ldcg(cur + (unsigned)a[u]) : 0ull;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned i = i0 + u * RANK_NT;
+                if (i < nch) {
+                    if ((unsigned)a[u] != SENT) { nxt[i] = (((a[u] >> 32) + (q[u] >> 32)) << 32) | (unsigned)q[u]; pend = 1; }
+                    else nxt[i] = a[u];
+                }
             }
         }
+        unsigned long long* t = cur; cur = nxt; nxt = t;
         if (!__syncthreads_or(pend)) break;
     }
-    const unsigned long long org = node[bk.K];
+    const unsigned long long org = __ldcg(cur + bk.K);
     const unsigned total = (unsigned)(org >> 32);             // the origin chain always reaches END
     unsigned* coff = chain_off + bk.chain0;
     for (unsigned i = tid; i < nch; i += RANK_NT) {
-        const unsigned long long a = node[i];
+        const unsigned long long a = __ldcg(cur + i);
         coff[i] = ((unsigned)a == SENT) ? total - (unsigned)(a >> 32) : OFF_INVALID;
     }
     if (tid == 0) { out_len[b] = total; status[b] = 0; }
@@ -349,43 +357,60 @@ extern "C" int rcz_bwt_decode_blocks(rcz_ctx* c, const void* in_base, const uint
     if (nblocks > 0x3fffffu) return RCZ_E_ARG;
     rt_set_device(c->device);
 
-    // ---- host-side geometry
+    // ---- host-side geometry.  Blocks are processed in GROUPS of <= 16 Mi symbols, one kernel sequence per group: the
+    // group's link tables (4 B / symbol, <= 64 MiB) are written by the partition kernel and walked right away, so the
+    // n dependent random hops per block hit the 126 MB L2 instead of HBM (measured with tools/micro/gather_bench.cu:
+    // ~285 G hops/s for a <= 64 MiB working set vs ~73 G hops/s from HBM).  All offsets in Blk are group-relative and the
+    // workspaces are reused by every group.  RCZ_IBWT_* are tuning overrides for tools/ibwt_sweep.sh.
+    const unsigned tune_slog = getenv("RCZ_IBWT_SLOG") ? (unsigned)atoi(getenv("RCZ_IBWT_SLOG")) : 6u;
+    const unsigned tune_ctas = getenv("RCZ_IBWT_WALK_CTAS") ? (unsigned)atoi(getenv("RCZ_IBWT_WALK_CTAS")) : 2u;
+    const unsigned long long group_syms = getenv("RCZ_IBWT_GROUP_SYMS") ? strtoull(getenv("RCZ_IBWT_GROUP_SYMS"), nullptr, 10) : (1ull << 30);
+    struct Group { size_t b0, b1; unsigned tile0_abs, ntiles; unsigned long long p_elems, scratch_bytes, chains, work; };
     std::vector<Blk> blks(nblocks);
     std::vector<int32_t> hstatus(nblocks, 0);
     std::vector<unsigned> tile2blk;
-    unsigned long long p_elems = 0, scratch_bytes = 0;
-    unsigned long long chains = 0, work = 0;
+    std::vector<Group> groups;
+    Group cur{0, 0, 0, 0, 0, 0, 0, 0};
     for (size_t i = 0; i < nblocks; ++i) {
+        const unsigned long long n = n_arr[i];
+        if (cur.b1 > cur.b0 && cur.p_elems && cur.p_elems + n > group_syms) {
+            groups.push_back(cur);
+            cur = Group{i, i, (unsigned)tile2blk.size(), 0, 0, 0, 0, 0};
+        }
         Blk& b = blks[i];
         memset(&b, 0, sizeof b);
         b.in_off = in_off[i]; b.out_off = out_off[i];
-        const unsigned long long n = n_arr[i];
-        b.tile0 = (unsigned)tile2blk.size();
-        b.chain0 = (unsigned)chains; b.work0 = (unsigned)work;
-        b.p_off = (unsigned)p_elems; b.scratch_off = scratch_bytes;
+        b.tile0 = cur.ntiles;
+        b.chain0 = (unsigned)cur.chains; b.work0 = (unsigned)cur.work;
+        b.p_off = (unsigned)cur.p_elems; b.scratch_off = cur.scratch_bytes;
+        cur.b1 = i + 1;
         if (n == 0 || origin[i] >= n) { b.skip = 1; hstatus[i] = RCZ_E_MALFORMED; continue; }   // bwt/mod.rs:230 index panic
         if (n > MAX_N) { b.skip = 1; hstatus[i] = RCZ_E_UNSUPPORTED; continue; }
         b.n = (unsigned)n; b.origin = origin[i];
-        unsigned slog = 8;
-        while ((n >> slog) > 16384) ++slog;                   // keep <= 16 Ki sampled rows per block
+        unsigned slog = tune_slog;
+        while ((n >> slog) > 65536) ++slog;                   // keep <= 64 Ki sampled rows per block
         b.stride_log2 = slog;
         b.K = (unsigned)((n + (1ull << slog) - 1) >> slog);
         b.cap = 2u << slog;
         b.max_chains = b.K + 1 + (unsigned)(n / b.cap) + 1;   // every row is walked at most once => <= n/cap continuations
-        if (b.max_chains + 1 > RANK_MAX_CHAINS) { b.skip = 1; hstatus[i] = RCZ_E_UNSUPPORTED; continue; }
         b.ntiles = (unsigned)((n + TB - 1) / TB);
-        for (unsigned t = 0; t < b.ntiles; ++t) tile2blk.push_back((unsigned)i);
-        p_elems += (n + 63) & ~63ull;
-        scratch_bytes += (unsigned long long)b.max_chains * b.cap;
-        chains += b.max_chains;
-        work += b.K + 1;
-        if (p_elems > 0xffffffffull || chains > 0xffffffffull) return RCZ_E_ARG;   // split the batch
+        for (unsigned t = 0; t < b.ntiles; ++t) tile2blk.push_back((unsigned)(i - cur.b0));
+        cur.ntiles += b.ntiles;
+        cur.p_elems += (n + 63) & ~63ull;
+        cur.scratch_bytes += (unsigned long long)b.max_chains * b.cap;
+        cur.chains += b.max_chains;
+        cur.work += b.K + 1;
     }
-    const unsigned ntiles = (unsigned)tile2blk.size();
+    groups.push_back(cur);
+    unsigned long long max_p = 0, max_scratch = 0, max_chains = 0; unsigned max_tiles = 0; size_t max_nb = 0;
+    for (auto& g : groups) {
+        max_p = std::max(max_p, g.p_elems); max_scratch = std::max(max_scratch, g.scratch_bytes); max_chains = std::max(max_chains, g.chains);
+        max_tiles = std::max(max_tiles, g.ntiles); max_nb = std::max(max_nb, g.b1 - g.b0);
+    }
 
     DescStager ds(c, mem_kind, nblocks);
     const size_t i_blk = ds.add_in(blks.data(), nblocks * sizeof(Blk));
-    const size_t i_t2b = ds.add_in(tile2blk.data(), (size_t)ntiles * 4);
+    const size_t i_t2b = ds.add_in(tile2blk.data(), tile2blk.size() * 4);
     const size_t i_hst = ds.add_in(hstatus.data(), nblocks * 4);
     const size_t o_len = ds.add_out(out_len, nblocks * 8);
     const size_t o_st = ds.add_out(status, nblocks * 4);
@@ -397,43 +422,41 @@ extern "C" int rcz_bwt_decode_blocks(rcz_ctx* c, const void* in_base, const uint
         st = stage_span_out(c, WS_OUT, out_off, n_arr, nblocks, 1, &dout); if (st) return st;
     }
     void *wP, *wS, *wM;
-    st = ctx_ws(c, WS_A, (size_t)p_elems * 4 + 256, &wP); if (st) return st;
-    st = ctx_ws(c, WS_B, (size_t)scratch_bytes + 256, &wS); if (st) return st;
+    st = ctx_ws(c, WS_A, (size_t)max_p * 4 + 256, &wP); if (st) return st;
+    st = ctx_ws(c, WS_B, (size_t)max_scratch + 256, &wS); if (st) return st;
     // misc: tile_hist | cbase | desc | chain_off | chain_ctr | queue
-    const size_t sz_hist = (size_t)ntiles * 256 * 4, sz_cb = nblocks * 256 * 4, sz_desc = (size_t)chains * 8, sz_coff = (size_t)chains * 4,
-                 sz_ctr = nblocks * 4;
+    const size_t sz_hist = (size_t)max_tiles * 256 * 4, sz_cb = max_nb * 256 * 4, sz_desc = (size_t)max_chains * 8, sz_coff = (size_t)max_chains * 4,
+                 sz_ctr = max_nb * 4, sz_node = ((size_t)max_chains + max_nb) * 16;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    st = ctx_ws(c, WS_C, al(sz_hist) + al(sz_cb) + al(sz_desc) + al(sz_coff) + al(sz_ctr) + 512, &wM); if (st) return st;
+    st = ctx_ws(c, WS_C, al(sz_hist) + al(sz_cb) + al(sz_desc) + al(sz_coff) + al(sz_ctr) + al(sz_node) + 512, &wM); if (st) return st;
     uint8_t* m = (uint8_t*)wM;
     unsigned* tile_hist = (unsigned*)m; m += al(sz_hist);
     unsigned* cbase = (unsigned*)m; m += al(sz_cb);
     Desc* desc = (Desc*)m; m += al(sz_desc);
     unsigned* chain_off = (unsigned*)m; m += al(sz_coff);
     unsigned* chain_ctr = (unsigned*)m; m += al(sz_ctr);
+    unsigned long long* nodes = (unsigned long long*)m; m += al(sz_node);
     unsigned* queue = (unsigned*)m;
 
-    const Blk* dblk = ds.in_ptr<Blk>(i_blk);
-    const unsigned* dt2b = ds.in_ptr<unsigned>(i_t2b);
-    uint64_t* d_len = ds.out_ptr<uint64_t>(o_len);
-    int32_t* d_st = ds.out_ptr<int32_t>(o_st);
-
+    RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(ibwt_scatter_kernel, sizeof(ScatterSmem)));
     st = ctx_timer_begin(c); if (st) return st;
-    RCZ_KLAUNCH(c, ibwt_init_kernel, (unsigned)((nblocks + 255) / 256), 256, 0, dblk, (unsigned)nblocks, chain_ctr, queue, d_len, d_st,
-                ds.in_ptr<int32_t>(i_hst));
-    if (ntiles) {
-        RCZ_KLAUNCH(c, ibwt_hist_kernel, ntiles, NT_TILE, 0, din, dblk, dt2b, tile_hist);
-        RCZ_KLAUNCH(c, ibwt_scan_kernel, (unsigned)nblocks, 256, 0, dblk, tile_hist, cbase);
-        RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(ibwt_scatter_kernel, sizeof(ScatterSmem)));
-        RCZ_KLAUNCH(c, ibwt_scatter_kernel, ntiles, NT_TILE, sizeof(ScatterSmem), din, dblk, dt2b, tile_hist, cbase, (unsigned*)wP);
-        const unsigned walk_grid = (unsigned)std::min<unsigned long long>((work + 255) / 256, (unsigned long long)c->sm_count * 8);
-        RCZ_KLAUNCH(c, ibwt_walk_kernel, walk_grid, 256, 0, dblk, (unsigned)nblocks, (unsigned)work, (const unsigned*)wP, (uint8_t*)wS, desc,
-                    chain_ctr, queue);
-        const size_t rank_smem = (size_t)RANK_MAX_CHAINS * 8;
-        RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(ibwt_rank_kernel, rank_smem));
-        RCZ_KLAUNCH(c, ibwt_rank_kernel, (unsigned)nblocks, RANK_NT, rank_smem, dblk, desc, chain_ctr, chain_off, d_len, d_st);
-        const unsigned cgrid = (unsigned)std::min<unsigned long long>((chains + 7) / 8, (unsigned long long)c->sm_count * 16);
-        RCZ_KLAUNCH(c, ibwt_compact_kernel, cgrid, 256, 0, dblk, (unsigned)nblocks, (unsigned)chains, (const uint8_t*)wS, desc, chain_ctr,
-                    chain_off, dout);
+    for (auto& g : groups) {
+        const unsigned nb = (unsigned)(g.b1 - g.b0);
+        if (nb == 0) continue;
+        const Blk* dblk = ds.in_ptr<Blk>(i_blk) + g.b0;
+        const unsigned* dt2b = ds.in_ptr<unsigned>(i_t2b) + g.tile0_abs;
+        uint64_t* d_len = ds.out_ptr<uint64_t>(o_len) + g.b0;
+        int32_t* d_st = ds.out_ptr<int32_t>(o_st) + g.b0;
+        RCZ_KLAUNCH(c, ibwt_init_kernel, (nb + 255) / 256, 256, 0, dblk, nb, chain_ctr, queue, d_len, d_st, ds.in_ptr<int32_t>(i_hst) + g.b0);
+        if (!g.ntiles) continue;
+        RCZ_KLAUNCH(c, ibwt_hist_kernel, g.ntiles, NT_TILE, 0, din, dblk, dt2b, tile_hist);
+        RCZ_KLAUNCH(c, ibwt_scan_kernel, nb, 256, 0, dblk, tile_hist, cbase);
+        RCZ_KLAUNCH(c, ibwt_scatter_kernel, g.ntiles, NT_TILE, sizeof(ScatterSmem), din, dblk, dt2b, tile_hist, cbase, (unsigned*)wP);
+        const unsigned walk_grid = (unsigned)std::min<unsigned long long>((g.work + 255) / 256, (unsigned long long)c->sm_count * tune_ctas);
+        RCZ_KLAUNCH(c, ibwt_walk_kernel, walk_grid, 256, 0, dblk, nb, (unsigned)g.work, (const unsigned*)wP, (uint8_t*)wS, desc, chain_ctr, queue);
+        RCZ_KLAUNCH(c, ibwt_rank_kernel, nb, RANK_NT, 0, dblk, desc, chain_ctr, nodes, chain_off, d_len, d_st);
+        const unsigned cgrid = (unsigned)std::min<unsigned long long>((g.chains + 7) / 8, (unsigned long long)c->sm_count * 16);
+        RCZ_KLAUNCH(c, ibwt_compact_kernel, cgrid, 256, 0, dblk, nb, (unsigned)g.chains, (const uint8_t*)wS, desc, chain_ctr, chain_off, dout);
     }
     st = ctx_timer_end(c); if (st) return st;
     st = ds.download(); if (st) return st;

@@ -11,6 +11,7 @@ extern "C" int rcz_ctx_create(int device, unsigned flags, rcz_ctx** out) {
     c->device = device;
     if (rt_set_device(device) != 0) { delete c; return RCZ_E_CUDA; }
     rt_sm_count(device, &c->sm_count);
+    if (getenv("RCZ_L2_FETCH")) rt_l2_fetch_granularity(atoi(getenv("RCZ_L2_FETCH")));
     if (rt_stream_create(&c->stream) != 0) { delete c; return RCZ_E_CUDA; }
     c->own_stream = true;
     if (rt_event_create(&c->ev0) != 0 || rt_event_create(&c->ev1) != 0) { delete c; return RCZ_E_CUDA; }

@@ -9,6 +9,7 @@ typedef void* rt_stream_t;
 struct rt_event_emu { int dummy; };
 typedef rt_event_emu* rt_event_t;
 inline int rt_set_device(int) { return 0; }
+inline int rt_l2_fetch_granularity(int) { return 0; }
 inline int rt_device_count(int* n) { *n = 1; return 0; }
 inline int rt_sm_count(int, int* n) { *n = 4; return 0; }
 inline int rt_malloc(void** p, size_t n) { *p = aligned_alloc(256, (n + 255) / 256 * 256 + 256); return *p ? 0 : 2; }
@@ -32,6 +33,8 @@ inline int rt_event_elapsed(float* ms, rt_event_t, rt_event_t) { *ms = 0.f; retu
 typedef cudaStream_t rt_stream_t;
 typedef cudaEvent_t rt_event_t;
 inline int rt_set_device(int d) { return (int)cudaSetDevice(d); }
+// performance hint: DRAM -> L2 fill size for a sector miss (random 4-byte gathers want 32 B, not 64/128 B)
+inline int rt_l2_fetch_granularity(int bytes) { return (int)cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes); }
 inline int rt_device_count(int* n) { return (int)cudaGetDeviceCount(n); }
 inline int rt_sm_count(int d, int* n) { return (int)cudaDeviceGetAttribute(n, cudaDevAttrMultiProcessorCount, d); }
 inline int rt_malloc(void** p, size_t n) { return (int)cudaMalloc(p, n ? n : 256); }
