@@ -22,6 +22,7 @@
 // Malformed input (truncated fields, offset 0, offset before block start — the cases on which the
 // reference panics) yields RCZ_E_MALFORMED for that block.
 #include "rcz_internal.h"
+#include <algorithm>
 
 namespace lz4k {
 
@@ -475,6 +476,85 @@ static int lz4_launch(rcz_ctx* c, const uint8_t* in, const uint64_t* in_off, con
     return ctx_timer_end(c);
 }
 
+// Host-resident buffers, pipelined: the batch is cut into chunks of consecutive blocks; chunk k's compressed bytes go up
+// (stream 0) while chunk k-1 decodes (stream 1) and chunk k-2's output comes down (stream 2), so the call costs about
+// max(H2D, kernel, D2H) instead of their sum.  Host buffers should be pinned (rcz_host_alloc) for the copies to overlap.
+static int lz4_host_pipelined(rcz_ctx* c, DescStager& ds, const void* in_base, const uint64_t* in_off, const uint64_t* in_len, void* out_base,
+                              const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len, int32_t* status, size_t nblocks) {
+    const uint64_t CHUNK_BYTES = getenv("RCZ_LZ4_CHUNK_BYTES") ? strtoull(getenv("RCZ_LZ4_CHUNK_BYTES"), nullptr, 10) : (64ull << 20);   // decoded bytes per chunk
+    std::vector<size_t> cut{0};
+    uint64_t acc = 0;
+    for (size_t i = 0; i < nblocks; ++i) { acc += out_cap[i]; if (acc >= CHUNK_BYTES && i + 1 < nblocks) { cut.push_back(i + 1); acc = 0; } }
+    cut.push_back(nblocks);
+    const size_t nchunks = cut.size() - 1;
+    int st = ctx_aux_streams(c); if (st) return st;
+    st = ctx_events(c, 3 * nchunks); if (st) return st;
+    // device arenas laid out like the host arenas (same offsets), as in the single-shot path
+    const uint8_t* din; uint8_t* dout;
+    {   // stage_span_in without the copy: compute the span, allocate, copy chunk by chunk below
+        uint64_t lo = UINT64_MAX, hi = 0;
+        for (size_t i = 0; i < nblocks; ++i) { if (!in_len[i]) continue; lo = std::min(lo, in_off[i]); hi = std::max(hi, in_off[i] + in_len[i]); }
+        if (lo == UINT64_MAX) { lo = 0; hi = 0; }
+        const uint64_t lo_al = lo & ~(uint64_t)255;
+        void* d; st = ctx_ws(c, WS_IN, (size_t)(hi - lo_al) + 512, &d); if (st) return st;
+        din = (const uint8_t*)d - lo_al;
+    }
+    st = stage_span_out(c, WS_OUT, out_off, out_cap, nblocks, 1, &dout); if (st) return st;
+    void* tk;
+    st = ctx_ws(c, WS_A, 4 * nchunks + 256, &tk); if (st) return st;
+    RCZ_CK(c, rt_memset(tk, 0, 4 * nchunks + 256, c->stream));
+    const size_t smem = sizeof(lz4k::Smem);
+    RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(lz4k::lz4_decode_kernel, smem));
+    uint64_t* d_len = ds.out_ptr<uint64_t>(0); int32_t* d_st = ds.out_ptr<int32_t>(1);
+    for (size_t k = 0; k < nchunks; ++k) {
+        const size_t b0 = cut[k], nb = cut[k + 1] - cut[k];
+        uint64_t lo = UINT64_MAX, hi = 0;
+        for (size_t i = b0; i < b0 + nb; ++i) { if (!in_len[i]) continue; lo = std::min(lo, in_off[i]); hi = std::max(hi, in_off[i] + in_len[i]); }
+        if (lo != UINT64_MAX) RCZ_CK(c, rt_h2d((uint8_t*)din + lo, (const uint8_t*)in_base + lo, (size_t)(hi - lo), c->stream));
+        RCZ_CK(c, rt_event_record(c->events[3 * k], c->stream));
+        const rt_stream_t ks = c->aux[1 + (k & 7)];                // chunk kernels run concurrently: one chunk alone cannot fill the GPU
+        RCZ_CK(c, rt_stream_wait_event(ks, c->events[3 * k]));
+        const size_t grid = nb < (size_t)2 * c->sm_count ? nb : (size_t)2 * c->sm_count;
+        RCZ_LAUNCH(lz4k::lz4_decode_kernel, (unsigned)grid, lz4k::NT, smem, ks, din, ds.in_ptr<uint64_t>(0) + b0, ds.in_ptr<uint64_t>(1) + b0, dout,
+                   ds.in_ptr<uint64_t>(2) + b0, ds.in_ptr<uint64_t>(3) + b0, d_len + b0, d_st + b0, (unsigned)nb, (unsigned*)tk + k);
+        c->launches++;
+        RCZ_CK(c, rt_last_error());
+        RCZ_CK(c, rt_event_record(c->events[3 * k + 1], ks));
+    }
+    // results and output come down on one D2H stream in chunk order; the (tiny) result copy targets a pinned scratch so that
+    // it does not block the host, and the host only waits for it right before it sizes the chunk's output copies
+    void* pin; st = ctx_pinned(c, nblocks * 12 + 64, &pin); if (st) return st;
+    uint64_t* p_len = (uint64_t*)pin; int32_t* p_st = (int32_t*)((uint8_t*)pin + nblocks * 8);
+    const rt_stream_t dsm = c->aux[0];
+    size_t issued = 0;                                          // result copies issued so far
+    auto issue_results = [&](size_t k) -> int {
+        const size_t b0 = cut[k], nb = cut[k + 1] - cut[k];
+        RCZ_CK(c, rt_stream_wait_event(dsm, c->events[3 * k + 1]));
+        RCZ_CK(c, rt_d2h(p_len + b0, d_len + b0, nb * 8, dsm));
+        RCZ_CK(c, rt_d2h(p_st + b0, d_st + b0, nb * 4, dsm));
+        RCZ_CK(c, rt_event_record(c->events[3 * k + 2], dsm));
+        return RCZ_OK;
+    };
+    for (size_t k = 0; k < nchunks; ++k) {
+        while (issued < nchunks && issued <= k + 1) { st = issue_results(issued++); if (st) return st; }   // one chunk ahead
+        RCZ_CK(c, rt_event_sync(c->events[3 * k + 2]));
+        size_t i = cut[k];
+        const size_t e = cut[k + 1];
+        for (size_t q = i; q < e; ++q) { out_len[q] = p_len[q]; status[q] = p_st[q]; }
+        while (i < e) {
+            if (out_len[i] == 0) { ++i; continue; }
+            const uint64_t s = out_off[i]; uint64_t t = s + out_len[i];
+            size_t j = i + 1;
+            while (j < e && (out_len[j] == 0 || out_off[j] == t)) { t += out_len[j]; ++j; }
+            RCZ_CK(c, rt_d2h((uint8_t*)out_base + s, dout + s, (size_t)(t - s), dsm));
+            i = j;
+        }
+    }
+    RCZ_CK(c, rt_stream_sync(dsm));
+    c->ev_valid = false;
+    return RCZ_OK;
+}
+
 extern "C" int rcz_lz4_decode_blocks(rcz_ctx* c, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
                                      void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
                                      uint64_t* out_len, int32_t* status, size_t nblocks, int mem_kind) {
@@ -488,6 +568,8 @@ extern "C" int rcz_lz4_decode_blocks(rcz_ctx* c, const void* in_base, const uint
     ds.add_in(in_off, nblocks * 8); ds.add_in(in_len, nblocks * 8); ds.add_in(out_off, nblocks * 8); ds.add_in(out_cap, nblocks * 8);
     ds.add_out(out_len, nblocks * 8); ds.add_out(status, nblocks * 4);
     int st = ds.upload(); if (st) return st;
+    if (mem_kind == RCZ_MEM_HOST && nblocks >= 8)
+        return lz4_host_pipelined(c, ds, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, nblocks);
     const uint8_t* din = (const uint8_t*)in_base; uint8_t* dout = (uint8_t*)out_base;
     if (mem_kind == RCZ_MEM_HOST) {
         st = stage_span_in(c, WS_IN, in_base, in_off, in_len, nblocks, 1, &din); if (st) return st;

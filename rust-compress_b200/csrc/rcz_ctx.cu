@@ -26,6 +26,8 @@ extern "C" int rcz_ctx_destroy(rcz_ctx* c) {
     for (auto& w : c->ws) if (w.p) rt_free(w.p);
     if (c->pinned) rt_host_free(c->pinned);
     rt_event_destroy(c->ev0); rt_event_destroy(c->ev1);
+    for (auto e : c->events) rt_event_destroy(e);
+    for (int i = 0; i < 9; ++i) if (c->aux[i]) rt_stream_destroy(c->aux[i]);
     if (c->own_stream) rt_stream_destroy(c->stream);
     delete c;
     return RCZ_OK;

@@ -19,6 +19,8 @@ struct rcz_ctx {
     struct { void* p; size_t cap; } ws[WS_COUNT] = {};
     void* pinned = nullptr;
     size_t pinned_cap = 0;
+    rt_stream_t aux[9] = {};          // D2H stream + 8 kernel streams of the pipelined host-buffer path (created on first use)
+    std::vector<rt_event_t> events;   // event pool of the pipelined path
 };
 
 #define RCZ_CK(ctx, expr)                                                                              \
@@ -37,6 +39,15 @@ struct rcz_ctx {
         (ctx)->launches++;                                               \
         RCZ_CK(ctx, rt_last_error());                                    \
     } while (0)
+
+inline int ctx_aux_streams(rcz_ctx* c) {
+    for (int i = 0; i < 9; ++i) if (!c->aux[i]) RCZ_CK(c, rt_stream_create(&c->aux[i]));
+    return RCZ_OK;
+}
+inline int ctx_events(rcz_ctx* c, size_t n) {
+    while (c->events.size() < n) { rt_event_t e; RCZ_CK(c, rt_event_create(&e)); c->events.push_back(e); }
+    return RCZ_OK;
+}
 
 // grow-only device workspace slot
 inline int ctx_ws(rcz_ctx* c, int slot, size_t bytes, void** out) {

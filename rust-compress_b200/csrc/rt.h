@@ -29,6 +29,8 @@ inline int rt_event_create(rt_event_t* e) { *e = nullptr; return 0; }
 inline int rt_event_destroy(rt_event_t) { return 0; }
 inline int rt_event_record(rt_event_t, rt_stream_t) { return 0; }
 inline int rt_event_elapsed(float* ms, rt_event_t, rt_event_t) { *ms = 0.f; return 0; }
+inline int rt_stream_wait_event(rt_stream_t, rt_event_t) { return 0; }
+inline int rt_event_sync(rt_event_t) { return 0; }
 #else
 typedef cudaStream_t rt_stream_t;
 typedef cudaEvent_t rt_event_t;
@@ -54,4 +56,6 @@ inline int rt_event_create(rt_event_t* e) { return (int)cudaEventCreate(e); }
 inline int rt_event_destroy(rt_event_t e) { return (int)cudaEventDestroy(e); }
 inline int rt_event_record(rt_event_t e, rt_stream_t s) { return (int)cudaEventRecord(e, s); }
 inline int rt_event_elapsed(float* ms, rt_event_t a, rt_event_t b) { return (int)cudaEventElapsedTime(ms, a, b); }
+inline int rt_stream_wait_event(rt_stream_t s, rt_event_t e) { return (int)cudaStreamWaitEvent(s, e, 0); }
+inline int rt_event_sync(rt_event_t e) { return (int)cudaEventSynchronize(e); }
 #endif

@@ -116,6 +116,14 @@ def test_lz4_emu_frame_fixtures(emu_ctx, oracle):
         assert got[0] == (0, TXT)
 
 
+def test_lz4_emu_pipelined_host_path(emu_ctx, oracle, gen, monkeypatch):
+    """Host buffers with >= 8 blocks take the chunked H2D / decode / D2H pipeline; small chunks force many of them."""
+    monkeypatch.setenv("RCZ_LZ4_CHUNK_BYTES", "50000")
+    units = [gen.lz4_compress(gen.one("lzsyn", 200 + i, 9000 + 1311 * i)) for i in range(23)] + [b"", bytes([0x10, 0x41, 0, 0, 0])]
+    caps = [9000 + 1311 * i for i in range(23)] + [0, 64]
+    _check(emu_ctx, oracle, units, caps, pad_front=5, gap=3)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("device", [True, False])
 def test_lz4_gpu_cases(gpu_ctx, oracle, gen, device):
@@ -145,6 +153,21 @@ def test_lz4_gpu_4mib_blocks(gpu_ctx, oracle, gen):
     assert bytes(d_out.cpu().numpy()) == raw.tobytes()
     ref_len, ref_st = oracle.lz4_decode_blocks_mt(packed, off, lens, np.zeros(unit * count, np.uint8), out_off, np.full(count, unit, np.uint64), 4)
     assert (ref_st == 0).all() and (ref_len == out_len).all()
+
+
+@pytest.mark.gpu
+def test_lz4_gpu_pipelined_host_path(gpu_ctx, oracle, gen):
+    """64 x 4 MiB blocks from pinned host buffers: 4 pipeline chunks of 64 MiB; bytes equal the generator's."""
+    import torch
+    unit, count = 4 << 20, 64
+    raw = gen.units("lzsyn", gen.unit_seed(2, 0), unit, count)
+    packed, off, lens = gen.lz4_compress_units(raw, unit, count)
+    h_in = torch.from_numpy(packed).pin_memory()
+    h_out = torch.zeros(unit * count + 64, dtype=torch.uint8).pin_memory()
+    out_off = np.arange(count, dtype=np.uint64) * unit
+    out_len, status = gpu_ctx.lz4_decode_blocks(h_in.numpy(), off, lens, h_out.numpy(), out_off, np.full(count, unit, dtype=np.uint64))
+    assert (status == 0).all() and (out_len == unit).all()
+    assert bytes(h_out.numpy()[: unit * count]) == raw.tobytes()
 
 
 @pytest.mark.gpu
