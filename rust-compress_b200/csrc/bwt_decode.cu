@@ -6,7 +6,7 @@
 //
 //   A  ibwt_hist     per 16 Ki-symbol tile: 256-bin histogram of L (Radix::gather, bwt/mod.rs:95-99)
 //   B  ibwt_scan     per block: exclusive scan over symbols and tiles (Radix::accumulate, :102-109)
-//   C  ibwt_scatter  per tile: stable 256-way partition (match_any ranking inside each warp, smem-staged so
+//   C  ibwt_scatter  per tile: stable 256-way partition (ballot-based equal-key ranking inside each warp, smem-staged so
 //                    that every (tile, symbol) run leaves the SM as one contiguous store) ->
 //                    P[slot] = (position-in-L << 8) | symbol, with the `origin`-first rule of :230-236
 //                    (origin's entry is the END marker; the reference stores index+1 and 0)
@@ -14,8 +14,8 @@
 //                    cur = P[cur]>>8 until it meets the next sampled row (or END), packing the emitted bytes
 //                    16 at a time into a chain-local scratch slot; over-long chains are split on the fly
 //                    (continuation slots come from an atomic ticket) so no chain is walked twice
-//   E  ibwt_rank     per block: Wyllie pointer jumping over the chain descriptors (dist and next packed in one 64-bit
-//                    word, ping-pong arrays that stay L2 resident) -> output offset of every chain
+//   E  ibwt_rank     per block: the chain descriptors are ranked by sampled list ranking again (every 16th chain is a
+//                    head; heads are ranked by Wyllie pointer jumping in shared memory) -> output offset of every chain
 //   F  ibwt_compact  chain-local bytes -> final positions (coalesced copies)
 //
 // The walk starts at `origin`, emits F[cur] (== L[table[cur]-1], bwt/mod.rs:270-279) per hop, and ends at the END
@@ -117,7 +117,11 @@ ibwt_scatter_kernel(const uint8_t* __restrict__ in_base, const Blk* __restrict__
     // pass A: per-warp symbol counts
     for (unsigned g = 0; g < WSPAN / 32; ++g) {
         const unsigned i = lo + w * WSPAN + g * 32 + lane;
-        if (i < hi) atomicAdd(&sm.wcnt[w][L[i]], 1u);
+        const bool valid = i < hi;
+        const unsigned s = valid ? (unsigned)L[i] : 0u;
+        const unsigned m = warp_match_u8(s, valid);
+        if (valid && (m & ((1u << lane) - 1u)) == 0) sm.wcnt[w][s] += (unsigned)__popc(m);   // one add per distinct symbol
+        __syncwarp();
     }
     __syncthreads();
     // pass B: exclusive scan over warps (per symbol), then over symbols
@@ -134,12 +138,12 @@ ibwt_scatter_kernel(const uint8_t* __restrict__ in_base, const Blk* __restrict__
         sm.gbase[tid] = cbase[(size_t)bi * 256 + tid] + tile_hist[(size_t)tile * 256 + tid] - sb;
     }
     __syncthreads();
-    // pass C: stable ranking, 32 symbols at a time per warp (match_any groups equal symbols)
+    // pass C: stable ranking, 32 symbols at a time per warp (warp_match_u8 groups equal symbols)
     for (unsigned g = 0; g < WSPAN / 32; ++g) {
         const unsigned i = lo + w * WSPAN + g * 32 + lane;
         const bool valid = i < hi;
-        const unsigned s = valid ? (unsigned)L[i] : 256u + lane;     // invalid lanes get unique keys
-        const unsigned m = __match_any_sync(RCZ_FULL, s);
+        const unsigned s = valid ? (unsigned)L[i] : 0u;
+        const unsigned m = warp_match_u8(s, valid);
         const unsigned r = __popc(m & ((1u << lane) - 1u));
         unsigned base = 0;
         if (valid) base = sm.wcnt[w][s];
@@ -258,80 +262,116 @@ ibwt_walk_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned total_
 }
 
 // ------------------------------------------------------------------------------------------ E: rank chains
-// node[i] = (distance to END << 32) | next; two arrays per block (ping-pong), one CTA per block.
+// Sampled list ranking once more, one level up (one CTA per block): every 16th chain descriptor (and the origin chain) is a
+// HEAD; a head walks the chain list to the next head summing lengths (pass 1), the <= nch/16 + 1 heads are ranked by Wyllie
+// pointer jumping in shared memory ((distance to END << 32) | next head), and a second walk hands every chain its output
+// offset (pass 2).  Work is O(nch) instead of O(nch log nch); the descriptors (8 B each) stay L2 resident.
+constexpr unsigned HEAD_LOG2 = 4;
+constexpr unsigned RANK_MAX_HEADS = 24576;                    // 8 B each in shared memory
+
 __global__ void __launch_bounds__(RANK_NT, 1)
 ibwt_rank_kernel(const Blk* __restrict__ blks, const Desc* __restrict__ desc_base, const unsigned* __restrict__ chain_ctr,
-                 unsigned long long* __restrict__ node_base, unsigned* __restrict__ chain_off, uint64_t* __restrict__ out_len,
-                 int32_t* __restrict__ status) {
+                 unsigned* __restrict__ chain_off, uint64_t* __restrict__ out_len, int32_t* __restrict__ status) {
+    RCZ_DYN_SMEM(raw);
+    unsigned long long* node = reinterpret_cast<unsigned long long*>(raw);
+    volatile unsigned long long* vnode = node;
     const unsigned b = blockIdx.x, tid = threadIdx.x;
     const Blk bk = blks[b];
     if (bk.skip) return;
     const Desc* desc = desc_base + bk.chain0;
+    unsigned* coff = chain_off + bk.chain0;
     unsigned nch = chain_ctr[b];
     if (nch > bk.max_chains) nch = bk.max_chains;
-    const unsigned SENT = nch;                                // absorbing node for END
-    const size_t stride = (size_t)bk.max_chains + 1;
-    unsigned long long* cur = node_base + 2 * ((size_t)bk.chain0 + b);   // 2 * (max_chains + 1) words per block
-    unsigned long long* nxt = cur + stride;
-    for (unsigned i = tid; i < nch; i += RANK_NT) {
-        const Desc d = desc[i];
-        unsigned s = d.succ == SUCC_END ? SENT : d.succ;
-        if (s > nch) s = i;                                   // defensive: dangling link becomes a self-loop (never reaches END)
-        cur[i] = ((unsigned long long)d.len << 32) | s;
-    }
-    if (tid == 0) { cur[SENT] = SENT; nxt[SENT] = SENT; }
-    __syncthreads();
-    unsigned rounds = 2;
-    for (unsigned v = nch; v; v >>= 1) ++rounds;
-    for (unsigned r = 0; r < rounds; ++r) {
-        int pend = 0;
-        for (unsigned i0 = tid; i0 < nch; i0 += RANK_NT * 4) {     // 4 independent node updates in flight per thread
-            unsigned long long a[4], q[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { const unsigned i = i0 + u * RANK_NT; a[u] = i < nch ? __ldcg(cur + i) : (unsigned long long)SENT; }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) q[u] = (unsigned)a[u] != SENT ? __ldcg(cur + (unsigned)a[u]) : 0ull;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const unsigned i = i0 + u * RANK_NT;
-                if (i < nch) {
-                    if ((unsigned)a[u] != SENT) { nxt[i] = (((a[u] >> 32) + (q[u] >> 32)) << 32) | (unsigned)q[u]; pend = 1; }
-                    else nxt[i] = a[u];
-                }
+    const unsigned nreg = (nch + (1u << HEAD_LOG2) - 1) >> HEAD_LOG2;   // heads at chain ids 0, 16, 32, ...
+    const unsigned H = nreg + 1;                                        // + the origin chain (id K); SENT = H
+    const unsigned SENT = H, mask = (1u << HEAD_LOG2) - 1u, K = bk.K;
+    for (unsigned i = tid; i < nch; i += RANK_NT) coff[i] = OFF_INVALID;
+    // ---- pass 1: head -> (length up to the next head, next head)
+    for (unsigned h = tid; h < H; h += RANK_NT) {
+        unsigned cur = h < nreg ? h << HEAD_LOG2 : K;
+        unsigned long long acc = 0;
+        unsigned nxt_head = h;                                          // self-loop unless the walk reaches a head or END
+        if (cur < nch) {
+            for (unsigned steps = 0; steps <= nch; ++steps) {
+                const Desc d = desc[cur];
+                acc += d.len;
+                const unsigned s = d.succ;
+                if (s == SUCC_END) { nxt_head = SENT; break; }
+                if (s >= nch) break;                                    // dangling link: never reaches END
+                if (s == K) { nxt_head = nreg; break; }
+                if ((s & mask) == 0) { nxt_head = s >> HEAD_LOG2; break; }
+                cur = s;
             }
         }
-        unsigned long long* t = cur; cur = nxt; nxt = t;
+        node[h] = (acc << 32) | nxt_head;
+    }
+    if (tid == 0) node[SENT] = SENT;
+    __syncthreads();
+    // ---- Wyllie over the heads
+    unsigned rounds = 2;
+    for (unsigned v = H; v; v >>= 1) ++rounds;
+    for (unsigned r = 0; r < rounds; ++r) {
+        int pend = 0;
+        for (unsigned i = tid; i < H; i += RANK_NT) {
+            const unsigned long long a = vnode[i];
+            const unsigned s = (unsigned)a;
+            if (s != SENT && s != i) {
+                const unsigned long long q = vnode[s];
+                vnode[i] = (((a >> 32) + (q >> 32)) << 32) | (unsigned)q;
+                pend = 1;
+            }
+        }
         if (!__syncthreads_or(pend)) break;
     }
-    const unsigned long long org = __ldcg(cur + bk.K);
-    const unsigned total = (unsigned)(org >> 32);             // the origin chain always reaches END
-    unsigned* coff = chain_off + bk.chain0;
-    for (unsigned i = tid; i < nch; i += RANK_NT) {
-        const unsigned long long a = __ldcg(cur + i);
-        coff[i] = ((unsigned)a == SENT) ? total - (unsigned)(a >> 32) : OFF_INVALID;
+    const unsigned long long org = node[nreg];
+    const unsigned total = (unsigned)org == SENT ? (unsigned)(org >> 32) : 0u;   // the origin chain always reaches END
+    // ---- pass 2: offsets of the chains behind every head that reaches END
+    for (unsigned h = tid; h < H; h += RANK_NT) {
+        const unsigned long long a = node[h];
+        if ((unsigned)a != SENT) continue;
+        unsigned cur = h < nreg ? h << HEAD_LOG2 : K;
+        if (cur >= nch) continue;
+        if (h < nreg && cur == K) continue;                             // the origin chain is walked once, as head `nreg`
+        unsigned off = total - (unsigned)(a >> 32);
+        for (unsigned steps = 0; steps <= nch; ++steps) {
+            const Desc d = desc[cur];
+            coff[cur] = off;
+            off += d.len;
+            const unsigned s = d.succ;
+            if (s == SUCC_END || s >= nch || s == K || (s & mask) == 0) break;
+            cur = s;
+        }
     }
     if (tid == 0) { out_len[b] = total; status[b] = 0; }
 }
 
 // ------------------------------------------------------------------------------------------ F: compact
+// blockIdx.y = block, one warp per chain: lane l moves bytes [4l, 4l+4) of every 128-byte piece (aligned 4-byte loads from
+// the chain slot, byte stores to the arbitrarily aligned final position; neighbouring lanes hit neighbouring bytes)
 __global__ void __launch_bounds__(256)
-ibwt_compact_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned total_chains, const uint8_t* __restrict__ scratch_base,
-                    const Desc* __restrict__ desc_base, const unsigned* __restrict__ chain_ctr, const unsigned* __restrict__ chain_off,
-                    uint8_t* __restrict__ out_base) {
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned wpb = blockDim.x >> 5;
-    for (unsigned g = blockIdx.x * wpb + (threadIdx.x >> 5); g < total_chains; g += gridDim.x * wpb) {
-        unsigned lo = 0, hi = nblocks;
-        while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (blks[mid].chain0 <= g) lo = mid; else hi = mid; }
-        const Blk bk = blks[lo];
-        const unsigned chain = g - bk.chain0;
-        if (bk.skip || chain >= chain_ctr[lo]) continue;
-        const unsigned off = chain_off[g];
+ibwt_compact_kernel(const Blk* __restrict__ blks, const uint8_t* __restrict__ scratch_base, const Desc* __restrict__ desc_base,
+                    const unsigned* __restrict__ chain_ctr, const unsigned* __restrict__ chain_off, uint8_t* __restrict__ out_base) {
+    const unsigned lane = threadIdx.x & 31, wpb = blockDim.x >> 5, b = blockIdx.y;
+    const Blk bk = blks[b];
+    if (bk.skip) return;
+    unsigned nch = chain_ctr[b];
+    if (nch > bk.max_chains) nch = bk.max_chains;
+    const Desc* desc = desc_base + bk.chain0;
+    const unsigned* coff = chain_off + bk.chain0;
+    uint8_t* out = out_base + bk.out_off;
+    for (unsigned g = blockIdx.x * wpb + (threadIdx.x >> 5); g < nch; g += gridDim.x * wpb) {
+        const unsigned off = coff[g];
         if (off == OFF_INVALID) continue;
-        const unsigned len = desc_base[g].len;
-        const uint8_t* src = scratch_base + bk.scratch_off + (size_t)chain * bk.cap;
-        uint8_t* dst = out_base + bk.out_off + off;
-        for (unsigned i = lane; i < len; i += 32) dst[i] = src[i];
+        const unsigned len = desc[g].len;
+        const uint8_t* src = scratch_base + bk.scratch_off + (size_t)g * bk.cap;
+        uint8_t* dst = out + off;
+        for (unsigned base = 4 * lane; base < len; base += 128) {
+            const unsigned v = *reinterpret_cast<const unsigned*>(src + base);
+            dst[base] = (uint8_t)v;
+            if (base + 1 < len) dst[base + 1] = (uint8_t)(v >> 8);
+            if (base + 2 < len) dst[base + 2] = (uint8_t)(v >> 16);
+            if (base + 3 < len) dst[base + 3] = (uint8_t)(v >> 24);
+        }
     }
 }
 
@@ -363,7 +403,7 @@ extern "C" int rcz_bwt_decode_blocks(rcz_ctx* c, const void* in_base, const uint
     // ~285 G hops/s for a <= 64 MiB working set vs ~73 G hops/s from HBM).  All offsets in Blk are group-relative and the
     // workspaces are reused by every group.  RCZ_IBWT_* are tuning overrides for tools/ibwt_sweep.sh.
     const unsigned tune_slog = getenv("RCZ_IBWT_SLOG") ? (unsigned)atoi(getenv("RCZ_IBWT_SLOG")) : 6u;
-    const unsigned tune_ctas = getenv("RCZ_IBWT_WALK_CTAS") ? (unsigned)atoi(getenv("RCZ_IBWT_WALK_CTAS")) : 2u;
+    const unsigned tune_ctas = getenv("RCZ_IBWT_WALK_CTAS") ? (unsigned)atoi(getenv("RCZ_IBWT_WALK_CTAS")) : 4u;
     const unsigned long long group_syms = getenv("RCZ_IBWT_GROUP_SYMS") ? strtoull(getenv("RCZ_IBWT_GROUP_SYMS"), nullptr, 10) : (1ull << 30);
     struct Group { size_t b0, b1; unsigned tile0_abs, ntiles; unsigned long long p_elems, scratch_bytes, chains, work; };
     std::vector<Blk> blks(nblocks);
@@ -393,6 +433,7 @@ extern "C" int rcz_bwt_decode_blocks(rcz_ctx* c, const void* in_base, const uint
         b.K = (unsigned)((n + (1ull << slog) - 1) >> slog);
         b.cap = 2u << slog;
         b.max_chains = b.K + 1 + (unsigned)(n / b.cap) + 1;   // every row is walked at most once => <= n/cap continuations
+        if ((b.max_chains >> HEAD_LOG2) + 2 > RANK_MAX_HEADS) { b.skip = 1; hstatus[i] = RCZ_E_UNSUPPORTED; continue; }
         b.ntiles = (unsigned)((n + TB - 1) / TB);
         for (unsigned t = 0; t < b.ntiles; ++t) tile2blk.push_back((unsigned)(i - cur.b0));
         cur.ntiles += b.ntiles;
@@ -426,19 +467,20 @@ extern "C" int rcz_bwt_decode_blocks(rcz_ctx* c, const void* in_base, const uint
     st = ctx_ws(c, WS_B, (size_t)max_scratch + 256, &wS); if (st) return st;
     // misc: tile_hist | cbase | desc | chain_off | chain_ctr | queue
     const size_t sz_hist = (size_t)max_tiles * 256 * 4, sz_cb = max_nb * 256 * 4, sz_desc = (size_t)max_chains * 8, sz_coff = (size_t)max_chains * 4,
-                 sz_ctr = max_nb * 4, sz_node = ((size_t)max_chains + max_nb) * 16;
+                 sz_ctr = max_nb * 4;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    st = ctx_ws(c, WS_C, al(sz_hist) + al(sz_cb) + al(sz_desc) + al(sz_coff) + al(sz_ctr) + al(sz_node) + 512, &wM); if (st) return st;
+    st = ctx_ws(c, WS_C, al(sz_hist) + al(sz_cb) + al(sz_desc) + al(sz_coff) + al(sz_ctr) + 512, &wM); if (st) return st;
     uint8_t* m = (uint8_t*)wM;
     unsigned* tile_hist = (unsigned*)m; m += al(sz_hist);
     unsigned* cbase = (unsigned*)m; m += al(sz_cb);
     Desc* desc = (Desc*)m; m += al(sz_desc);
     unsigned* chain_off = (unsigned*)m; m += al(sz_coff);
     unsigned* chain_ctr = (unsigned*)m; m += al(sz_ctr);
-    unsigned long long* nodes = (unsigned long long*)m; m += al(sz_node);
     unsigned* queue = (unsigned*)m;
 
     RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(ibwt_scatter_kernel, sizeof(ScatterSmem)));
+    const size_t rank_smem = ((size_t)RANK_MAX_HEADS + 2) * 8;
+    RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(ibwt_rank_kernel, rank_smem));
     st = ctx_timer_begin(c); if (st) return st;
     for (auto& g : groups) {
         const unsigned nb = (unsigned)(g.b1 - g.b0);
@@ -454,9 +496,9 @@ extern "C" int rcz_bwt_decode_blocks(rcz_ctx* c, const void* in_base, const uint
         RCZ_KLAUNCH(c, ibwt_scatter_kernel, g.ntiles, NT_TILE, sizeof(ScatterSmem), din, dblk, dt2b, tile_hist, cbase, (unsigned*)wP);
         const unsigned walk_grid = (unsigned)std::min<unsigned long long>((g.work + 255) / 256, (unsigned long long)c->sm_count * tune_ctas);
         RCZ_KLAUNCH(c, ibwt_walk_kernel, walk_grid, 256, 0, dblk, nb, (unsigned)g.work, (const unsigned*)wP, (uint8_t*)wS, desc, chain_ctr, queue);
-        RCZ_KLAUNCH(c, ibwt_rank_kernel, nb, RANK_NT, 0, dblk, desc, chain_ctr, nodes, chain_off, d_len, d_st);
-        const unsigned cgrid = (unsigned)std::min<unsigned long long>((g.chains + 7) / 8, (unsigned long long)c->sm_count * 16);
-        RCZ_KLAUNCH(c, ibwt_compact_kernel, cgrid, 256, 0, dblk, nb, (unsigned)g.chains, (const uint8_t*)wS, desc, chain_ctr, chain_off, dout);
+        RCZ_KLAUNCH(c, ibwt_rank_kernel, nb, RANK_NT, rank_smem, dblk, desc, chain_ctr, chain_off, d_len, d_st);
+        unsigned cx = (unsigned)std::min<unsigned long long>((g.chains / nb + 7) / 8 + 1, std::max<unsigned long long>(1, (unsigned long long)c->sm_count * 16 / nb));
+        RCZ_KLAUNCH(c, ibwt_compact_kernel, dim3(cx, nb), 256, 0, dblk, (const uint8_t*)wS, desc, chain_ctr, chain_off, dout);
     }
     st = ctx_timer_end(c); if (st) return st;
     st = ds.download(); if (st) return st;

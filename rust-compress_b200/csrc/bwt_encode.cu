@@ -12,7 +12,7 @@
 //   after every round: group heads in the sorted keys give the new ranks; a block whose n keys are all distinct is
 //   finished and its L column / origin are gathered at once.  Random data (BASELINE config 3) finishes in round 0.
 // One radix pass = per-tile digit histogram, per-block exclusive scan, stable 256-way partition per tile
-// (match_any ranking inside each warp, shared-memory staging so every (tile, digit) run leaves as one contiguous
+// (ballot-based equal-key ranking inside each warp, shared-memory staging so every (tile, digit) run leaves as one contiguous
 // store).  No host synchronisation is needed: finished blocks are skipped on the device (state[]), so the whole
 // round schedule can be enqueued blind (DEVICE_ASYNC); the synchronous modes read one counter per round to stop early.
 #include "rcz_internal.h"
@@ -100,8 +100,8 @@ hist_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* __re
     for (unsigned base = lo; base < hi; base += NT) {
         const unsigned i = base + tid;
         const bool valid = i < hi;
-        const unsigned d = valid ? (unsigned)(k[i] >> shift) & 255u : 256u + lane;
-        const unsigned m = __match_any_sync(RCZ_FULL, d);
+        const unsigned d = valid ? (unsigned)(k[i] >> shift) & 255u : 0u;
+        const unsigned m = warp_match_u8(d, valid);
         if (valid && (m & ((1u << lane) - 1u)) == 0) atomicAdd(&hsm[d], (unsigned)__popc(m));
     }
     __syncthreads();
@@ -156,8 +156,8 @@ scatter_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* _
     for (unsigned g = 0; g < WSPAN / 32; ++g) {                                // per-warp digit counts
         const unsigned i = lo + w * WSPAN + g * 32 + lane;
         const bool valid = i < hi;
-        const unsigned d = valid ? (unsigned)(kin[i] >> shift) & 255u : 256u + lane;
-        const unsigned m = __match_any_sync(RCZ_FULL, d);
+        const unsigned d = valid ? (unsigned)(kin[i] >> shift) & 255u : 0u;
+        const unsigned m = warp_match_u8(d, valid);
         if (valid && (m & ((1u << lane) - 1u)) == 0) sm.wcnt[w][d] += (unsigned)__popc(m);
         __syncwarp();
     }
@@ -175,8 +175,8 @@ scatter_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* _
         const bool valid = i < hi;
         const unsigned long long key = valid ? kin[i] : 0ull;
         const unsigned val = valid ? vin[i] : 0u;
-        const unsigned d = valid ? (unsigned)(key >> shift) & 255u : 256u + lane;
-        const unsigned m = __match_any_sync(RCZ_FULL, d);
+        const unsigned d = valid ? (unsigned)(key >> shift) & 255u : 0u;
+        const unsigned m = warp_match_u8(d, valid);
         const unsigned r = __popc(m & ((1u << lane) - 1u));
         unsigned base = 0;
         if (valid) base = sm.wcnt[w][d];

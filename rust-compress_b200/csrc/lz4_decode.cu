@@ -202,16 +202,30 @@ lz4_decode_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restric
                 const uint4 q = *reinterpret_cast<const uint4*>(chunk + j0);
                 const unsigned w4[4] = {q.x, q.y, q.z, q.w};
                 unsigned nx[16];
-                // interior threads: every field of a short token (no 0xF nibble) provably lies inside the window,
-                // so the next-token index is pure arithmetic on the token byte
-                const bool interior = (j0 >= lead) && (j0 + 16 + 17 < lim);
+                // interior threads: the next-token index is arithmetic on the token byte plus at most one 0xFF-continuation
+                // byte per length (one more shared-memory byte load each); anything longer, and every position near the window
+                // or input edge, is decided exactly by next_code()
+                const bool interior = (j0 >= lead) && (j0 + 16 + 20 < lim);
+                const unsigned nb = chunk[j0 + 16];                  // first byte of the next thread's group (16 B of slack)
                 unsigned slowmask = 0;
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
+                    const unsigned j = j0 + k;
                     const unsigned tk = (w4[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+                    const unsigned e1 = k == 15 ? nb : ((w4[(k + 1) >> 2] >> (((k + 1) & 3) * 8)) & 0xffu);
                     const unsigned L = tk >> 4;
-                    nx[k] = j0 + k + 3 + L;
-                    if (L == 15 || (tk & 15u) == 15u) slowmask |= 1u << k;
+                    const bool l15 = L == 15u, m15 = (tk & 15u) == 15u;
+                    const unsigned p = j + 1 + L + (l15 ? 1u + e1 : 0u);      // position of the 2-byte offset
+                    bool slow = l15 && e1 == 255u;
+                    unsigned nxt = p + 2;
+                    if (m15) {
+                        const unsigned ei = p + 2 < (unsigned)CH + 15u ? p + 2 : (unsigned)CH + 15u;
+                        slow |= chunk[ei] == 255u;
+                        nxt += 1;
+                    }
+                    slow |= l15 && nxt >= lim;                                // a long literal run may reach the window / input edge
+                    nx[k] = nxt;
+                    if (slow) slowmask |= 1u << k;
                 }
                 if (!interior) slowmask = 0xffffu;
                 *reinterpret_cast<uint4*>(&sm.nxt1[j0]) = pack8(nx);
@@ -221,7 +235,7 @@ lz4_decode_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restric
                 *reinterpret_cast<uint4*>(&sm.pp[0][j0]) = pack8(nx);
                 *reinterpret_cast<uint4*>(&sm.pp[0][j0 + 8]) = pack8(nx + 8);
 #pragma unroll 1
-                while (slowmask) {                                   // ~12 % of positions: 0xF nibbles, window edges
+                while (slowmask) {                                   // window edges, lengths with two or more continuation bytes
                     const int k = __ffs((int)slowmask) - 1;
                     slowmask &= slowmask - 1;
                     const unsigned j = j0 + k;

@@ -96,6 +96,21 @@ __device__ __forceinline__ void sts128_volatile(void* p, uint4 v) {
 #endif
 
 // ---------------------------------------------------------------------------------------------
+// lanes of the warp that hold the same 8-bit key as this lane (among the lanes with valid == true).  Eight ballots instead
+// of __match_any_sync: constant cost, where MATCH.ANY serialises over the distinct values (~28 of 32 for high-entropy bytes).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned warp_match_u8(unsigned key, bool valid) {
+    unsigned m = __ballot_sync(RCZ_FULL, valid);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const unsigned bit = (key >> b) & 1u;
+        const unsigned bal = __ballot_sync(RCZ_FULL, bit);
+        m &= bit ? bal : ~bal;
+    }
+    return m;
+}
+
+// ---------------------------------------------------------------------------------------------
 // warp / block scans (warp-shuffle prefix scans; the block level goes through one smem array)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned warp_incl_scan_add(unsigned v) {
