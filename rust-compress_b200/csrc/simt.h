@@ -41,6 +41,12 @@ __device__ inline void prefetch_l2(const void*, unsigned) {}
 __device__ inline void rcz_backoff(unsigned) {}
 __device__ inline uint4 lds128_volatile(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ inline void sts128_volatile(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+// shared-memory addresses as values (32-bit shared-window addresses on the device, plain pointers in the emulation)
+typedef uintptr_t rcz_saddr;
+__device__ inline rcz_saddr saddr_of(const void* p) { return (uintptr_t)p; }
+__device__ inline unsigned lds32_volatile(rcz_saddr a) { return *reinterpret_cast<const volatile unsigned*>(a); }
+__device__ inline unsigned lds8_volatile(rcz_saddr a) { return *reinterpret_cast<const volatile uint8_t*>(a); }
+__device__ inline void sts8_volatile(rcz_saddr a, unsigned v) { *reinterpret_cast<volatile uint8_t*>(a) = (uint8_t)v; }
 #else
 struct rcz_mbar { unsigned long long v; };
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -93,6 +99,11 @@ __device__ __forceinline__ uint4 lds128_volatile(const void* p) {
 __device__ __forceinline__ void sts128_volatile(void* p, uint4 v) {
     asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+typedef unsigned rcz_saddr;
+__device__ __forceinline__ rcz_saddr saddr_of(const void* p) { return smem_u32(p); }
+__device__ __forceinline__ unsigned lds32_volatile(rcz_saddr a) { unsigned r; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(r) : "r"(a) : "memory"); return r; }
+__device__ __forceinline__ unsigned lds8_volatile(rcz_saddr a) { unsigned r; asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(r) : "r"(a) : "memory"); return r; }
+__device__ __forceinline__ void sts8_volatile(rcz_saddr a, unsigned v) { asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 #endif
 
 // ---------------------------------------------------------------------------------------------
