@@ -31,6 +31,10 @@
 #include "rcz_internal.h"
 #include <algorithm>
 
+#ifndef RCZ_LZ4_SPLIT
+#define RCZ_LZ4_SPLIT 0
+#endif
+
 namespace lz4k {
 
 constexpr int W = 8192;                    // compressed bytes per window
@@ -45,7 +49,7 @@ constexpr int MT = 512;                    // materialise: threads per CTA (2 CT
 constexpr int TCAP = 8192;                 // materialise: at most this many output bytes per tile (one chunk per thread)
 constexpr int NCH = TCAP / 16;
 constexpr int RING = 73760;                // output ring in shared memory: 64 KiB of history + one tile + 16-byte chunk slack
-constexpr int DCAP = 640;                  // sequence descriptors of a unit staged in shared memory (the rest is read from HBM)
+constexpr int DCAP = 576;                  // sequence descriptors of a unit staged in shared memory (the rest is read from HBM)
 static_assert(RING % 16 == 0 && RING > 65535 + TCAP + 16, "a tile must not overwrite history that its matches can reach");
 
 constexpr unsigned long long CH_VALID = 1ull << 63;
@@ -458,7 +462,7 @@ struct MatSmem {
     __align__(16) uint4 lt[17];                      // lt[k]: low k bytes set
     UnitInfo ui[2];
     uint32_t cmask[NCH + 1];                         // per chunk of the tile: bit i = byte i is final
-    uint16_t sbase[MT];                              // first piece of every sequence of the batch
+    uint16_t sbase[2][MT];                           // first piece of every sequence of the batch: [0] pieces whose sources are final, [1] the others
     unsigned scan[40];
     uint32_t blk, ja_next;
     rcz_mbar barw[2], bard[2];
@@ -468,7 +472,7 @@ __device__ __forceinline__ unsigned ld_gen_u32(uintptr_t a) { return *(volatile 
 __device__ __forceinline__ unsigned ld_gen_u8(uintptr_t a) { return *(volatile const uint8_t*)a; }
 
 struct MatCtx {
-    const SeqEnt* D; const SeqEnt* ds; const uint4* lt; const uint16_t* sbase; uint32_t* cmask;
+    const SeqEnt* D; const SeqEnt* ds; const uint4* lt; uint32_t* cmask;
     const uint8_t* in; uint8_t* outb; uint8_t* ring; rcz_saddr rings, wins;
     unsigned ob, uend, nseq, n, cbase, limw, hb, T0, T1, h, c00, nch, tend;
 };
@@ -497,22 +501,67 @@ __device__ __forceinline__ unsigned chunk_bits(unsigned a, unsigned b, unsigned 
     return ((1u << hi) - 1u) & ~((1u << lo) - 1u);
 }
 
+// Byte-by-byte fetch of a piece (rare, out of line): literals at the very edge of the input (kind 1) and the head of an
+// overlapping match with offset < 16 (kind 3), where byte i of the piece is seed byte ((pos - ms) + i) mod off.
+__device__ __noinline__ uint4 piece_bytes(const MatCtx& k, unsigned kind, unsigned pos, unsigned ms, unsigned doff, uintptr_t gsrc, unsigned d0, unsigned len) {
+    unsigned long long tl = 0, th = 0;
+    unsigned sidx = 0, sro = 0;
+    if (kind == 3) { sidx = (pos - ms) % doff; sro = ring_off(k, ms - doff); }      // ring offset of the seed
+    for (unsigned i = 0; i < len; ++i) {
+        unsigned v;
+        if (kind == 3) {
+            unsigned a = sro + sidx; a = a >= (unsigned)RING ? a - RING : a;
+            v = lds8_volatile(k.rings + a);
+            sidx = sidx + 1 == doff ? 0 : sidx + 1;
+        } else v = ld_gen_u8(gsrc + i);
+        const unsigned bi = d0 + i;
+        if (bi < 8u) tl |= (unsigned long long)v << (8u * bi); else th |= (unsigned long long)v << (8u * (bi - 8u));
+    }
+    uint4 t; t.x = (unsigned)tl; t.y = (unsigned)(tl >> 32); t.z = (unsigned)th; t.w = (unsigned)(th >> 32);
+    return t;
+}
+
+// source distance for byte kk >= off of an overlapping match: the largest whole number of periods that stays inside the
+// periodic region and within 32 KiB (out of line: two integer divisions that the common path must not pay for)
+__device__ __noinline__ unsigned far_back(unsigned kk, unsigned off) {
+    const unsigned mmax = kk / off + 1u, reach = 32768u / off;
+    return (mmax < reach ? mmax : (reach ? reach : 1u)) * off;
+}
+
 // One piece = the part of a literal run or of a match that falls into one 16-byte chunk of the output.  Piece p of the batch
 // belongs to the sequence i with sbase[i] <= p < sbase[i + 1]; its rank there says which part and which chunk.  The piece is
 // fetched with 4-byte loads + funnel shifts (staged compressed window, ring) and OR-ed into the zeroed chunk; per-chunk byte
 // masks order pieces whose source lies inside the tile, and whoever completes a chunk stores its 16 bytes to HBM.
 // All lanes of the warp call it together; lanes with active == false only take part in the votes.
-__device__ __forceinline__ void mat_piece(const MatCtx& k, unsigned j0, unsigned p, bool active) {
+template <bool DEP, bool LIT>
+__device__ __forceinline__ void mat_piece(const MatCtx& k, const uint16_t* sbase, unsigned j0, unsigned p, bool active) {
     constexpr unsigned NOCHK = 0xffffu;
     const unsigned T0 = k.T0, T1 = k.T1, c00 = k.c00;
     unsigned len = 0, d0 = 0, cc = 0, kind = 0, pos = 0, ms = 0, doff = 0, dlit = 0, dS = 0;
     unsigned cA = NOCHK, cB = NOCHK, mA = 0, mB = 0;
     rcz_saddr srcs = 0;
     bool done = !active;
+    // sequence of every lane's piece = last i with sbase[i] <= p.  The lanes hold consecutive pieces, so the warp finds the sequence
+    // of its first piece together (two 16-way probes), loads the 32 bases from there on into registers, and every lane finishes
+    // with a 5-step search through shuffles; a lane whose piece lies beyond those 32 sequences falls back to a binary search.
+    unsigned si;
+    {
+        const unsigned lane = threadIdx.x & 31, pw = __shfl_sync(RCZ_FULL, p, 0);
+        const unsigned blk = (unsigned)__popc(__ballot_sync(RCZ_FULL, sbase[16u * lane] <= pw)) - 1u;
+        const unsigned i0 = 16u * blk + (unsigned)__popc(__ballot_sync(RCZ_FULL, lane < 16u && sbase[16u * blk + (lane & 15u)] <= pw)) - 1u;
+        const unsigned v = i0 + lane < (unsigned)MT ? (unsigned)sbase[i0 + lane] : 0xffffffffu;
+        unsigned lo = 0;
+#pragma unroll
+        for (int st = 16; st > 0; st >>= 1) { const unsigned vm = __shfl_sync(RCZ_FULL, v, (int)(lo + st)); if (vm <= p) lo += st; }
+        si = i0 + lo;
+        if (lo == 31u && si + 1u < (unsigned)MT && sbase[si + 1u] <= p) {
+            unsigned hi = MT; lo = si + 1u;
+            while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (sbase[mid] <= p) lo = mid; else hi = mid; }
+            si = lo;
+        }
+    }
     if (active) {
-        unsigned lo = 0, hi = MT;
-        while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (k.sbase[mid] <= p) lo = mid; else hi = mid; }
-        const unsigned j = j0 + lo, r = p - k.sbase[lo];
+        const unsigned j = j0 + si, r = p - sbase[si];
         const uint4 q = mat_desc(k, j);
         dS = k.ob + q.x; dlit = q.z; doff = q.w; ms = dS + q.y;
         const unsigned send = mat_start(k, j + 1);
@@ -520,10 +569,10 @@ __device__ __forceinline__ void mat_piece(const MatCtx& k, unsigned j0, unsigned
         unsigned nl = 0, ca = 0;
         if (lb > la) { ca = (la - c00) >> 4; nl = ((lb - 1u - c00) >> 4) - ca + 1u; }
         unsigned a, b;
-        if (r < nl) { cc = ca + r; a = la; b = lb; }
+        if (LIT && r < nl) { cc = ca + r; a = la; b = lb; }
         else {                                                                  // match inside the tile (lz4.rs:96-107, cp lz4.rs:131-140)
             a = ms > T0 ? ms : T0; b = send < T1 ? send : T1;
-            cc = ((a - c00) >> 4) + (r - nl); kind = 2;
+            cc = ((a - c00) >> 4) + (LIT ? r - nl : r); kind = 2;
         }
         const unsigned cs = c00 + 16u * cc;                                     // block offset of the chunk's byte 0 (modular)
         if (cc && a < cs) a = cs;                                               // cc == 0: cs may lie below zero, a >= T0 > cs anyway
@@ -539,21 +588,18 @@ __device__ __forceinline__ void mat_piece(const MatCtx& k, unsigned j0, unsigned
             // whole number of periods back, as far as the ring safely reaches, so that long overlapping matches form no
             // chunk-to-chunk chain and never look behind the ring
             unsigned back = doff;
-            if (kk >= doff) {
-                const unsigned mmax = kk / doff + 1u, reach = 32768u / doff;
-                back = (mmax < reach ? mmax : (reach ? reach : 1u)) * doff;
-            }
+            if (kk >= doff) back = far_back(kk, doff);                          // overlapping match (rare): kept out of line, it divides
             if (len > back) {                                                   // fewer than 16 bytes back: offset < 16 at the head of an overlapping match
                 kind = 3;                                                       // periodic: seed [ms - off, ms)
-                if (ms > T0) { x0 = (ms - doff > T0 ? ms - doff : T0) - c00; x1 = ms - c00; }
+                if (DEP && ms > T0) { x0 = (ms - doff > T0 ? ms - doff : T0) - c00; x1 = ms - c00; }
             } else {
                 const unsigned sp = pos - back;                                 // block offset of the first source byte
                 kind = 0;
                 srcs = k.rings + ring_off(k, sp);
-                if (sp + len > T0) { x0 = (sp > T0 ? sp : T0) - c00; x1 = sp + len - c00; }
+                if (DEP && sp + len > T0) { x0 = (sp > T0 ? sp : T0) - c00; x1 = sp + len - c00; }
             }
         }
-        if (x1 > x0) {
+        if (DEP && x1 > x0) {
             cA = x0 >> 4; mA = chunk_bits(x0, x1, cA);
             const unsigned c2 = (x1 - 1u) >> 4;
             if (c2 != cA) { cB = c2; mB = chunk_bits(x0, x1, c2); }
@@ -561,10 +607,12 @@ __device__ __forceinline__ void mat_piece(const MatCtx& k, unsigned j0, unsigned
     }
     while (__any_sync(RCZ_FULL, !done)) {
         bool progressed = false;
-        if (!done) {
-            bool ready = true;
+        bool ready = true;
+        if (DEP && !done) {
             if (cA != NOCHK) ready = (*(volatile uint32_t*)&k.cmask[cA] & mA) == mA;
             if (cB != NOCHK) ready = ready && (*(volatile uint32_t*)&k.cmask[cB] & mB) == mB;
+        }
+        if (!done) {
             if (ready) {
                 uint4 t;
                 if (kind == 0) {
@@ -580,22 +628,7 @@ __device__ __forceinline__ void mat_piece(const MatCtx& k, unsigned j0, unsigned
                         const unsigned sh = (unsigned)(a & 3) * 8u;
                         const unsigned w0 = ld_gen_u32(a0), w1 = ld_gen_u32(a0 + 4), w2 = ld_gen_u32(a0 + 8), w3 = ld_gen_u32(a0 + 12), w4 = ld_gen_u32(a0 + 16);
                         t.x = __funnelshift_r(w0, w1, sh); t.y = __funnelshift_r(w1, w2, sh); t.z = __funnelshift_r(w2, w3, sh); t.w = __funnelshift_r(w3, w4, sh);
-                    } else {                                                    // byte by byte: input edges, periodic matches
-                        unsigned long long tl = 0, th = 0;
-                        unsigned sidx = kind == 3 ? (pos - ms) % doff : 0u;
-                        const unsigned sro = kind == 3 ? ring_off(k, ms - doff) : 0u;       // ring offset of the seed
-                        for (unsigned i = 0; i < len; ++i) {
-                            unsigned v;
-                            if (kind == 3) {                                    // byte i of the piece is seed byte (k0 + i) mod off
-                                unsigned a = sro + sidx; a = a >= (unsigned)RING ? a - RING : a;
-                                v = lds8_volatile(k.rings + a);
-                                sidx = sidx + 1 == doff ? 0 : sidx + 1;
-                            } else v = ld_gen_u8(gsrc + i);
-                            const unsigned bi = d0 + i;
-                            if (bi < 8u) tl |= (unsigned long long)v << (8u * bi); else th |= (unsigned long long)v << (8u * (bi - 8u));
-                        }
-                        t.x = (unsigned)tl; t.y = (unsigned)(tl >> 32); t.z = (unsigned)th; t.w = (unsigned)(th >> 32);
-                    }
+                    } else t = piece_bytes(k, kind, pos, ms, doff, gsrc, d0, len);      // byte by byte (rare): input edges, periodic matches
                 }
                 const uint4 mlo = k.lt[d0], mhi = k.lt[d0 + len];
                 const unsigned cro = ring_off(k, c00 + 16u * cc);
@@ -624,13 +657,11 @@ __device__ __forceinline__ void mat_piece(const MatCtx& k, unsigned j0, unsigned
                 done = true; progressed = true;
             }
         }
-        if (!__any_sync(RCZ_FULL, progressed)) {
 #ifdef RCZ_EMU
-            emu::yield();
+        if (!__any_sync(RCZ_FULL, progressed)) emu::yield();
 #else
-            rcz_backoff(20);
+        (void)progressed;                                                       // no back-off: few warps ever wait here, and a sleep costs more than the producer takes
 #endif
-        }
     }
 }
 
@@ -684,7 +715,7 @@ lz4_mat_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__
         k.hb = (unsigned)((uintptr_t)k.outb & 15);
         k.ring = sm.ring_ + 32;
         k.rings = saddr_of(k.ring);
-        k.lt = sm.lt; k.sbase = sm.sbase; k.cmask = sm.cmask;
+        k.lt = sm.lt; k.cmask = sm.cmask;
         if (tid == 0) { fence_proxy_async_smem(); mat_prefetch(sm, 0, wb, winfo, obase, seqs, k.in, k.n); }
 
         for (unsigned w = 0; w < nw; ++w) {
@@ -743,16 +774,24 @@ lz4_mat_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__
                             const unsigned la = s > k.T0 ? s : k.T0, lb = ms < k.T1 ? ms : k.T1;
                             if (lb > la) cnt = ((lb - 1u - k.c00) >> 4) - ((la - k.c00) >> 4) + 1u;
                             const unsigned ma = ms > k.T0 ? ms : k.T0, mb = send < k.T1 ? send : k.T1;
-                            if (mb > ma) cnt += ((mb - 1u - k.c00) >> 4) - ((ma - k.c00) >> 4) + 1u;
+                            if (mb > ma) {
+                                const unsigned nm = ((mb - 1u - k.c00) >> 4) - ((ma - k.c00) >> 4) + 1u;
+                                cnt += (RCZ_LZ4_SPLIT && mb - k.T0 > q.w) ? nm << 16 : nm;     // a match that may read this tile goes to the second class
+                            }
                             if (send >= k.T1) atomicMax(&sm.ja_next, j);       // the sequence that holds the next tile's first byte
                         }
                     }
+                    // one scan for both classes: low half = pieces with final sources (literals, matches from before the tile)
                     unsigned P;
                     const unsigned base = block_excl_scan_add<MT>(cnt, sm.scan, &P);
-                    sm.sbase[tid] = (uint16_t)base;
+                    sm.sbase[0][tid] = (uint16_t)base; sm.sbase[1][tid] = (uint16_t)(base >> 16);
                     __syncthreads();
-                    for (unsigned p0 = 0; p0 < P; p0 += MT) {
-                        if (p0 + (tid & ~31u) < P) mat_piece(k, j0, p0 + tid, p0 + tid < P);     // warp-uniform
+                    const unsigned Pi = P & 0xffffu, Pd = P >> 16;
+                    // one index space, the pieces that may have to wait last: a warp lies in one class or (one warp per batch) straddles both
+                    for (unsigned p0 = 0; p0 < Pi + Pd; p0 += MT) {
+                        const unsigned pw = p0 + (tid & ~31u), p = p0 + tid;
+                        if (pw < Pi) mat_piece<!RCZ_LZ4_SPLIT, true>(k, sm.sbase[0], j0, p, p < Pi);
+                        if (pw + 32u > Pi && pw < Pi + Pd) mat_piece<true, false>(k, sm.sbase[1], j0, p >= Pi ? p - Pi : 0u, p >= Pi && p < Pi + Pd);
                     }
                     if (!__syncthreads_or(more && j0 + MT < k.nseq)) break;
                 }
