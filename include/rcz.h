@@ -78,6 +78,9 @@ uint64_t rcz_kernel_launches(rcz_ctx* ctx);
 /* device time of the kernels of the most recent batch call, from CUDA events on the context's stream
  * (valid after rcz_ctx_sync or a synchronous call) */
 float rcz_last_kernel_ms(rcz_ctx* ctx);
+/* per-kernel split of the same batch call, for ops that launch several kernels in a row (lz4: parse, scan, materialise):
+ * writes up to `cap` durations in launch order and returns how many stages the call had (0 when it was not timed) */
+int rcz_last_stage_ms(rcz_ctx* ctx, float* ms, int cap);
 /* pinned host memory for staging (cudaMallocHost) */
 int rcz_host_alloc(void** p, size_t bytes);
 int rcz_host_free(void* p);

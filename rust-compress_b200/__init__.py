@@ -101,6 +101,13 @@ class Context:
     def last_kernel_ms(self):
         return float(self._lib.rcz_last_kernel_ms(self._h))
 
+    def last_stage_ms(self):
+        """Per-kernel durations of the most recent multi-kernel batch call (lz4: parse, scan, materialise)."""
+        import ctypes
+        buf = (ctypes.c_float * 4)()
+        n = self._lib.rcz_last_stage_ms(self._h, buf, 4)
+        return [float(buf[i]) for i in range(n)]
+
     def _check(self, st, what):
         if st != OK:
             raise RczError(st, "%s: %s %s" % (what, self._lib.rcz_strerror(st).decode(), self._lib.rcz_last_error(self._h).decode()))

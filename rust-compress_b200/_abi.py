@@ -28,6 +28,7 @@ SIGNATURES = {
     "rcz_last_error": (C.c_char_p, [_P]),
     "rcz_kernel_launches": (C.c_uint64, [_P]),
     "rcz_last_kernel_ms": (C.c_float, [_P]),
+    "rcz_last_stage_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int]),
     "rcz_host_alloc": (_I, [C.POINTER(_P), _SZ]),
     "rcz_host_free": (_I, [_P]),
     "rcz_build_info": (C.c_char_p, []),

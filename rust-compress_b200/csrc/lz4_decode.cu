@@ -260,8 +260,10 @@ lz4_parse_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict
             const unsigned sb = gbase + (unsigned)s * 32u, se = sb + 32u, p = sb + lane;
             unsigned a = TERM | p;
             { TokF t; if (tok_fast(sm, c, p, lim, limq, e_rel, t)) a = t.next; }
+            // pointer doubling inside the segment; a token is >= 3 bytes, so 4 rounds always suffice, and 2 usually do
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
+                if (r >= 2 && !__any_sync(RCZ_FULL, a < se)) break;
                 const unsigned t2 = __shfl_sync(RCZ_FULL, a, (int)(a & 31u));
                 if (a < se) a = t2;                                       // TERM codes are >= 0x8000: never inside the segment
             }
@@ -840,15 +842,19 @@ static int lz4_enqueue(rcz_ctx* c, rt_stream_t stream, const Lz4Dev& d, size_t r
                        const uint2* tk, size_t ntk) {
     using namespace lz4k;
     unsigned* ctr = d.ctr + 2 * range_idx;
+    const bool timed = stream == c->stream;                                  // single-shot path: per-kernel event marks
+    if (timed) { int st = ctx_stage_mark(c, 0); if (st) return st; }
     if (ntk) {
         const size_t g1 = std::min<size_t>(ntk, (size_t)c->sm_count * 4);
         RCZ_LAUNCH(lz4_parse_kernel, (unsigned)g1, PT, sizeof(ParseSmem), stream, din, in_off, in_len, d.wbase, tk, (unsigned)ntk, d.chain, d.winfo, d.seqs, ctr);
         c->launches++;
         RCZ_CK(c, rt_last_error());
     }
+    if (timed) { int st = ctx_stage_mark(c, 1); if (st) return st; }
     RCZ_LAUNCH(lz4_scan_kernel, (unsigned)((nb + 7) / 8), 256, 0, stream, d.wbase, d.nw, out_cap, d.winfo, d.seqs, d.obase, out_len, status, d.blkstate, (unsigned)nb);
     c->launches++;
     RCZ_CK(c, rt_last_error());
+    if (timed) { int st = ctx_stage_mark(c, 2); if (st) return st; }
     if (ntk) {
         const size_t g2 = std::min<size_t>(nb, (size_t)c->sm_count * 2);
         RCZ_LAUNCH(lz4_mat_kernel, (unsigned)g2, MT, sizeof(MatSmem), stream, din, in_off, in_len, dout, out_off, d.wbase, d.nw, (unsigned)nb, d.winfo, d.seqs,
@@ -856,6 +862,7 @@ static int lz4_enqueue(rcz_ctx* c, rt_stream_t stream, const Lz4Dev& d, size_t r
         c->launches++;
         RCZ_CK(c, rt_last_error());
     }
+    if (timed) { int st = ctx_stage_mark(c, 3); if (st) return st; }
     return RCZ_OK;
 }
 

@@ -26,6 +26,7 @@ extern "C" int rcz_ctx_destroy(rcz_ctx* c) {
     for (auto& w : c->ws) if (w.p) rt_free(w.p);
     if (c->pinned) rt_host_free(c->pinned);
     rt_event_destroy(c->ev0); rt_event_destroy(c->ev1);
+    for (auto e : c->stage_ev) if (e) rt_event_destroy(e);
     for (auto e : c->events) rt_event_destroy(e);
     for (int i = 0; i < 9; ++i) if (c->aux[i]) rt_stream_destroy(c->aux[i]);
     if (c->own_stream) rt_stream_destroy(c->stream);
@@ -65,6 +66,17 @@ extern "C" const char* rcz_strerror(int s) {
 
 extern "C" const char* rcz_last_error(rcz_ctx* c) { return c ? c->err : ""; }
 extern "C" uint64_t rcz_kernel_launches(rcz_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int rcz_last_stage_ms(rcz_ctx* c, float* ms, int cap) {
+    if (!c || !ms || !c->ev_valid) return 0;
+    int n = 0;
+    for (int i = 0; i < c->nstage && i < cap; ++i) {
+        float t = 0.f;
+        if (rt_event_elapsed(&t, c->stage_ev[i], c->stage_ev[i + 1]) != 0) break;
+        ms[n++] = t;
+    }
+    return n;
+}
 
 extern "C" float rcz_last_kernel_ms(rcz_ctx* c) {
     if (!c || !c->ev_valid) return -1.f;

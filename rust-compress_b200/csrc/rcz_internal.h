@@ -15,6 +15,8 @@ struct rcz_ctx {
     uint64_t launches = 0;
     rt_event_t ev0 = 0, ev1 = 0;
     bool ev_valid = false;
+    rt_event_t stage_ev[5] = {};      // stage boundaries of the most recent multi-kernel call
+    int nstage = 0;
     char err[256] = {0};
     struct { void* p; size_t cap; } ws[WS_COUNT] = {};
     void* pinned = nullptr;
@@ -70,7 +72,14 @@ inline int ctx_pinned(rcz_ctx* c, size_t bytes, void** out) {
     *out = c->pinned;
     return RCZ_OK;
 }
-inline int ctx_timer_begin(rcz_ctx* c) { c->ev_valid = false; RCZ_CK(c, rt_event_record(c->ev0, c->stream)); return RCZ_OK; }
+inline int ctx_stage_mark(rcz_ctx* c, int i) {      // boundary i of the call's kernel sequence (0 = before the first kernel)
+    if (i > 4) return RCZ_OK;
+    if (!c->stage_ev[i]) RCZ_CK(c, rt_event_create(&c->stage_ev[i]));
+    RCZ_CK(c, rt_event_record(c->stage_ev[i], c->stream));
+    c->nstage = i;
+    return RCZ_OK;
+}
+inline int ctx_timer_begin(rcz_ctx* c) { c->ev_valid = false; c->nstage = 0; RCZ_CK(c, rt_event_record(c->ev0, c->stream)); return RCZ_OK; }
 inline int ctx_timer_end(rcz_ctx* c) { RCZ_CK(c, rt_event_record(c->ev1, c->stream)); c->ev_valid = true; return RCZ_OK; }
 
 // ------------------------------------------------------------------------------------------------
