@@ -185,3 +185,81 @@ def test_lz4_gpu_full_config_roundtrip(gpu_ctx, gen):
     out_len, status = gpu_ctx.lz4_decode_blocks(d_in, off, lens, d_out, out_off, np.full(count, unit, dtype=np.uint64))
     assert (status == 0).all() and (out_len == unit).all()
     assert torch.equal(d_out, d_raw)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Cases aimed at the window-parallel parse (8 KiB windows of compressed bytes, 320-byte halo, look-back chain) and at the
+# ring-buffer materialise kernel (8 KiB tiles, 64 KiB of history): fields that straddle window ends, 0xFF bytes that the
+# speculative parse may take for length extensions, long matches / literal runs that span windows and tiles.
+# ---------------------------------------------------------------------------------------------------------------------
+def _window_cases(oracle, gen):
+    rl = random.Random(11)
+    cases = {}
+    # literal runs of many lengths (also > halo, > window) between compressible stretches: tokens whose fields cross window ends
+    parts = []
+    for i in range(60):
+        parts.append(gen.one("lzsyn", 300 + i, rl.choice([700, 3000, 9000])))
+        parts.append(gen.one("random", 400 + i, rl.choice([1, 14, 15, 16, 270, 300, 330, 500, 8000, 8200, 20000])))
+    d = b"".join(parts)
+    cases["literal_runs_across_windows"] = ([gen.lz4_compress(d)], [len(d)])
+    # a long match whose length extension bytes straddle the end of window 0 at every alignment near it
+    units, caps = [], []
+    for pre in list(range(8150, 8200, 3)) + [16360, 16383, 16384, 16385]:
+        d = gen.one("random", 900 + pre, pre) + bytes(700000 + pre)
+        units.append(gen.lz4_compress(d)); caps.append(len(d))
+    cases["match_extension_across_windows"] = (units, caps)
+    # hand-assembled: literals full of 0xFF (every byte looks like a token with both lengths extended), long and short, with matches
+    # of all sizes in between; several windows long
+    seqs = []
+    for i in range(900):
+        lit = bytes([0xFF]) * rl.choice([0, 1, 2, 15, 16, 33, 254, 255, 256, 300, 700]) + bytes(rl.randrange(256) for _ in range(rl.choice([0, 1, 3])))
+        if not seqs and not lit:
+            lit = b"\xff"
+        have = sum(len(l) + m for l, _, m in seqs) + len(lit)
+        off = rl.choice([1, 2, 3, 15, 16, 17, 255, 4097]) if have > 4097 else 1
+        seqs.append((lit, off, rl.choice([4, 5, 18, 19, 20, 273, 274, 275, 529, 2000])))
+    blk = _lz4_raw(seqs, b"\xff" * 40)
+    cases["ff_literals"] = ([blk], [sum(len(l) + m for l, _, m in seqs) + 40])
+    # many small blocks (also empty ones) in one batch
+    units = [gen.lz4_compress(gen.one("lzsyn", 700 + i, (i * 37) % 2100)) if (i % 9) else b"" for i in range(300)]
+    caps = [(i * 37) % 2100 if (i % 9) else 0 for i in range(300)]
+    cases["many_small_blocks"] = (units, caps)
+    # hexdump text: 9-byte sequences, every match reaches into the current tile (long in-tile dependency chains)
+    d = gen.one("hextext", 5, 700000)
+    cases["hextext_700k"] = ([gen.lz4_compress(d)], [len(d)])
+    # matches of every length class at offsets around the 64 KiB reach of the ring and around the tile size
+    seqs = [(bytes(rl.randrange(256) for _ in range(70000)), 1, 4)]
+    for i in range(3000):
+        seqs.append((bytes(rl.randrange(256) for _ in range(rl.choice([0, 0, 1, 5, 40]))),
+                     rl.choice([65535, 65534, 65520, 65000, 57344, 49152, 40000, 32769, 32768, 32767, 16384, 8193, 8192, 8191, 4096, 100, 17, 16, 15, 8, 4, 1]),
+                     rl.choice([4, 7, 16, 17, 31, 32, 33, 64, 100, 1000, 9000])))
+    blk = _lz4_raw(seqs, b"end")
+    cases["ring_reach"] = ([blk], [sum(len(l) + m for l, _, m in seqs) + 3])
+    # corruptions of a block that spans many windows: status (and bytes when it still decodes) must match the oracle
+    c = gen.lz4_compress(gen.one("lzsyn", 77, 300000))
+    for k in range(12):
+        bb = bytearray(c)
+        for _ in range(2):
+            bb[rl.randrange(len(bb))] = rl.randrange(256)
+        cases["fuzz_multiwindow_%d" % k] = ([bytes(bb), bytes(bb[: rl.randrange(len(bb))])], [300000, 300000])
+    cases["output_full_multiwindow"] = ([c, c, c], [299999, 150000, 8000])
+    return cases
+
+
+WINDOW_CASE_NAMES = ["literal_runs_across_windows", "match_extension_across_windows", "ff_literals", "many_small_blocks", "hextext_700k",
+                     "ring_reach", "output_full_multiwindow"] + ["fuzz_multiwindow_%d" % k for k in range(12)]
+
+
+@pytest.mark.parametrize("name", WINDOW_CASE_NAMES)
+def test_lz4_emu_window_cases(emu_ctx, oracle, gen, name):
+    units, caps = _window_cases(oracle, gen)[name]
+    _check(emu_ctx, oracle, units, caps, pad_front=7, gap=1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("device", [True, False])
+def test_lz4_gpu_window_cases(gpu_ctx, oracle, gen, device):
+    cases = _window_cases(oracle, gen)
+    for name in WINDOW_CASE_NAMES:
+        units, caps = cases[name]
+        _check(gpu_ctx, oracle, units, caps, device=device, pad_front=7, gap=1)
