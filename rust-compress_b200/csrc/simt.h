@@ -39,6 +39,7 @@ __device__ inline void bulk_wait_read0() {}
 __device__ inline void bulk_wait0() {}
 __device__ inline void prefetch_l2(const void*, unsigned) {}
 __device__ inline void rcz_backoff(unsigned) {}
+__device__ inline void rcz_bar_sync(unsigned id, unsigned count) { rcz_named_bar_emu(id, count); }
 __device__ inline uint4 lds128_volatile(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ inline void sts128_volatile(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
 // shared-memory addresses as values (32-bit shared-window addresses on the device, plain pointers in the emulation)
@@ -46,6 +47,7 @@ typedef uintptr_t rcz_saddr;
 __device__ inline rcz_saddr saddr_of(const void* p) { return (uintptr_t)p; }
 __device__ inline unsigned lds32_volatile(rcz_saddr a) { return *reinterpret_cast<const volatile unsigned*>(a); }
 __device__ inline unsigned lds8_volatile(rcz_saddr a) { return *reinterpret_cast<const volatile uint8_t*>(a); }
+__device__ inline unsigned long long lds64_volatile(rcz_saddr a) { return *reinterpret_cast<const volatile unsigned long long*>(a); }
 __device__ inline void sts8_volatile(rcz_saddr a, unsigned v) { *reinterpret_cast<volatile uint8_t*>(a) = (uint8_t)v; }
 #else
 struct rcz_mbar { unsigned long long v; };
@@ -87,6 +89,8 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // polling back-off: frees the issue slots of a warp that waits on a flag in shared memory
 __device__ __forceinline__ void rcz_backoff(unsigned ns) { __nanosleep(ns); }
+// named barrier: `count` threads (a multiple of 32) of the CTA meet on barrier `id` (1..15; 0 is __syncthreads)
+__device__ __forceinline__ void rcz_bar_sync(unsigned id, unsigned count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
@@ -103,6 +107,7 @@ typedef unsigned rcz_saddr;
 __device__ __forceinline__ rcz_saddr saddr_of(const void* p) { return smem_u32(p); }
 __device__ __forceinline__ unsigned lds32_volatile(rcz_saddr a) { unsigned r; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(r) : "r"(a) : "memory"); return r; }
 __device__ __forceinline__ unsigned lds8_volatile(rcz_saddr a) { unsigned r; asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(r) : "r"(a) : "memory"); return r; }
+__device__ __forceinline__ unsigned long long lds64_volatile(rcz_saddr a) { unsigned long long r; asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(r) : "r"(a) : "memory"); return r; }
 __device__ __forceinline__ void sts8_volatile(rcz_saddr a, unsigned v) { asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 #endif
 

@@ -42,6 +42,7 @@ struct State {
     unsigned nthreads = 0;
     unsigned bar_count = 0, bar_gen = 0;
     int bar_or[2] = {0, 0}, bar_cnt[2] = {0, 0};
+    unsigned nb_count[16] = {0}, nb_gen[16] = {0};   // named barriers (bar.sync id, count)
     unsigned char* dyn_smem = nullptr;
     size_t dyn_smem_cap = 0;
     char* stacks = nullptr;
@@ -80,6 +81,7 @@ inline void run_block(unsigned nthreads) {
     }
     s.nthreads = nthreads;
     s.bar_count = 0; s.bar_gen = 0; s.bar_or[0] = s.bar_or[1] = 0; s.bar_cnt[0] = s.bar_cnt[1] = 0;
+    for (int i = 0; i < 16; ++i) { s.nb_count[i] = 0; s.nb_gen[i] = 0; }
     s.fibers.assign(nthreads, Fiber{});
     s.warps.assign((nthreads + 31) / 32, WarpState{});
     for (unsigned t = 0; t < nthreads; ++t) {
@@ -182,6 +184,13 @@ inline void __syncthreads() {
     unsigned g = s.bar_gen;
     if (++s.bar_count == s.nthreads) { s.bar_count = 0; s.bar_or[(g + 1) & 1] = 0; s.bar_cnt[(g + 1) & 1] = 0; ++s.bar_gen; }
     else while (s.bar_gen == g) emu::yield();
+}
+// bar.sync id, count: rendezvous of `count` threads of the CTA on barrier `id`
+inline void rcz_named_bar_emu(unsigned id, unsigned count) {
+    emu::State& s = emu::S();
+    unsigned g = s.nb_gen[id];
+    if (++s.nb_count[id] == count) { s.nb_count[id] = 0; ++s.nb_gen[id]; }
+    else while (s.nb_gen[id] == g) emu::yield();
 }
 inline int __syncthreads_or(int p) {
     emu::State& s = emu::S();
