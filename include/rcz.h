@@ -60,7 +60,13 @@ enum {
     RCZ_FL_INVALID_HUFFMAN_TREE_HEADER = 5,
     RCZ_FL_INVALID_HUFFMAN_CODE = 6,
     RCZ_FL_INVALID_STATIC_SIZE = 7,
-    RCZ_FL_NOT_ENOUGH_BITS = 8
+    RCZ_FL_NOT_ENOUGH_BITS = 8,
+    /* zlib wrapper (zlib.rs:55-117), all InvalidInput */
+    RCZ_ZL_UNSUPPORTED_FORMAT = 16,   /* "unsupported zlib stream format"  zlib.rs:58-63 */
+    RCZ_ZL_UNSUPPORTED_WINDOW = 17,   /* "unsupported zlib window size"    zlib.rs:65-70 */
+    RCZ_ZL_PRESET_DICTIONARY = 18,    /* "unsupported initial dictionary"  zlib.rs:72-77 */
+    RCZ_ZL_BAD_HEADER_CHECKSUM = 19,  /* "invalid zlib header checksum"    zlib.rs:79-84 */
+    RCZ_ZL_BAD_CHECKSUM = 20          /* "invalid checksum on zlib stream" zlib.rs:108-113 */
 };
 
 typedef enum rcz_mem_kind { RCZ_MEM_HOST = 0, RCZ_MEM_DEVICE = 1, RCZ_MEM_DEVICE_ASYNC = 2 } rcz_mem_kind;
@@ -117,6 +123,19 @@ int rcz_flate_decode_streams(rcz_ctx* ctx, const void* in_base, const uint64_t* 
                              void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
                              uint64_t* out_len, uint64_t* in_used, int32_t* status, int32_t* detail,
                              size_t nstreams, int mem_kind);
+
+/* ---------------- zlib.rs + checksum/adler.rs ----------------
+ * rcz_zlib_decode_streams replaces `zlib::Decoder` driven by read_to_end (zlib.rs:55-117): header checks, the DEFLATE
+ * stream to its final block (the inflate kernel), Adler-32 of the output (adler.rs:34-44) against the big-endian
+ * trailer.  detail[i] (optional) = RCZ_ZL_* for the wrapper's own errors, RCZ_FL_* for inflate's; in_used[i] (optional)
+ * = bytes consumed including header and trailer; adler[i] (optional) = checksum of the decoded bytes.
+ * rcz_adler32_streams is `checksum::adler::State32::{feed,result}` over independent byte ranges. */
+int rcz_zlib_decode_streams(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                            void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
+                            uint64_t* out_len, uint64_t* in_used, int32_t* status, int32_t* detail, uint32_t* adler,
+                            size_t nstreams, int mem_kind);
+int rcz_adler32_streams(rcz_ctx* ctx, const void* base, const uint64_t* off, const uint64_t* len, uint32_t* adler,
+                        size_t nstreams, int mem_kind);
 
 /* ---------------- entropy/ari ----------------
  * rcz_ari_encode_streams replaces `ByteEncoder::write` + `finish` (table.rs:203-219 -> ari/mod.rs:117-150,

@@ -222,3 +222,37 @@ extern "C" int orc_flate_decode_streams_mt(const uint8_t* in_base, const uint64_
     for (auto& t : th) t.join();
     return ORC_OK;
 }
+
+// zlib.rs:55-126  zlib::Decoder as driven by read_to_end: two header bytes (validate_header, zlib.rs:55-84), the DEFLATE
+// stream to its final block, then the big-endian Adler-32 of the output (zlib.rs:106-117; checksum/adler.rs:34-44).
+// detail: ORC_ZL_* for the wrapper's own errors, ORC_FL_* when the inner flate::Decoder failed.
+extern "C" uint32_t orc_adler32(const uint8_t* in, size_t n);
+extern "C" int orc_zlib_decode(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* out_len, size_t* consumed,
+                               int* detail, uint32_t* adler) {
+    *out_len = 0;
+    if (consumed) *consumed = 0;
+    if (detail) *detail = ORC_FL_NONE;
+    if (adler) *adler = 1;
+    if (n < 2) return ORC_E_UNEXPECTED_EOF;                                   // read_u8: raw UnexpectedEof
+    const uint8_t cmf = in[0], flg = in[1];
+    int zd = 0;
+    if ((cmf & 0xf) != 0x8) zd = ORC_ZL_UNSUPPORTED_FORMAT;                   // zlib.rs:58-63
+    else if ((cmf & 0xf0) != 0x70) zd = ORC_ZL_UNSUPPORTED_WINDOW;            // zlib.rs:65-70
+    else if (flg & 0x20) zd = ORC_ZL_PRESET_DICTIONARY;                       // zlib.rs:72-77
+    else if ((((unsigned)cmf << 8) + flg) % 31 != 0) zd = ORC_ZL_BAD_HEADER_CHECKSUM;   // zlib.rs:79-84
+    if (zd) { if (detail) *detail = zd; if (consumed) *consumed = 2; return ORC_E_INVALID_INPUT; }
+    size_t got = 0, used = 0; int fd = 0;
+    const int st = orc_flate_decode(in + 2, n - 2, out, cap, &got, &used, &fd);
+    *out_len = got;
+    if (consumed) *consumed = 2 + used;
+    if (st != ORC_OK) { if (detail) *detail = fd; return st; }
+    const uint32_t a = orc_adler32(out, got);
+    if (adler) *adler = a;
+    if (n - 2 - used < 4) return ORC_E_UNEXPECTED_EOF;                        // read_u32::<BigEndian>
+    const uint8_t* t = in + 2 + used;
+    const uint32_t ck = ((uint32_t)t[0] << 24) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 8) | t[3];
+    if (consumed) *consumed = 2 + used + 4;
+    if (ck != a) { if (detail) *detail = ORC_ZL_BAD_CHECKSUM; return ORC_E_INVALID_INPUT; }   // zlib.rs:108-113
+    return ORC_OK;
+}
+

@@ -45,6 +45,12 @@ enum {
     ORC_FL_INVALID_HUFFMAN_CODE = 6,
     ORC_FL_INVALID_STATIC_SIZE = 7,
     ORC_FL_NOT_ENOUGH_BITS = 8,
+    /* zlib.rs:55-117 wrapper errors (all io::ErrorKind::InvalidInput) */
+    ORC_ZL_UNSUPPORTED_FORMAT = 16,
+    ORC_ZL_UNSUPPORTED_WINDOW = 17,
+    ORC_ZL_PRESET_DICTIONARY = 18,
+    ORC_ZL_BAD_HEADER_CHECKSUM = 19,
+    ORC_ZL_BAD_CHECKSUM = 20,
 };
 
 /* ---- rle.rs ---- */
@@ -96,6 +102,9 @@ int orc_flate_decode(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size
 int orc_flate_decode_blocks(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* out_len,
                             size_t* consumed, int* detail, uint32_t* blk_sizes, size_t blk_cap,
                             size_t* nblk);
+/* ---- zlib.rs (header + flate + Adler-32 trailer) ---- */
+int orc_zlib_decode(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* out_len, size_t* consumed,
+                    int* detail, uint32_t* adler);
 int orc_flate_decode_streams_mt(const uint8_t* in_base, const uint64_t* in_off, const uint64_t* in_len,
                                 uint8_t* out_base, const uint64_t* out_off, const uint64_t* out_cap,
                                 uint64_t* out_len, int32_t* status, size_t nstreams, int nthreads);

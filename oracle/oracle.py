@@ -190,6 +190,16 @@ def flate_decode(data, cap, blocks=False):
     return res
 
 
+def zlib_decode(data, cap):
+    """zlib::Decoder read_to_end: returns (status, bytes, consumed, detail, adler32 of the output)."""
+    a, pa = _u8(data)
+    out = np.empty(max(cap, 1), dtype=np.uint8)
+    n, used, detail, ad = C.c_size_t(0), C.c_size_t(0), C.c_int(0), C.c_uint32(0)
+    st = lib().orc_zlib_decode(pa, C.c_size_t(a.size), out.ctypes.data_as(C.c_void_p), C.c_size_t(cap), C.byref(n), C.byref(used),
+                               C.byref(detail), C.byref(ad))
+    return st, out[: n.value].tobytes(), used.value, detail.value, ad.value
+
+
 def ari_encode(data):
     st, out, n = _simple(lib().orc_ari_encode, data, 2 * len(data) + 64)
     assert st == OK

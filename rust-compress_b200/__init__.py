@@ -171,6 +171,26 @@ class Context:
         self._check(st, "rcz_flate_decode_streams")
         return out_len, status, in_used, detail
 
+    # ---- zlib (zlib.rs + checksum/adler.rs) -------------------------------------------------------------------
+    def zlib_decode_streams(self, in_buf, in_off, in_len, out_buf, out_off, out_cap, async_=False):
+        """rcz_zlib_decode_streams.  Returns (out_len, status, in_used, detail, adler) arrays."""
+        kind, n, (io, il, oo, oc), out_len, status, (in_used, detail, adler) = self._batch(
+            None, "zlib", in_buf, in_off, in_len, out_buf, out_off, out_cap, extra_out=(np.uint64, np.int32, np.uint32), async_=async_)
+        st = self._lib.rcz_zlib_decode_streams(self._h, _ptr(in_buf), _ptr(io), _ptr(il), _ptr(out_buf), _ptr(oo), _ptr(oc),
+                                               _ptr(out_len), _ptr(in_used), _ptr(status), _ptr(detail), _ptr(adler), n, kind)
+        self._check(st, "rcz_zlib_decode_streams")
+        return out_len, status, in_used, detail, adler
+
+    def adler32_streams(self, buf, off, length, async_=False):
+        """rcz_adler32_streams: Adler-32 of every byte range."""
+        kind = _kind_of(buf, async_)
+        n = len(off)
+        o, l = map(_u64, (off, length))
+        (adler,) = self._results(kind, n, buf, [np.uint32])
+        st = self._lib.rcz_adler32_streams(self._h, _ptr(buf), _ptr(o), _ptr(l), _ptr(adler), n, kind)
+        self._check(st, "rcz_adler32_streams")
+        return adler
+
     # ---- ari -----------------------------------------------------------------------------------------------
     def ari_encode_streams(self, in_buf, in_off, in_len, out_buf, out_off, out_cap, async_=False):
         kind, n, (io, il, oo, oc), out_len, status, _ = self._batch(None, "ari", in_buf, in_off, in_len, out_buf, out_off, out_cap, async_=async_)

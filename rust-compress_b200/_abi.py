@@ -37,6 +37,8 @@ SIGNATURES = {
     "rcz_bwt_decode_blocks": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I]),
     "rcz_bwt_encode_blocks": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I]),
     "rcz_flate_decode_streams": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I]),
+    "rcz_zlib_decode_streams": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I]),
+    "rcz_adler32_streams": (_I, [_P, _P, _P, _P, _P, _SZ, _I]),
     "rcz_ari_encode_streams": (_I, _BATCH),
     "rcz_ari_decode_streams": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I]),
     "rcz_dc_encode_blocks": (_I, _BATCH),

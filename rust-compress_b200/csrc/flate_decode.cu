@@ -360,3 +360,149 @@ extern "C" int rcz_flate_decode_streams(rcz_ctx* c, const void* in_base, const u
     }
     return RCZ_OK;
 }
+
+// ======================================================================================================
+// zlib wrapper: zlib.rs:55-117 header checks + the inflate kernel above + Adler-32
+// (checksum/adler.rs:34-44) of the output against the big-endian trailer.
+// ======================================================================================================
+namespace zlk {
+
+constexpr unsigned MOD_ADLER = 65521u;   // adler.rs:18
+constexpr int NT = 256, WPB = NT / 32;
+
+// Adler-32 of p[0..n) by one warp.  a = 1 + sum(b_i), b = n + sum((n - i) * b_i) (mod 65521): the serial recurrence of
+// adler.rs:34-39 in closed form, so chunks of 4096 bytes reduce independently (warp-shuffle sums) and fold with their offset.
+__device__ __forceinline__ unsigned warp_adler32(const uint8_t* __restrict__ p, unsigned long long n) {
+    const unsigned lane = threadIdx.x & 31;
+    unsigned long long S1 = 0, S2 = 0;                                // sum b_i, sum i * b_i (mod 65521)
+    for (unsigned long long g = 0; g < n; g += 4096) {
+        const unsigned m = n - g < 4096 ? (unsigned)(n - g) : 4096u;
+        unsigned s1 = 0, s2 = 0;
+        for (unsigned j = lane; j < m; j += 32) { const unsigned b = p[g + j]; s1 += b; s2 += j * b; }
+        s1 = warp_reduce_add(s1); s2 = warp_reduce_add(s2);           // <= 4096 * 255 and < 2^31.1: no overflow
+        S2 = (S2 + (g % MOD_ADLER) * (unsigned long long)(s1 % MOD_ADLER) + s2) % MOD_ADLER;
+        S1 = (S1 + s1) % MOD_ADLER;
+    }
+    const unsigned long long nm = n % MOD_ADLER;
+    const unsigned a = (unsigned)((1 + S1) % MOD_ADLER);
+    const unsigned b = (unsigned)((nm + nm * S1 + MOD_ADLER - S2) % MOD_ADLER);
+    return (b << 16) | a;                                             // adler.rs:42-44
+}
+
+__global__ void __launch_bounds__(NT)
+adler32_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, const uint64_t* __restrict__ len, uint32_t* __restrict__ out, unsigned n) {
+    const unsigned lane = threadIdx.x & 31;
+    for (unsigned i = blockIdx.x * WPB + (threadIdx.x >> 5); i < n; i += gridDim.x * WPB) {
+        const unsigned v = warp_adler32(base + off[i], len[i]);
+        if (lane == 0) out[i] = v;
+    }
+}
+
+// one warp per stream, after inflate ran on bytes [2, n): header checks first (zlib.rs:55-84), then inflate's own outcome, then
+// the trailer (zlib.rs:106-117)
+__global__ void __launch_bounds__(NT)
+zlib_finish_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ in_len,
+                   const uint8_t* __restrict__ out_base, const uint64_t* __restrict__ out_off, uint64_t* __restrict__ out_len,
+                   const uint64_t* __restrict__ used_fl, uint64_t* __restrict__ in_used, int32_t* __restrict__ status, int32_t* __restrict__ detail,
+                   uint32_t* __restrict__ adler, unsigned n) {
+    const unsigned lane = threadIdx.x & 31;
+    for (unsigned i = blockIdx.x * WPB + (threadIdx.x >> 5); i < n; i += gridDim.x * WPB) {
+        const uint8_t* in = in_base + in_off[i];
+        const unsigned long long len = in_len[i];
+        int st = status[i], det = detail[i];
+        unsigned long long used = 0, olen = out_len[i];
+        unsigned ad = 1;
+        if (len < 2) { st = RCZ_E_UNEXPECTED_EOF; det = RCZ_FL_NONE; olen = 0; used = 0; }      // read_u8 on an empty reader
+        else {
+            const unsigned cmf = in[0], flg = in[1];
+            int zd = 0;
+            if ((cmf & 0xf) != 0x8) zd = RCZ_ZL_UNSUPPORTED_FORMAT;
+            else if ((cmf & 0xf0) != 0x70) zd = RCZ_ZL_UNSUPPORTED_WINDOW;
+            else if (flg & 0x20) zd = RCZ_ZL_PRESET_DICTIONARY;
+            else if (((cmf << 8) + flg) % 31 != 0) zd = RCZ_ZL_BAD_HEADER_CHECKSUM;
+            if (zd) { st = RCZ_E_INVALID_INPUT; det = zd; olen = 0; used = 2; }
+            else {
+                used = 2 + used_fl[i];
+                if (st == RCZ_OK) {
+                    ad = warp_adler32(out_base + out_off[i], olen);
+                    if (len - used < 4) st = RCZ_E_UNEXPECTED_EOF;                                  // read_u32::<BigEndian>
+                    else {
+                        const uint8_t* t = in + used;
+                        const unsigned ck = ((unsigned)t[0] << 24) | ((unsigned)t[1] << 16) | ((unsigned)t[2] << 8) | t[3];
+                        used += 4;
+                        if (ck != ad) { st = RCZ_E_INVALID_INPUT; det = RCZ_ZL_BAD_CHECKSUM; }
+                    }
+                }
+            }
+        }
+        if (lane == 0) { status[i] = st; detail[i] = det; out_len[i] = olen; if (in_used) in_used[i] = used; if (adler) adler[i] = ad; }
+    }
+}
+
+}  // namespace zlk
+
+extern "C" int rcz_adler32_streams(rcz_ctx* c, const void* base, const uint64_t* off, const uint64_t* len, uint32_t* adler, size_t n, int mem_kind) {
+    if (!c || rcz_bad_kind(mem_kind)) return RCZ_E_ARG;
+    if (n == 0) return RCZ_OK;
+    if (!base || !off || !len || !adler || n > 0x7fffffffu) return RCZ_E_ARG;
+    rt_set_device(c->device);
+    DescStager ds(c, mem_kind, n);
+    ds.add_in(off, n * 8); ds.add_in(len, n * 8);
+    ds.add_out(adler, n * 4);
+    int st = ds.upload(); if (st) return st;
+    const uint8_t* d = (const uint8_t*)base;
+    if (mem_kind == RCZ_MEM_HOST) { st = stage_span_in(c, WS_IN, base, off, len, n, 1, &d); if (st) return st; }
+    const unsigned grid = (unsigned)std::min<size_t>((n + zlk::WPB - 1) / zlk::WPB, (size_t)c->sm_count * 8);
+    st = ctx_timer_begin(c); if (st) return st;
+    RCZ_KLAUNCH(c, zlk::adler32_kernel, grid, zlk::NT, 0, d, ds.in_ptr<uint64_t>(0), ds.in_ptr<uint64_t>(1), ds.out_ptr<uint32_t>(0), (unsigned)n);
+    st = ctx_timer_end(c); if (st) return st;
+    return ds.download();
+}
+
+extern "C" int rcz_zlib_decode_streams(rcz_ctx* c, const void* in_base, const uint64_t* in_off, const uint64_t* in_len, void* out_base,
+                                       const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len, uint64_t* in_used,
+                                       int32_t* status, int32_t* detail, uint32_t* adler, size_t n, int mem_kind) {
+    if (!c || rcz_bad_kind(mem_kind)) return RCZ_E_ARG;
+    if (n == 0) return RCZ_OK;
+    if (!in_base || !in_off || !in_len || !out_base || !out_off || !out_cap || !out_len || !status || n > 0x7fffffffu) return RCZ_E_ARG;
+    rt_set_device(c->device);
+    for (size_t i = 0; i < n; ++i) if (in_len[i] >= (1ull << 31)) return RCZ_E_ARG;
+    // the DEFLATE stream starts after the two header bytes (zlib.rs:55-57)
+    std::vector<uint64_t> off2(n), len2(n);
+    for (size_t i = 0; i < n; ++i) { const uint64_t h = in_len[i] < 2 ? in_len[i] : 2; off2[i] = in_off[i] + h; len2[i] = in_len[i] - h; }
+    DescStager ds(c, mem_kind, n);
+    ds.add_in(in_off, n * 8); ds.add_in(in_len, n * 8); ds.add_in(out_off, n * 8); ds.add_in(out_cap, n * 8);
+    const size_t i_off2 = ds.add_in(off2.data(), n * 8), i_len2 = ds.add_in(len2.data(), n * 8);
+    ds.add_out(out_len, n * 8); ds.add_out(status, n * 4);
+    const size_t o_used = ds.add_out(in_used, in_used ? n * 8 : 0);
+    const size_t o_det = ds.add_out(detail, detail ? n * 4 : 0);
+    const size_t o_ad = ds.add_out(adler, adler ? n * 4 : 0);
+    int st = ds.upload(); if (st) return st;
+    // inflate's own bookkeeping, and the optional outputs the caller did not ask for
+    void* scr; st = ctx_ws(c, WS_B, n * 16 + 64, &scr); if (st) return st;
+    uint64_t* d_used_fl = (uint64_t*)scr;
+    int32_t* d_det = detail ? ds.out_ptr<int32_t>(o_det) : (int32_t*)((uint8_t*)scr + n * 8);
+    const uint8_t* din = (const uint8_t*)in_base; uint8_t* dout = (uint8_t*)out_base;
+    if (mem_kind == RCZ_MEM_HOST) {
+        st = stage_span_in(c, WS_IN, in_base, in_off, in_len, n, 1, &din); if (st) return st;
+        st = stage_span_out(c, WS_OUT, out_off, out_cap, n, 1, &dout); if (st) return st;
+    }
+    const size_t smem = sizeof(flk::WarpSmem) * flk::WPB;
+    RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(flk::inflate_kernel, smem));
+    const unsigned grid = (unsigned)std::min<size_t>((n + flk::WPB - 1) / flk::WPB, (size_t)c->sm_count * 12);
+    st = ctx_timer_begin(c); if (st) return st;
+    RCZ_KLAUNCH(c, flk::inflate_kernel, grid, flk::NT, smem, din, ds.in_ptr<uint64_t>(i_off2), ds.in_ptr<uint64_t>(i_len2), dout, ds.in_ptr<uint64_t>(2),
+                ds.in_ptr<uint64_t>(3), ds.out_ptr<uint64_t>(0), d_used_fl, ds.out_ptr<int32_t>(1), d_det, (unsigned)n);
+    const unsigned grid2 = (unsigned)std::min<size_t>((n + zlk::WPB - 1) / zlk::WPB, (size_t)c->sm_count * 8);
+    RCZ_KLAUNCH(c, zlk::zlib_finish_kernel, grid2, zlk::NT, 0, din, ds.in_ptr<uint64_t>(0), ds.in_ptr<uint64_t>(1), dout, ds.in_ptr<uint64_t>(2),
+                ds.out_ptr<uint64_t>(0), d_used_fl, in_used ? ds.out_ptr<uint64_t>(o_used) : (uint64_t*)nullptr, ds.out_ptr<int32_t>(1), d_det,
+                adler ? ds.out_ptr<uint32_t>(o_ad) : (uint32_t*)nullptr, (unsigned)n);
+    st = ctx_timer_end(c); if (st) return st;
+    st = ds.download(); if (st) return st;
+    if (mem_kind == RCZ_MEM_HOST) {
+        std::vector<uint64_t> clipped(n);
+        for (size_t i = 0; i < n; ++i) clipped[i] = out_len[i] < out_cap[i] ? out_len[i] : out_cap[i];
+        st = unstage_span_out(c, out_base, dout, out_off, clipped.data(), n, 1); if (st) return st;
+    }
+    return RCZ_OK;
+}

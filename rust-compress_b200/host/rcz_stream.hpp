@@ -455,6 +455,63 @@ template <class R> class Decoder {                                           // 
 };
 }  // namespace flate
 
+// ================================================================================================ zlib
+namespace zlib {
+inline const char* message_of(int detail) {                                   // the reference's InvalidInput messages, zlib.rs:58-113
+    switch (detail) {
+    case RCZ_ZL_UNSUPPORTED_FORMAT: return "unsupported zlib stream format";
+    case RCZ_ZL_UNSUPPORTED_WINDOW: return "unsupported zlib window size";
+    case RCZ_ZL_PRESET_DICTIONARY: return "unsupported initial dictionary in the output stream";
+    case RCZ_ZL_BAD_HEADER_CHECKSUM: return "invalid zlib header checksum";
+    case RCZ_ZL_BAD_CHECKSUM: return "invalid checksum on zlib stream";
+    default: return "zlib::Decoder";
+    }
+}
+template <class R> class Decoder {                                           // zlib.rs:32-117
+  public:
+    R r;
+    size_t max_output = 1ull << 30;
+    Decoder(Context& ctx, R r_) : r(std::move(r_)), ctx_(ctx) {}
+    bool eof() const { return decoded_ && out_.avail() == 0; }                // zlib.rs:88: the inner decoder has handed out its final block
+    void reset() { decoded_ = false; out_.clear(); in_.clear(); }            // zlib.rs:91-95
+    uint32_t checksum() const { return adler_; }                              // hash.result() after the last byte
+
+    // header on the first call (zlib.rs:99-102), then decoded bytes; the trailer is checked when the data runs out (zlib.rs:106-117)
+    size_t read(uint8_t* dst, size_t len) {
+        if (!decoded_) decode_all();
+        size_t k = out_.take(dst, len);
+        if (k == 0 && len > 0 && pending_err_) { pending_err_ = false; throw pending_; }
+        return k;
+    }
+
+  private:
+    void decode_all() {
+        detail::read_to_end(r, in_);
+        const uint64_t n = in_.size();
+        in_.resize(in_.size() + 64);
+        uint64_t off = 0, cap = n * 8 + 4096;
+        for (;;) {
+            out_.buf.assign((size_t)cap + 64, 0);
+            uint64_t olen = 0, used = 0; int32_t st = 0, det = 0; uint32_t ad = 1;
+            ctx_.check(rcz_zlib_decode_streams(ctx_.get(), in_.data(), &off, &n, out_.buf.data(), &off, &cap, &olen, &used, &st, &det, &ad, 1, RCZ_MEM_HOST),
+                       "rcz_zlib_decode_streams");
+            if (st == RCZ_E_OUTPUT_FULL && cap < max_output) { cap = cap * 4 < max_output ? cap * 4 : max_output; continue; }
+            out_.buf.resize((size_t)(olen < cap ? olen : cap));
+            adler_ = ad;
+            if (st != RCZ_OK) { pending_ = error_from_status(st, det >= RCZ_ZL_UNSUPPORTED_FORMAT ? message_of(det) : "flate::Decoder", det); pending_err_ = true; }
+            break;
+        }
+        decoded_ = true;
+    }
+    Context& ctx_;
+    detail::Outlet out_;
+    std::vector<uint8_t> in_;
+    uint32_t adler_ = 1;
+    bool decoded_ = false, pending_err_ = false;
+    io_error pending_{ErrorKind::Other, ""};
+};
+}  // namespace zlib
+
 // ================================================================================================ ari
 namespace ari {
 template <class W> class ByteEncoder {                                       // entropy/ari/table.rs:185-224

@@ -201,6 +201,45 @@ int main(int argc, char** argv) {
         CHECK(threw);
     });
 
+    // ------------------------------------------------------------------------------------------ zlib (zlib.rs:140-205)
+    run("zlib::decode fixtures", [&] {
+        for (int i = 0; i <= 9; ++i) {
+            bytes f = load("ref_test.z." + std::to_string(i));
+            rcz::zlib::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(f));
+            CHECK(read_to_end(d) == txt);
+            CHECK(d.checksum() == 0xfb4fcfa6u);
+        }
+    });
+    run("zlib::one_byte_at_a_time", [&] {
+        bytes f = load("ref_test.z.1");
+        rcz::zlib::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(f));
+        CHECK(!d.eof());
+        bytes out; uint8_t b;
+        while (d.read(&b, 1) == 1) out.push_back(b);
+        CHECK(d.eof());
+        CHECK(out == txt);
+    });
+    run("zlib::random_byte_lengths", [&] {
+        bytes f = load("ref_test.z.1");
+        rcz::zlib::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(f));
+        bytes out, buf(40);
+        for (;;) { size_t want = 1 + rng() % 40; size_t k = d.read(buf.data(), want); if (k == 0) break; out.insert(out.end(), buf.begin(), buf.begin() + (long)k); }
+        CHECK(out == txt);
+    });
+    run("zlib::header and trailer errors are InvalidInput", [&] {
+        auto fails_with = [&](bytes f, int detail) {
+            rcz::zlib::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(f));
+            try { read_to_end(d); } catch (const rcz::io_error& e) { return e.kind == rcz::ErrorKind::InvalidInput && e.detail == detail; }
+            return false;
+        };
+        bytes f = load("ref_test.z.5");
+        bytes a = f; a[0] = 0x77; CHECK(fails_with(a, RCZ_ZL_UNSUPPORTED_FORMAT));
+        bytes b = f; b[0] = 0x68; b[1] = 0x81; CHECK(fails_with(b, RCZ_ZL_UNSUPPORTED_WINDOW));
+        bytes c = f; c[0] = 0x78; c[1] = 0xBB; CHECK(fails_with(c, RCZ_ZL_PRESET_DICTIONARY));
+        bytes e = f; e[1] ^= 1; CHECK(fails_with(e, RCZ_ZL_BAD_HEADER_CHECKSUM));
+        bytes g = f; g[g.size() - 1] ^= 1; CHECK(fails_with(g, RCZ_ZL_BAD_CHECKSUM));
+    });
+
     // ------------------------------------------------------------------------------------------ rle
     auto rle_enc = [&](const bytes& in) { rcz::rle::Encoder<rcz::VecWriter> e(ctx, rcz::VecWriter()); e.write(in.data(), in.size()); return e.finish().v; };
     auto rle_dec = [&](const bytes& in) { rcz::rle::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(in)); return read_to_end(d); };

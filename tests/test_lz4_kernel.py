@@ -263,3 +263,20 @@ def test_lz4_gpu_window_cases(gpu_ctx, oracle, gen, device):
     for name in WINDOW_CASE_NAMES:
         units, caps = cases[name]
         _check(gpu_ctx, oracle, units, caps, device=device, pad_front=7, gap=1)
+
+
+@pytest.mark.gpu
+def test_lz4_gpu_stage_timings(gpu_ctx, gen):
+    """rcz_last_stage_ms: the three kernels of a device-resident call (parse, scan, materialise) are timed separately."""
+    import torch
+    unit, count = 1 << 20, 32
+    raw = gen.units("lzsyn", gen.unit_seed(2, 0), unit, count)
+    packed, off, lens = gen.lz4_compress_units(raw, unit, count)
+    d_in = torch.from_numpy(packed).cuda()
+    d_out = torch.zeros(unit * count, dtype=torch.uint8, device="cuda")
+    out_off = np.arange(count, dtype=np.uint64) * unit
+    out_len, status = gpu_ctx.lz4_decode_blocks(d_in, off, lens, d_out, out_off, np.full(count, unit, dtype=np.uint64))
+    assert (status == 0).all() and bytes(d_out.cpu().numpy()) == raw.tobytes()
+    st = gpu_ctx.last_stage_ms()
+    assert len(st) == 3 and all(t > 0 for t in st)
+    assert abs(sum(st) - gpu_ctx.last_kernel_ms()) < 0.25 * gpu_ctx.last_kernel_ms() + 0.05

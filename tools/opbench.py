@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-op device timings at (scaled) BASELINE config sizes — a tuning aid, not the judged bench (that is bench.py).
 
-    python tools/opbench.py [lz4] [ibwt] [bwt] [flate] [dc] [ari] [rle] [--blocks N] [--reps R]
+    python tools/opbench.py [lz4] [ibwt] [bwt] [flate] [zlib] [dc] [ari] [rle] [--blocks N] [--reps R]
 
 Prints one JSON line per op: uncompressed GB/s from CUDA events around the C-ABI call (device-resident buffers)."""
 import importlib
@@ -37,7 +37,7 @@ def main():
     rcz = importlib.import_module("rust-compress_b200")
     opt = {sys.argv[i][2:]: int(sys.argv[i + 1]) for i in range(1, len(sys.argv) - 1) if sys.argv[i].startswith("--")}
     args = [a for a in sys.argv[1:] if not a.startswith("--") and not a.isdigit()]
-    ops = args or ["lz4", "ibwt", "bwt", "flate", "dc", "ari", "rle"]
+    ops = args or ["lz4", "ibwt", "bwt", "flate", "zlib", "dc", "ari", "rle"]
     nblk, reps = opt.get("blocks", 32), opt.get("reps", 5)
     ctx = rcz.Context(device=0)
     ctx.set_stream(torch.cuda.current_stream())
@@ -108,6 +108,24 @@ def main():
         ms = timed(lambda: ctx.flate_decode_streams(d_in, foff, lens, d_out, ooff, caps, async_=True), reps)
         assert torch.equal(d_out, torch.from_numpy(raw).cuda())
         report("inflate_64k_streams", unit * count, ms, {"streams": count, "C_bytes": int(lens.sum())})
+    if "zlib" in ops:
+        unit, count = 65536, nblk * 64
+        raw = gen.units("hextext", gen.unit_seed(4, 0), unit, count)
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(os.cpu_count()) as ex:
+            cs = list(ex.map(lambda i: zlib.compress(raw[i * unit: (i + 1) * unit].tobytes(), 6), range(count)))
+        lens = np.array([len(c) for c in cs], dtype=np.uint64)
+        foff = np.zeros(count, dtype=np.uint64); foff[1:] = np.cumsum(lens)[:-1]
+        d_in = torch.from_numpy(np.frombuffer(b"".join(cs) + bytes(64), dtype=np.uint8).copy()).cuda()
+        d_out = torch.zeros(unit * count, dtype=torch.uint8, device="cuda")
+        ooff = np.arange(count, dtype=np.uint64) * unit
+        caps = np.full(count, unit, dtype=np.uint64)
+        ms = timed(lambda: ctx.zlib_decode_streams(d_in, foff, lens, d_out, ooff, caps, async_=True), reps)
+        res = ctx.zlib_decode_streams(d_in, foff, lens, d_out, ooff, caps)
+        assert (res[1] == 0).all() and torch.equal(d_out, torch.from_numpy(raw).cuda())
+        report("zlib_64k_streams (inflate + adler32 + trailer)", unit * count, ms, {"streams": count, "C_bytes": int(lens.sum())})
+        ms = timed(lambda: ctx.adler32_streams(d_out, ooff, caps, async_=True), reps)
+        report("adler32_64k_streams", unit * count, ms, {"streams": count})
     if "ari" in ops:
         unit, count = 65536, nblk * 64
         raw = gen.units("hextext", gen.unit_seed(5, 0), unit, count)
