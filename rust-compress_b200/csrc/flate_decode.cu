@@ -371,17 +371,45 @@ constexpr unsigned MOD_ADLER = 65521u;   // adler.rs:18
 constexpr int NT = 256, WPB = NT / 32;
 
 // Adler-32 of p[0..n) by one warp.  a = 1 + sum(b_i), b = n + sum((n - i) * b_i) (mod 65521): the serial recurrence of
-// adler.rs:34-39 in closed form, so chunks of 4096 bytes reduce independently (warp-shuffle sums) and fold with their offset.
+// adler.rs:34-39 in closed form, so pieces of <= 4096 bytes reduce independently (warp-shuffle sums) and fold with their
+// offset.  The body runs on aligned 16-byte loads and DP4A (byte sums and index-weighted byte sums, four bytes per instruction).
+__device__ __forceinline__ void adler_fold(unsigned long long& S1, unsigned long long& S2, unsigned long long g, unsigned s1, unsigned s2) {
+    s1 = warp_reduce_add(s1); s2 = warp_reduce_add(s2);               // <= 4096 * 255 and < 2^31.1: no overflow
+    S2 = (S2 + (g % MOD_ADLER) * (unsigned long long)(s1 % MOD_ADLER) + s2) % MOD_ADLER;
+    S1 = (S1 + s1) % MOD_ADLER;
+}
 __device__ __forceinline__ unsigned warp_adler32(const uint8_t* __restrict__ p, unsigned long long n) {
     const unsigned lane = threadIdx.x & 31;
-    unsigned long long S1 = 0, S2 = 0;                                // sum b_i, sum i * b_i (mod 65521)
-    for (unsigned long long g = 0; g < n; g += 4096) {
-        const unsigned m = n - g < 4096 ? (unsigned)(n - g) : 4096u;
+    unsigned long long S1 = 0, S2 = 0, g = 0;                         // sum b_i, sum i * b_i (mod 65521); bytes done
+    {   // head: up to the first 16-byte boundary
+        const unsigned long long h64 = (16u - (unsigned)((uintptr_t)p & 15u)) & 15u;
+        const unsigned h = (unsigned)(h64 < n ? h64 : n);
         unsigned s1 = 0, s2 = 0;
-        for (unsigned j = lane; j < m; j += 32) { const unsigned b = p[g + j]; s1 += b; s2 += j * b; }
-        s1 = warp_reduce_add(s1); s2 = warp_reduce_add(s2);           // <= 4096 * 255 and < 2^31.1: no overflow
-        S2 = (S2 + (g % MOD_ADLER) * (unsigned long long)(s1 % MOD_ADLER) + s2) % MOD_ADLER;
-        S1 = (S1 + s1) % MOD_ADLER;
+        if (lane < h) { s1 = p[lane]; s2 = lane * s1; }
+        adler_fold(S1, S2, 0, s1, s2);
+        g = h;
+    }
+    while (n - g >= 16) {                                             // body: pieces of <= 4096 bytes, 16 per lane and round
+        const unsigned long long rest = n - g;
+        const unsigned nv = rest >= 4096 ? 256u : (unsigned)(rest >> 4);
+        const uint4* v = reinterpret_cast<const uint4*>(p + g);
+        unsigned s1 = 0, s2 = 0;
+        for (unsigned k = lane; k < nv; k += 32) {
+            const uint4 q = __ldg(v + k);
+            const unsigned a0 = __dp4a(q.x, 0x01010101u, 0u), a1 = __dp4a(q.y, 0x01010101u, 0u), a2 = __dp4a(q.z, 0x01010101u, 0u), a3 = __dp4a(q.w, 0x01010101u, 0u);
+            unsigned w = __dp4a(q.x, 0x03020100u, 0u);
+            w = __dp4a(q.y, 0x07060504u, w); w = __dp4a(q.z, 0x0b0a0908u, w); w = __dp4a(q.w, 0x0f0e0d0cu, w);
+            const unsigned sv = a0 + a1 + a2 + a3;
+            s1 += sv; s2 += 16u * k * sv + w;
+        }
+        adler_fold(S1, S2, g, s1, s2);
+        g += 16ull * nv;
+    }
+    if (g < n) {                                                      // tail: < 16 bytes
+        const unsigned t = (unsigned)(n - g);
+        unsigned s1 = 0, s2 = 0;
+        if (lane < t) { s1 = p[g + lane]; s2 = lane * s1; }
+        adler_fold(S1, S2, g, s1, s2);
     }
     const unsigned long long nm = n % MOD_ADLER;
     const unsigned a = (unsigned)((1 + S1) % MOD_ADLER);

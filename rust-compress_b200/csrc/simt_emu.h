@@ -325,6 +325,7 @@ inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
     for (int i = 0; i < 4; ++i) { unsigned s = (sel >> (4 * i)) & 7; r |= (unsigned)((v >> (8 * s)) & 0xff) << (8 * i); }
     return r;
 }
+inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) { for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 255u) * ((b >> (8 * i)) & 255u); return c; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T __ldcs(const T* p) { return *p; }
 template <class T> inline T __ldcg(const T* p) { return *p; }
