@@ -31,10 +31,6 @@
 #include "rcz_internal.h"
 #include <algorithm>
 
-#ifndef RCZ_LZ4_SPLIT
-#define RCZ_LZ4_SPLIT 0
-#endif
-
 namespace lz4k {
 
 constexpr int W = 8192;                    // compressed bytes per window
@@ -464,7 +460,7 @@ struct MatSmem {
     __align__(16) uint4 lt[17];                      // lt[k]: low k bytes set
     UnitInfo ui[2];
     uint32_t cmask[NCH + 1];                         // per chunk of the tile: bit i = byte i is final
-    uint16_t sbase[2][MT];                           // first piece of every sequence of the batch: [0] pieces whose sources are final, [1] the others
+    uint16_t sbase[MT];                              // first piece of every sequence of the batch
     unsigned scan[40];
     uint32_t blk, ja_next;
     rcz_mbar barw[2], bard[2];
@@ -778,22 +774,23 @@ lz4_mat_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__
                             const unsigned ma = ms > k.T0 ? ms : k.T0, mb = send < k.T1 ? send : k.T1;
                             if (mb > ma) {
                                 const unsigned nm = ((mb - 1u - k.c00) >> 4) - ((ma - k.c00) >> 4) + 1u;
-                                cnt += (RCZ_LZ4_SPLIT && mb - k.T0 > q.w) ? nm << 16 : nm;     // a match that may read this tile goes to the second class
+                                cnt += nm;
                             }
                             if (send >= k.T1) atomicMax(&sm.ja_next, j);       // the sequence that holds the next tile's first byte
                         }
                     }
-                    // one scan for both classes: low half = pieces with final sources (literals, matches from before the tile)
-                    unsigned P;
-                    const unsigned base = block_excl_scan_add<MT>(cnt, sm.scan, &P);
-                    sm.sbase[0][tid] = (uint16_t)base; sm.sbase[1][tid] = (uint16_t)(base >> 16);
+                    // block prefix scan of the piece counts with ONE barrier: warp-shuffle scan, warp totals through shared memory,
+                    // every warp adds up the totals before it
+                    const unsigned incl = warp_incl_scan_add(cnt);
+                    if ((tid & 31u) == 31u) sm.scan[tid >> 5] = incl;
                     __syncthreads();
-                    const unsigned Pi = P & 0xffffu, Pd = P >> 16;
-                    // one index space, the pieces that may have to wait last: a warp lies in one class or (one warp per batch) straddles both
-                    for (unsigned p0 = 0; p0 < Pi + Pd; p0 += MT) {
-                        const unsigned pw = p0 + (tid & ~31u), p = p0 + tid;
-                        if (pw < Pi) mat_piece<!RCZ_LZ4_SPLIT, true>(k, sm.sbase[0], j0, p, p < Pi);
-                        if (pw + 32u > Pi && pw < Pi + Pd) mat_piece<true, false>(k, sm.sbase[1], j0, p >= Pi ? p - Pi : 0u, p >= Pi && p < Pi + Pd);
+                    unsigned base = incl - cnt, P = 0;
+#pragma unroll
+                    for (unsigned g = 0; g < MT / 32; ++g) { const unsigned t2 = sm.scan[g]; if (g < (tid >> 5)) base += t2; P += t2; }
+                    sm.sbase[tid] = (uint16_t)base;
+                    __syncthreads();
+                    for (unsigned p0 = 0; p0 < P; p0 += MT) {
+                        if (p0 + (tid & ~31u) < P) mat_piece<true, true>(k, sm.sbase, j0, p0 + tid, p0 + tid < P);    // warp-uniform
                     }
                     if (!__syncthreads_or(more && j0 + MT < k.nseq)) break;
                 }

@@ -56,6 +56,13 @@ def main():
         ms = timed(lambda: ctx.lz4_decode_blocks(d_in, ioff, ilen, d_out, off, n, async_=True), reps)
         assert torch.equal(d_out, torch.from_numpy(raw).cuda())
         report("lz4_decode", UNIT * nblk, ms, {"C_bytes": int(ilen.sum())})
+        for kind in ("hextext", "runs", "random"):          # other shapes of input: 9-byte sequences with in-tile chains, long matches, one literal run
+            raw = gen.units(kind, gen.unit_seed(2, 0), UNIT, nblk)
+            packed, ioff, ilen = gen.lz4_compress_units(raw, UNIT, nblk)
+            d_in = torch.from_numpy(packed).cuda()
+            ms = timed(lambda: ctx.lz4_decode_blocks(d_in, ioff, ilen, d_out, off, n, async_=True), reps)
+            assert torch.equal(d_out, torch.from_numpy(raw).cuda())
+            report("lz4_decode_" + kind, UNIT * nblk, ms, {"C_bytes": int(ilen.sum()), "stage_ms": ctx.last_stage_ms()})
     if "ibwt" in ops or "bwt" in ops:
         for kind in ("random", "hextext"):
             raw = gen.units(kind, gen.unit_seed(3, 0), UNIT, nblk)
