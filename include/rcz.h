@@ -160,6 +160,17 @@ int rcz_dc_decode_blocks(rcz_ctx* ctx, const uint32_t* in_base, const uint64_t* 
                          void* out_base, const uint64_t* out_off, const uint64_t* n, int32_t* status,
                          size_t nblocks, int mem_kind);
 
+/* ---------------- bwt/mtf.rs ----------------
+ * rcz_mtf_encode_streams replaces `mtf::Encoder<W>::write` (mtf.rs:118-125: `MTF::encode` per byte, alphabetical start
+ * list), rcz_mtf_decode_streams replaces `mtf::Decoder<R>::read` (mtf.rs:155-168: `MTF::decode` per byte).  One
+ * rank/symbol per input byte: out_len[i] == in_len[i]. */
+int rcz_mtf_encode_streams(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                           void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
+                           uint64_t* out_len, int32_t* status, size_t nstreams, int mem_kind);
+int rcz_mtf_decode_streams(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                           void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
+                           uint64_t* out_len, int32_t* status, size_t nstreams, int mem_kind);
+
 /* ---------------- rle.rs ----------------
  * rcz_rle_decode_streams replaces `Decoder::read_run` (rle.rs:212-259); rcz_rle_encode_streams replaces
  * `Encoder::write` + `finish` (rle.rs:62-122) for one whole-buffer write. */

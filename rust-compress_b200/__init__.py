@@ -191,6 +191,21 @@ class Context:
         self._check(st, "rcz_adler32_streams")
         return adler
 
+    # ---- mtf (bwt/mtf.rs stream coder) -----------------------------------------------------------------------
+    def mtf_encode_streams(self, in_buf, in_off, in_len, out_buf, out_off, out_cap, async_=False):
+        kind, n, (io, il, oo, oc), out_len, status, _ = self._batch(None, "mtf", in_buf, in_off, in_len, out_buf, out_off, out_cap, async_=async_)
+        st = self._lib.rcz_mtf_encode_streams(self._h, _ptr(in_buf), _ptr(io), _ptr(il), _ptr(out_buf), _ptr(oo), _ptr(oc),
+                                              _ptr(out_len), _ptr(status), n, kind)
+        self._check(st, "rcz_mtf_encode_streams")
+        return out_len, status
+
+    def mtf_decode_streams(self, in_buf, in_off, in_len, out_buf, out_off, out_cap, async_=False):
+        kind, n, (io, il, oo, oc), out_len, status, _ = self._batch(None, "mtf", in_buf, in_off, in_len, out_buf, out_off, out_cap, async_=async_)
+        st = self._lib.rcz_mtf_decode_streams(self._h, _ptr(in_buf), _ptr(io), _ptr(il), _ptr(out_buf), _ptr(oo), _ptr(oc),
+                                              _ptr(out_len), _ptr(status), n, kind)
+        self._check(st, "rcz_mtf_decode_streams")
+        return out_len, status
+
     # ---- ari -----------------------------------------------------------------------------------------------
     def ari_encode_streams(self, in_buf, in_off, in_len, out_buf, out_off, out_cap, async_=False):
         kind, n, (io, il, oo, oc), out_len, status, _ = self._batch(None, "ari", in_buf, in_off, in_len, out_buf, out_off, out_cap, async_=async_)

@@ -45,6 +45,8 @@ SIGNATURES = {
     "rcz_dc_decode_blocks": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I]),
     "rcz_rle_decode_streams": (_I, _BATCH),
     "rcz_rle_encode_streams": (_I, _BATCH),
+    "rcz_mtf_encode_streams": (_I, _BATCH),
+    "rcz_mtf_decode_streams": (_I, _BATCH),
 }
 
 _libs = {}

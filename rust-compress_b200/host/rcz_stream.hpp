@@ -579,6 +579,59 @@ template <class R> class ByteDecoder {                                       // 
 };
 }  // namespace ari
 
+// ================================================================================================ mtf
+namespace mtf {
+// bwt/mtf.rs:95-169.  The reference codes byte by byte as they are written / read; the list state carries over between calls,
+// so buffering the whole stream and coding it with one kernel call at finish() / on the first read() gives the same bytes.
+template <class W> class Encoder {                                           // mtf.rs:95-130
+  public:
+    Encoder(Context& ctx, W w) : ctx_(ctx), w_(std::move(w)) {}
+    size_t write(const uint8_t* buf, size_t len) { in_.insert(in_.end(), buf, buf + len); return len; }
+    void flush() { w_.flush(); }
+    W finish() {                                                              // mtf.rs:112-114 (+ the ranks of everything written so far)
+        const uint64_t n = in_.size();
+        in_.resize(in_.size() + 64);
+        uint64_t off = 0, cap = n, olen = 0; int32_t st = 0;
+        std::vector<uint8_t> out((size_t)cap + 64);
+        ctx_.check(rcz_mtf_encode_streams(ctx_.get(), in_.data(), &off, &n, out.data(), &off, &cap, &olen, &st, 1, RCZ_MEM_HOST), "rcz_mtf_encode_streams");
+        if (st != RCZ_OK) throw error_from_status(st, "mtf::Encoder");
+        w_.write(out.data(), (size_t)olen);
+        w_.flush();
+        return std::move(w_);
+    }
+
+  private:
+    Context& ctx_; W w_; std::vector<uint8_t> in_;
+};
+
+template <class R> class Decoder {                                           // mtf.rs:133-169
+  public:
+    Decoder(Context& ctx, R r) : ctx_(ctx), r_(std::move(r)) {}
+    size_t read(uint8_t* dst, size_t len) {                                   // mtf.rs:155-168: short count at the end of the inner stream
+        if (!decoded_) decode_all();
+        return out_.take(dst, len);
+    }
+    R finish() { return std::move(r_); }                                      // mtf.rs:149-151
+
+  private:
+    void decode_all() {
+        std::vector<uint8_t> in;
+        detail::read_to_end(r_, in);
+        const uint64_t n = in.size();
+        in.resize(in.size() + 64);
+        uint64_t off = 0, cap = n, olen = 0; int32_t st = 0;
+        out_.buf.assign((size_t)cap + 64, 0);
+        ctx_.check(rcz_mtf_decode_streams(ctx_.get(), in.data(), &off, &n, out_.buf.data(), &off, &cap, &olen, &st, 1, RCZ_MEM_HOST), "rcz_mtf_decode_streams");
+        if (st != RCZ_OK) throw error_from_status(st, "mtf::Decoder");
+        out_.buf.resize((size_t)olen);
+        decoded_ = true;
+    }
+    Context& ctx_; R r_;
+    detail::Outlet out_;
+    bool decoded_ = false;
+};
+}  // namespace mtf
+
 // ================================================================================================ rle
 namespace rle {
 template <class W> class Encoder {                                           // rle.rs:40-123 (one whole-buffer write; App. B #11, #12)

@@ -240,6 +240,24 @@ int main(int argc, char** argv) {
         bytes g = f; g[g.size() - 1] ^= 1; CHECK(fails_with(g, RCZ_ZL_BAD_CHECKSUM));
     });
 
+    // ------------------------------------------------------------------------------------------ mtf (bwt/mtf.rs:176-192)
+    run("mtf::some_roundtrips", [&] {
+        bytes r;
+        auto roundtrip = [&](const bytes& in) {
+            rcz::mtf::Encoder<rcz::VecWriter> e(ctx, rcz::VecWriter());
+            e.write(in.data(), in.size());
+            r = e.finish().v;
+            CHECK(r.size() == in.size());
+            rcz::mtf::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(r));
+            CHECK(read_to_end(d) == in);
+        };
+        const char* t = "teeesst_mtf";
+        roundtrip(bytes(t, t + 11));
+        CHECK(r[0] == 't' && r[1] == 'e' + 1 && r[2] == 0 && r[3] == 0);        // 't' at rank 116; 'e' (101) pushed back by one; repeats are rank 0
+        roundtrip(bytes());
+        roundtrip(txt);
+    });
+
     // ------------------------------------------------------------------------------------------ rle
     auto rle_enc = [&](const bytes& in) { rcz::rle::Encoder<rcz::VecWriter> e(ctx, rcz::VecWriter()); e.write(in.data(), in.size()); return e.finish().v; };
     auto rle_dec = [&](const bytes& in) { rcz::rle::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(in)); return read_to_end(d); };

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-op device timings at (scaled) BASELINE config sizes — a tuning aid, not the judged bench (that is bench.py).
 
-    python tools/opbench.py [lz4] [ibwt] [bwt] [flate] [zlib] [dc] [ari] [rle] [--blocks N] [--reps R]
+    python tools/opbench.py [lz4] [ibwt] [bwt] [flate] [zlib] [mtf] [dc] [ari] [rle] [--blocks N] [--reps R]
 
 Prints one JSON line per op: uncompressed GB/s from CUDA events around the C-ABI call (device-resident buffers)."""
 import importlib
@@ -37,7 +37,7 @@ def main():
     rcz = importlib.import_module("rust-compress_b200")
     opt = {sys.argv[i][2:]: int(sys.argv[i + 1]) for i in range(1, len(sys.argv) - 1) if sys.argv[i].startswith("--")}
     args = [a for a in sys.argv[1:] if not a.startswith("--") and not a.isdigit()]
-    ops = args or ["lz4", "ibwt", "bwt", "flate", "zlib", "dc", "ari", "rle"]
+    ops = args or ["lz4", "ibwt", "bwt", "flate", "zlib", "mtf", "dc", "ari", "rle"]
     nblk, reps = opt.get("blocks", 32), opt.get("reps", 5)
     ctx = rcz.Context(device=0)
     ctx.set_stream(torch.cuda.current_stream())
@@ -133,6 +133,21 @@ def main():
         report("zlib_64k_streams (inflate + adler32 + trailer)", unit * count, ms, {"streams": count, "C_bytes": int(lens.sum())})
         ms = timed(lambda: ctx.adler32_streams(d_out, ooff, caps, async_=True), reps)
         report("adler32_64k_streams", unit * count, ms, {"streams": count})
+    if "mtf" in ops:
+        # (i) C5 shape: one stream per 4 MiB block (the L column of a BWT would come here; hexdump text has the same alphabet);
+        # (ii) many short streams: the coder is one dependency chain per stream, throughput comes from the number of streams
+        for unit, count, tag in ((UNIT, nblk, "4mib_blocks"), (65536, nblk * 64, "64k_streams")):
+            raw = gen.units("hextext", gen.unit_seed(5, 0), unit, count)
+            d_raw = torch.from_numpy(raw).cuda()
+            d_rk = torch.zeros(unit * count, dtype=torch.uint8, device="cuda")
+            d_back = torch.zeros(unit * count, dtype=torch.uint8, device="cuda")
+            so = np.arange(count, dtype=np.uint64) * unit
+            sn = np.full(count, unit, dtype=np.uint64)
+            ms = timed(lambda: ctx.mtf_encode_streams(d_raw, so, sn, d_rk, so, sn, async_=True), reps)
+            report("mtf_encode_" + tag, unit * count, ms, {"streams": count})
+            ms = timed(lambda: ctx.mtf_decode_streams(d_rk, so, sn, d_back, so, sn, async_=True), reps)
+            assert torch.equal(d_back, d_raw)
+            report("mtf_decode_" + tag, unit * count, ms, {"streams": count})
     if "ari" in ops:
         unit, count = 65536, nblk * 64
         raw = gen.units("hextext", gen.unit_seed(5, 0), unit, count)
