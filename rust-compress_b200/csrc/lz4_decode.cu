@@ -499,6 +499,13 @@ __device__ __forceinline__ unsigned chunk_bits(unsigned a, unsigned b, unsigned 
     return ((1u << hi) - 1u) & ~((1u << lo) - 1u);
 }
 
+// bytes [lo, hi) of a 16-byte chunk to HBM: the ragged first / last chunk of a unit (out of line: the sixteen byte predicates
+// must not be hoisted into every piece)
+__device__ __noinline__ void store_chunk_bytes(uint8_t* g, uint4 v, unsigned lo, unsigned hi) {
+    const unsigned wv[4] = {v.x, v.y, v.z, v.w};
+    for (unsigned i = lo; i < hi; ++i) g[i] = (uint8_t)(wv[i >> 2] >> ((i & 3u) * 8u));
+}
+
 // Byte-by-byte fetch of a piece (rare, out of line): literals at the very edge of the input (kind 1) and the head of an
 // overlapping match with offset < 16 (kind 3), where byte i of the piece is seed byte ((pos - ms) + i) mod off.
 __device__ __noinline__ uint4 piece_bytes(const MatCtx& k, unsigned kind, unsigned pos, unsigned ms, unsigned doff, uintptr_t gsrc, unsigned d0, unsigned len) {
@@ -631,10 +638,18 @@ __device__ __forceinline__ void mat_piece(const MatCtx& k, const uint16_t* sbase
                 const uint4 mlo = k.lt[d0], mhi = k.lt[d0 + len];
                 const unsigned cro = ring_off(k, c00 + 16u * cc);
                 const unsigned vx = t.x & mhi.x & ~mlo.x, vy = t.y & mhi.y & ~mlo.y, vz = t.z & mhi.z & ~mlo.z, vw = t.w & mhi.w & ~mlo.w;
-                if (mhi.x & ~mlo.x) ring_or(k, cro, vx);
-                if (mhi.y & ~mlo.y) ring_or(k, cro + 4, vy);
-                if (mhi.z & ~mlo.z) ring_or(k, cro + 8, vz);
-                if (mhi.w & ~mlo.w) ring_or(k, cro + 12, vw);
+                uint32_t* const cw = reinterpret_cast<uint32_t*>(k.ring + cro);
+                if (cro >= 32u && cro < (unsigned)RING - 32u) {                 // (all but the two chunks at either end of the ring: no mirror)
+                    if (mhi.x & ~mlo.x) atomicOr(cw, vx);
+                    if (mhi.y & ~mlo.y) atomicOr(cw + 1, vy);
+                    if (mhi.z & ~mlo.z) atomicOr(cw + 2, vz);
+                    if (mhi.w & ~mlo.w) atomicOr(cw + 3, vw);
+                } else {
+                    if (mhi.x & ~mlo.x) ring_or(k, cro, vx);
+                    if (mhi.y & ~mlo.y) ring_or(k, cro + 4, vy);
+                    if (mhi.z & ~mlo.z) ring_or(k, cro + 8, vz);
+                    if (mhi.w & ~mlo.w) ring_or(k, cro + 12, vw);
+                }
                 __threadfence_block();
                 const unsigned bits = ((1u << len) - 1u) << d0;
                 const unsigned old = atomicOr(&k.cmask[cc], bits);
@@ -646,11 +661,7 @@ __device__ __forceinline__ void mat_piece(const MatCtx& k, const uint16_t* sbase
                     uint8_t* g = k.outb + T0 - k.h + 16u * cc;                  // pointer arithmetic: T0 - h alone may wrap below zero
                     const unsigned lo = cc ? 0u : k.h;
                     if (lo == 0 && hi == 16u) *reinterpret_cast<uint4*>(g) = v;
-                    else {
-                        const unsigned wv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) if ((unsigned)i >= lo && (unsigned)i < hi) g[i] = (uint8_t)(wv[i >> 2] >> ((i & 3) * 8));
-                    }
+                    else store_chunk_bytes(g, v, lo, hi);                       // first / last chunk of a unit (rare, out of line)
                 }
                 done = true; progressed = true;
             }
