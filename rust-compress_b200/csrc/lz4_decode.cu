@@ -45,7 +45,7 @@ constexpr int MT = 512;                    // materialise: threads per CTA (2 CT
 constexpr int TCAP = 8192;                 // materialise: at most this many output bytes per tile (one chunk per thread)
 constexpr int NCH = TCAP / 16;
 constexpr int RING = 73760;                // output ring in shared memory: 64 KiB of history + one tile + 16-byte chunk slack
-constexpr int DCAP = 576;                  // sequence descriptors of a unit staged in shared memory (the rest is read from HBM)
+constexpr int DCAP = 544;                  // sequence descriptors of a unit staged in shared memory (the rest is read from HBM)
 static_assert(RING % 16 == 0 && RING > 65535 + TCAP + 16, "a tile must not overwrite history that its matches can reach");
 
 constexpr unsigned long long CH_VALID = 1ull << 63;
@@ -461,6 +461,7 @@ struct MatSmem {
     UnitInfo ui[2];
     uint32_t cmask[NCH + 1];                         // per chunk of the tile: bit i = byte i is final
     uint16_t sbase[MT];                              // first piece of every sequence of the batch
+    uint16_t pseq[3 * MT];                           // sequence (index in the batch) of every piece: <= 2 per sequence + one per chunk
     unsigned scan[40];
     uint32_t blk, ja_next;
     rcz_mbar barw[2], bard[2];
@@ -539,32 +540,15 @@ __device__ __noinline__ unsigned far_back(unsigned kk, unsigned off) {
 // masks order pieces whose source lies inside the tile, and whoever completes a chunk stores its 16 bytes to HBM.
 // All lanes of the warp call it together; lanes with active == false only take part in the votes.
 template <bool DEP, bool LIT>
-__device__ __forceinline__ void mat_piece(const MatCtx& k, const uint16_t* sbase, unsigned j0, unsigned p, bool active) {
+__device__ __forceinline__ void mat_piece(const MatCtx& k, const uint16_t* sbase, const uint16_t* pseq, unsigned j0, unsigned p, bool active) {
     constexpr unsigned NOCHK = 0xffffu;
     const unsigned T0 = k.T0, T1 = k.T1, c00 = k.c00;
     unsigned len = 0, d0 = 0, cc = 0, kind = 0, pos = 0, ms = 0, doff = 0, dlit = 0, dS = 0;
     unsigned cA = NOCHK, cB = NOCHK, mA = 0, mB = 0;
     rcz_saddr srcs = 0;
     bool done = !active;
-    // sequence of every lane's piece = last i with sbase[i] <= p.  The lanes hold consecutive pieces, so the warp finds the sequence
-    // of its first piece together (two 16-way probes), loads the 32 bases from there on into registers, and every lane finishes
-    // with a 5-step search through shuffles; a lane whose piece lies beyond those 32 sequences falls back to a binary search.
-    unsigned si;
-    {
-        const unsigned lane = threadIdx.x & 31, pw = __shfl_sync(RCZ_FULL, p, 0);
-        const unsigned blk = (unsigned)__popc(__ballot_sync(RCZ_FULL, sbase[16u * lane] <= pw)) - 1u;
-        const unsigned i0 = 16u * blk + (unsigned)__popc(__ballot_sync(RCZ_FULL, lane < 16u && sbase[16u * blk + (lane & 15u)] <= pw)) - 1u;
-        const unsigned v = i0 + lane < (unsigned)MT ? (unsigned)sbase[i0 + lane] : 0xffffffffu;
-        unsigned lo = 0;
-#pragma unroll
-        for (int st = 16; st > 0; st >>= 1) { const unsigned vm = __shfl_sync(RCZ_FULL, v, (int)(lo + st)); if (vm <= p) lo += st; }
-        si = i0 + lo;
-        if (lo == 31u && si + 1u < (unsigned)MT && sbase[si + 1u] <= p) {
-            unsigned hi = MT; lo = si + 1u;
-            while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (sbase[mid] <= p) lo = mid; else hi = mid; }
-            si = lo;
-        }
-    }
+    // sequence of the piece: written by the sequence's thread when the pieces were counted
+    const unsigned si = active ? (unsigned)pseq[p] : 0u;
     if (active) {
         const unsigned j = j0 + si, r = p - sbase[si];
         const uint4 q = mat_desc(k, j);
@@ -795,13 +779,16 @@ lz4_mat_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__
                     const unsigned incl = warp_incl_scan_add(cnt);
                     if ((tid & 31u) == 31u) sm.scan[tid >> 5] = incl;
                     __syncthreads();
-                    unsigned base = incl - cnt, P = 0;
-#pragma unroll
-                    for (unsigned g = 0; g < MT / 32; ++g) { const unsigned t2 = sm.scan[g]; if (g < (tid >> 5)) base += t2; P += t2; }
+                    // (lane g of every warp holds warp g's total; one more shuffle scan gives the offsets)
+                    const unsigned wt = (tid & 31u) < MT / 32 ? sm.scan[tid & 31u] : 0u;
+                    const unsigned wi = warp_incl_scan_add(wt);
+                    const unsigned P = __shfl_sync(RCZ_FULL, wi, MT / 32 - 1);
+                    const unsigned base = incl - cnt + __shfl_sync(RCZ_FULL, wi - wt, (int)(tid >> 5));
                     sm.sbase[tid] = (uint16_t)base;
+                    for (unsigned i = 0; i < cnt; ++i) sm.pseq[base + i] = (uint16_t)tid;      // piece -> sequence (a few per thread; a long match has one per chunk)
                     __syncthreads();
                     for (unsigned p0 = 0; p0 < P; p0 += MT) {
-                        if (p0 + (tid & ~31u) < P) mat_piece<true, true>(k, sm.sbase, j0, p0 + tid, p0 + tid < P);    // warp-uniform
+                        if (p0 + (tid & ~31u) < P) mat_piece<true, true>(k, sm.sbase, sm.pseq, j0, p0 + tid, p0 + tid < P);    // warp-uniform
                     }
                     if (!__syncthreads_or(more && j0 + MT < k.nseq)) break;
                 }
