@@ -195,6 +195,20 @@ __device__ __forceinline__ bool tok_fast(const ParseSmem& sm, const uint8_t* c, 
     return ok;
 }
 
+// Level A only needs where the token ends: the same decision as tok_fast without the fields (no TokF in the common path:
+// its address would escape to tok_gen and put it in local memory).
+__device__ __forceinline__ unsigned tok_next(const ParseSmem& sm, const uint8_t* c, unsigned p, unsigned lim, unsigned limq, unsigned e_rel) {
+    const unsigned tk = c[p], b1 = c[p + 1];
+    const unsigned L4 = tk >> 4, M4 = tk & 15u;
+    const bool l15 = L4 == 15u, m15 = M4 == 15u;
+    const unsigned q = p + 1u + (l15 ? 1u + b1 : 0u) + L4;
+    const unsigned b2 = c[q + 2];
+    unsigned nx = q + 2u + (m15 ? 1u : 0u);
+    bool ok = nx <= limq;
+    if ((l15 && b1 == 255u) || (m15 && b2 == 255u)) { TokF t; ok = p < lim && tok_gen(sm, c, p, lim, e_rel, t); nx = t.next; }
+    return ok ? nx : (TERM | p);
+}
+
 __global__ void __launch_bounds__(PT, 4)
 lz4_parse_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ in_len,
                  const uint32_t* __restrict__ wbase, const uint2* __restrict__ tickets, unsigned nticket,
@@ -254,8 +268,7 @@ lz4_parse_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict
 #pragma unroll
         for (int s = 31; s >= 0; --s) {
             const unsigned sb = gbase + (unsigned)s * 32u, se = sb + 32u, p = sb + lane;
-            unsigned a = TERM | p;
-            { TokF t; if (tok_fast(sm, c, p, lim, limq, e_rel, t)) a = t.next; }
+            unsigned a = tok_next(sm, c, p, lim, limq, e_rel);
             // pointer doubling inside the segment; a token is >= 3 bytes, so 4 rounds always suffice (an early exit on a warp
             // vote was measured: slower)
 #pragma unroll
