@@ -17,15 +17,17 @@
 //     in the window's output (literal/match boundary resolution), and the descriptors go to HBM.
 //   lz4_scan_kernel   (one warp per block) exclusive scan of the windows' output sizes, block status with
 //     the reference's error order (literal overrun, output full, offset underflow lz4.rs:93, ...).
-//   lz4_mat_kernel    (unit = the output of one window, <= 24 KiB tiles in shared memory)
-//     one thread per aligned 16-byte output chunk: the chunk's pieces (literal run / match) are fetched
-//     with 4-byte loads + funnel shifts from the staged compressed window, from the tile (in-tile matches,
-//     ordered by per-chunk done bits, no barriers) or from already-final output in L2, and leave as one
-//     16-byte store.  Units of one block are chained by a done flag (look-back), again one link per unit.
+//   lz4_mat_kernel    (one CTA per block, its windows in order; next window's bytes and descriptors prefetched by TMA)
+//     the last 64 KiB of the block's output live in a ring in shared memory, so every match source is a
+//     shared-memory read.  Output is produced in tiles of <= 8 KiB; one thread per PIECE (the part of a literal
+//     run or match that falls into one aligned 16-byte chunk): pieces per sequence -> block prefix scan ->
+//     piece -> sequence table.  A piece is fetched with 4-byte loads + funnel shifts (staged compressed window,
+//     ring) and OR-ed into its zeroed chunk; per-chunk byte masks order the pieces whose source lies inside
+//     the tile (no barrier), and whoever completes a chunk stores its 16 bytes to HBM.
 //
 // Offsets < match length (incl. 1..3, the reference's DECR path lz4.rs:100-102) are folded analytically:
-// byte k of a match with offset `off` equals byte (k mod off) of the `off` bytes before the match, so long
-// overlapping matches form no chunk-to-chunk dependency chain.
+// byte k of a match with offset `off` equals byte k - m * off for any whole number of periods m that stays inside the
+// match's periodic region, so long overlapping matches read ~32 KiB back and form no chunk-to-chunk dependency chain.
 // Malformed input (truncated fields, offset 0, offset before block start — the cases on which the
 // reference panics) yields RCZ_E_MALFORMED for that block.
 #include "rcz_internal.h"
