@@ -193,7 +193,11 @@ __device__ __forceinline__ bool tok_fast(const ParseSmem& sm, const uint8_t* c, 
     const unsigned nx = q + 2u + (m15 ? 1u : 0u);
     t.L = L; t.M = M4 + 4u + (m15 ? b2 : 0u); t.off = (unsigned)c[q] | ((unsigned)c[q + 1] << 8); t.lit = lit; t.next = nx;
     bool ok = nx <= limq;
-    if ((l15 && b1 == 255u) || (m15 && b2 == 255u)) ok = p < lim && tok_gen(sm, c, p, lim, e_rel, t);
+    if ((l15 && b1 == 255u) || (m15 && b2 == 255u)) {      // (its own TokF: t's address must not escape, or t lives in local memory)
+        TokF g;
+        ok = p < lim && tok_gen(sm, c, p, lim, e_rel, g);
+        t.L = g.L; t.M = g.M; t.off = g.off; t.lit = g.lit; t.next = g.next;
+    }
     return ok;
 }
 
