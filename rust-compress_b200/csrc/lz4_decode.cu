@@ -528,15 +528,15 @@ __device__ __noinline__ void store_chunk_bytes(uint8_t* g, uint4 v, unsigned lo,
 
 // Byte-by-byte fetch of a piece (rare, out of line): literals at the very edge of the input (kind 1) and the head of an
 // overlapping match with offset < 16 (kind 3), where byte i of the piece is seed byte ((pos - ms) + i) mod off.
-__device__ __noinline__ uint4 piece_bytes(const MatCtx& k, unsigned kind, unsigned pos, unsigned ms, unsigned doff, uintptr_t gsrc, unsigned d0, unsigned len) {
+__device__ __noinline__ uint4 piece_bytes(rcz_saddr rings, unsigned hb, unsigned kind, unsigned pos, unsigned ms, unsigned doff, uintptr_t gsrc, unsigned d0, unsigned len) {
     unsigned long long tl = 0, th = 0;
     unsigned sidx = 0, sro = 0;
-    if (kind == 3) { sidx = (pos - ms) % doff; sro = ring_off(k, ms - doff); }      // ring offset of the seed
+    if (kind == 3) { sidx = (pos - ms) % doff; sro = (ms - doff + hb) % (unsigned)RING; }      // ring offset of the seed
     for (unsigned i = 0; i < len; ++i) {
         unsigned v;
         if (kind == 3) {
             unsigned a = sro + sidx; a = a >= (unsigned)RING ? a - RING : a;
-            v = lds8_volatile(k.rings + a);
+            v = lds8_volatile(rings + a);
             sidx = sidx + 1 == doff ? 0 : sidx + 1;
         } else v = ld_gen_u8(gsrc + i);
         const unsigned bi = d0 + i;
@@ -636,7 +636,7 @@ __device__ __forceinline__ void mat_piece(const MatCtx& k, const uint16_t* sbase
                         const unsigned sh = (unsigned)(a & 3) * 8u;
                         const unsigned w0 = ld_gen_u32(a0), w1 = ld_gen_u32(a0 + 4), w2 = ld_gen_u32(a0 + 8), w3 = ld_gen_u32(a0 + 12), w4 = ld_gen_u32(a0 + 16);
                         t.x = __funnelshift_r(w0, w1, sh); t.y = __funnelshift_r(w1, w2, sh); t.z = __funnelshift_r(w2, w3, sh); t.w = __funnelshift_r(w3, w4, sh);
-                    } else t = piece_bytes(k, kind, pos, ms, doff, gsrc, d0, len);      // byte by byte (rare): input edges, periodic matches
+                    } else t = piece_bytes(k.rings, k.hb, kind, pos, ms, doff, gsrc, d0, len);      // byte by byte (rare): input edges, periodic matches
                 }
                 const uint4 mlo = k.lt[d0], mhi = k.lt[d0 + len];
                 const unsigned cro = ring_off(k, c00 + 16u * cc);
