@@ -38,7 +38,7 @@ namespace lz4k {
 constexpr int W = 8192;                    // compressed bytes per window
 constexpr int HALO = 320;                  // bytes after the window that token fields may be read from
 constexpr int VIS = W + HALO;
-constexpr int NFW = (VIS + 31) / 32 + 2;   // words of the 0xFF bitmask
+constexpr int NFW = (16 + VIS + 31) / 32 + 2;   // words of the 0xFF bitmask (bit i = byte i of the staged chunk, i.e. window position + lead)
 constexpr int CHUNK_BYTES = 16 + VIS + 176;
 constexpr int PT = 256;                    // parse: 8 warps, one 1 KiB group each
 constexpr int SLOT = W / 3 + 3;            // sequence descriptors per window (a token is >= 3 bytes, except the last of a block)
@@ -134,6 +134,7 @@ struct ParseSmem {
     __align__(16) uint8_t chunk[CHUNK_BYTES];
     __align__(16) uint16_t exitB[W];
     uint32_t ff[NFW + 2];
+    uint32_t lead;
     uint16_t nfull[NFW + 2];
     uint32_t gentry[8], wcnt[8], wlen[8];
     int wmargin[8];
@@ -145,7 +146,8 @@ struct ParseSmem {
 };
 
 // number of consecutive 0xFF bytes starting at window position x (bits beyond the visible limit are 0)
-__device__ __forceinline__ unsigned ff_run(const ParseSmem& sm, unsigned x) {
+__device__ __forceinline__ unsigned ff_run(const ParseSmem& sm, unsigned xw) {
+    const unsigned x = xw + sm.lead;                                   // the mask is indexed by chunk byte
     const unsigned k = x >> 5, j = x & 31;
     unsigned r = (unsigned)__ffs((int)~(sm.ff[k] >> j)) - 1u;   // j == 0 and a full word: ffs(0) - 1 = 0xffffffff
     if (r >= 32u - j) {
@@ -243,15 +245,32 @@ lz4_parse_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict
         const unsigned widx = wbase[b] + w;
         const unsigned lead = (unsigned)((uintptr_t)(in + base) & 15);
         const uint8_t* c = sm.chunk + lead;
-        if (tid == 0) { issue_window(sm.chunk, &sm.bar, in, n, base); sm.t_kind = TK_NONE; }
+        if (tid == 0) { issue_window(sm.chunk, &sm.bar, in, n, base); sm.t_kind = TK_NONE; sm.lead = lead; }
         if (tid < 8) sm.gentry[tid] = NONE;
         mbar_wait(&sm.bar, phase); phase ^= 1;
 
-        // ---- 0xFF bitmask of the visible bytes + runs of full words
-        for (unsigned k = warp; k < (unsigned)NFW + 2; k += PT / 32) {
-            const unsigned p = k * 32 + lane;
-            const unsigned m = __ballot_sync(RCZ_FULL, p < lim && c[p] == 0xFFu);
-            if (lane == 0) sm.ff[k] = m;
+        // ---- 0xFF bitmask of the visible bytes + runs of full words: 16 chunk bytes per lane (one aligned 16-byte load, a
+        //      per-byte compare and a multiply that gathers the four result bits), two lanes make a mask word
+        for (unsigned it = warp; it * 512u < 32u * ((unsigned)NFW + 2u); it += PT / 32) {
+            const unsigned i0 = it * 512u + lane * 16u;                   // first chunk byte of this lane
+            unsigned m16 = 0;
+            if (i0 < (unsigned)CHUNK_BYTES) {
+                const uint4 q = *reinterpret_cast<const uint4*>(sm.chunk + i0);
+                const unsigned wv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned x = ~wv[k];                             // a 0xFF byte becomes 0x00
+                    const unsigned t = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;   // top bit of every zero byte (no borrows)
+                    m16 |= ((((t >> 7) * 0x00204081u) >> 21) & 0x0fu) << (4 * k);                // bits 0, 8, 16, 24 -> one nibble
+                }
+                const unsigned lo = lead, hi = lead + lim;                // valid chunk bytes [lo, hi)
+                const unsigned a = lo > i0 ? (lo - i0 < 16u ? lo - i0 : 16u) : 0u, b = hi > i0 ? (hi - i0 < 16u ? hi - i0 : 16u) : 0u;
+                m16 &= ((1u << b) - 1u) & ~((1u << a) - 1u);
+            }
+            unsigned v = m16 << (16u * (lane & 1u));
+            v |= __shfl_xor_sync(RCZ_FULL, v, 1);
+            const unsigned k = it * 16u + (lane >> 1);
+            if (!(lane & 1u) && k < (unsigned)NFW + 2u) sm.ff[k] = v;
         }
         __syncthreads();
         if (warp == 0) {
