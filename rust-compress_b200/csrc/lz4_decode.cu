@@ -298,7 +298,7 @@ lz4_parse_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict
             // vote was measured: slower)
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                const unsigned t2 = __shfl_sync(RCZ_FULL, a, (int)(a & 31u));
+                const unsigned t2 = __shfl_sync(RCZ_FULL, a, (int)a);          // (the source lane is taken modulo 32: position a of this segment)
                 if (a < se) a = t2;                                       // TERM codes are >= 0x8000: never inside the segment
             }
             if (s & 1) aA[s >> 1] = a << 16; else aA[s >> 1] |= a;
@@ -353,7 +353,7 @@ lz4_parse_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict
                 if (cur != NONE && (cur >> 5) == (gbase >> 5) + (unsigned)s) {      // warp-uniform
                     if (lane == (unsigned)s) myEntry = cur;
                     const unsigned av = (s & 1) ? (aA[s >> 1] >> 16) : (aA[s >> 1] & 0xffffu);
-                    const unsigned a = __shfl_sync(RCZ_FULL, av, (int)(cur & 31u));
+                    const unsigned a = __shfl_sync(RCZ_FULL, av, (int)cur);
                     cur = a < gend ? a : NONE;
                 }
             }
