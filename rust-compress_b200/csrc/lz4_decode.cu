@@ -205,8 +205,9 @@ __device__ __forceinline__ bool tok_fast(const ParseSmem& sm, const uint8_t* c, 
 
 // Level A only needs where the token ends: the same decision as tok_fast without the fields (no TokF in the common path:
 // its address would escape to tok_gen and put it in local memory).
-__device__ __forceinline__ unsigned tok_next(const ParseSmem& sm, const uint8_t* c, unsigned p, unsigned lim, unsigned limq, unsigned e_rel) {
-    const unsigned tk = c[p], b1 = c[p + 1];
+__device__ __forceinline__ unsigned tok_next(const ParseSmem& sm, const uint8_t* c, const uint8_t* cp /* = c + p, with a compile-time offset */,
+                                             unsigned p, unsigned lim, unsigned limq, unsigned e_rel) {
+    const unsigned tk = cp[0], b1 = cp[1];
     const unsigned L4 = tk >> 4, M4 = tk & 15u;
     const bool l15 = L4 == 15u, m15 = M4 == 15u;
     const unsigned q = p + 1u + (l15 ? 1u + b1 : 0u) + L4;
@@ -291,9 +292,12 @@ lz4_parse_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict
         const unsigned gbase = warp * 1024u, gend = gbase + 1024u;
         unsigned aA[16];                                                  // exit of (segment s, this lane) from the segment, two per register
 #pragma unroll
+        const unsigned pbase = gbase + lane;                              // position of this lane in segment 0 of the group
+        const uint8_t* const cpb = c + pbase;
+        uint16_t* const ebb = sm.exitB + pbase;
         for (int s = 31; s >= 0; --s) {
-            const unsigned sb = gbase + (unsigned)s * 32u, se = sb + 32u, p = sb + lane;
-            unsigned a = tok_next(sm, c, p, lim, limq, e_rel);
+            const unsigned se = gbase + (unsigned)s * 32u + 32u, p = pbase + (unsigned)s * 32u;
+            unsigned a = tok_next(sm, c, cpb + s * 32, p, lim, limq, e_rel);
             // pointer doubling inside the segment; a token is >= 3 bytes, so 4 rounds always suffice (an early exit on a warp
             // vote was measured: slower)
 #pragma unroll
@@ -304,7 +308,7 @@ lz4_parse_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict
             if (s & 1) aA[s >> 1] = a << 16; else aA[s >> 1] |= a;
             unsigned bb = a;
             if (a < gend) bb = sm.exitB[a];                               // a later segment of this group: already final
-            sm.exitB[p] = (uint16_t)bb;
+            ebb[s * 32] = (uint16_t)bb;
             __syncwarp();
         }
         __syncthreads();
