@@ -218,7 +218,7 @@ __device__ __forceinline__ unsigned tok_next(const ParseSmem& sm, const uint8_t*
     return ok ? nx : (TERM | p);
 }
 
-__global__ void __launch_bounds__(PT, 4)
+__global__ void __launch_bounds__(PT, 5)
 lz4_parse_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ in_len,
                  const uint32_t* __restrict__ wbase, const uint2* __restrict__ tickets, unsigned nticket,
                  unsigned long long* chain, WinInfo* __restrict__ winfo, SeqEnt* __restrict__ seqs, unsigned* ticket_ctr) {
@@ -882,7 +882,7 @@ static int lz4_enqueue(rcz_ctx* c, rt_stream_t stream, const Lz4Dev& d, size_t r
     const bool timed = stream == c->stream;                                  // single-shot path: per-kernel event marks
     if (timed) { int st = ctx_stage_mark(c, 0); if (st) return st; }
     if (ntk) {
-        const size_t g1 = std::min<size_t>(ntk, (size_t)c->sm_count * 4);
+        const size_t g1 = std::min<size_t>(ntk, (size_t)c->sm_count * 5);
         RCZ_LAUNCH(lz4_parse_kernel, (unsigned)g1, PT, sizeof(ParseSmem), stream, din, in_off, in_len, d.wbase, tk, (unsigned)ntk, d.chain, d.winfo, d.seqs, ctr);
         c->launches++;
         RCZ_CK(c, rt_last_error());
