@@ -1,5 +1,5 @@
 #!/bin/bash
-for cb in 16777216 33554432 67108864 134217728 268435456; do
+for cb in 33554432 50331648 67108864 100663296; do
 echo "chunk=$cb"
 RCZ_LZ4_CHUNK_BYTES=$cb timeout 300 python bench.py --steps 10 --warmup 3 2>&1 | tail -1 | python -c "
 import sys, json
