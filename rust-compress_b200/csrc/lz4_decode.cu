@@ -514,7 +514,7 @@ __device__ __forceinline__ unsigned ld_gen_u8(uintptr_t a) { return *(volatile c
 
 struct MatCtx {
     const SeqEnt* D; const SeqEnt* ds; const uint4* lt; uint32_t* cmask;
-    const uint8_t* in; uint8_t* outb; uint8_t* ring; rcz_saddr rings, wins;
+    const uint8_t* in; uint8_t* outb; uint8_t* ring; rcz_saddr rings, wins, cmasks;
     unsigned ob, uend, nseq, n, cbase, limw, hb, T0, T1, h, c00, nch, tend;
 };
 __device__ __forceinline__ uint4 mat_desc(const MatCtx& k, unsigned j) {
@@ -640,8 +640,8 @@ __device__ __forceinline__ void mat_piece(const MatCtx& k, const uint16_t* sbase
         bool progressed = false;
         bool ready = true;
         if (DEP && !done) {
-            if (cA != NOCHK) ready = (*(volatile uint32_t*)&k.cmask[cA] & mA) == mA;
-            if (cB != NOCHK) ready = ready && (*(volatile uint32_t*)&k.cmask[cB] & mB) == mB;
+            if (cA != NOCHK) ready = (lds32_volatile(k.cmasks + 4u * cA) & mA) == mA;          // (shared-memory loads, not generic ones)
+            if (cB != NOCHK) ready = ready && (lds32_volatile(k.cmasks + 4u * cB) & mB) == mB;
         }
         if (!done) {
             if (ready) {
@@ -750,7 +750,7 @@ lz4_mat_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__
         k.hb = (unsigned)((uintptr_t)k.outb & 15);
         k.ring = sm.ring_ + 32;
         k.rings = saddr_of(k.ring);
-        k.lt = sm.lt; k.cmask = sm.cmask;
+        k.lt = sm.lt; k.cmask = sm.cmask; k.cmasks = saddr_of(sm.cmask);
         if (tid == 0) { fence_proxy_async_smem(); mat_prefetch(sm, 0, wb, winfo, obase, seqs, k.in, k.n); }
 
         for (unsigned w = 0; w < nw; ++w) {
