@@ -509,8 +509,9 @@ struct MatSmem {
     rcz_mbar barw[2], bard[2];
 };
 
-__device__ __forceinline__ unsigned ld_gen_u32(uintptr_t a) { return *(volatile const unsigned*)a; }
-__device__ __forceinline__ unsigned ld_gen_u8(uintptr_t a) { return *(volatile const uint8_t*)a; }
+// literal bytes straight from the block's input (never written by these kernels): read-only path
+__device__ __forceinline__ unsigned ld_gen_u32(uintptr_t a) { return __ldg(reinterpret_cast<const unsigned*>(a)); }
+__device__ __forceinline__ unsigned ld_gen_u8(uintptr_t a) { return __ldg(reinterpret_cast<const uint8_t*>(a)); }
 
 struct MatCtx {
     const SeqEnt* D; const SeqEnt* ds; const uint4* lt; uint32_t* cmask;
