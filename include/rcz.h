@@ -160,6 +160,27 @@ int rcz_dc_decode_blocks(rcz_ctx* ctx, const uint32_t* in_base, const uint64_t* 
                          void* out_base, const uint64_t* out_off, const uint64_t* n, int32_t* status,
                          size_t nblocks, int mem_kind);
 
+/* ---------------- bwt -> dc -> entropy::ari (BASELINE configs[4]; "BWT + DC + EC", bwt/mod.rs:11-14) ----------------
+ * The three stage calls above chained on the device: rcz_bwt_encode_blocks (bwt/mod.rs:136-204), rcz_dc_encode_blocks
+ * (dc.rs:62-159), then `ByteEncoder` (table.rs:203-219) over the dc output serialised as init[256] followed by the distances,
+ * each a u32 LE; the decoder runs table.rs:255-272, dc.rs:162-252 and bwt/mod.rs:223-294.  No stage result visits the host.
+ * The reference has no wire format for this chain (dc is in-memory only), so the container is this library's:
+ *   u32 LE x 6: magic "BDA1", n, origin, nsym (256 + number of distances), ari_chunk, nstreams; nstreams x u32 LE code
+ *   length; then the code bytes of the streams back to back.
+ * ari_chunk = 0 codes the serialised bytes of a block as ONE ByteEncoder stream; ari_chunk = k (multiple of 4, >= 1024)
+ * cuts them into independent ByteEncoder streams of k bytes (the range coder is one serial chain per stream).
+ * encode: block i = in_base[in_off[i] .. +n[i]] -> container at out_base[out_off[i] ..], out_len[i] <= out_cap[i] bytes;
+ *         origin[i] (optional) = the BWT origin.  n[i] <= 16,777,214 (24-bit positions of the inverse transform).
+ * decode: container i = in_base[in_off[i] .. +in_len[i]]; n[i] = the block's decoded size (the caller's framing knows it, as
+ *         bwt/mod.rs:463 writes it in front of every block); a container whose header disagrees is RCZ_E_INVALID_INPUT.
+ * rcz_last_stage_ms: encode = {bwt, dc, ari, pack}, decode = {ari, dc, bwt}. */
+int rcz_bwt_dc_ari_encode_blocks(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* n,
+                                 void* out_base, const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len,
+                                 uint32_t* origin, int32_t* status, size_t nblocks, uint32_t ari_chunk, int mem_kind);
+int rcz_bwt_dc_ari_decode_blocks(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                                 void* out_base, const uint64_t* out_off, const uint64_t* n, uint64_t* out_len,
+                                 int32_t* status, size_t nblocks, uint32_t ari_chunk, int mem_kind);
+
 /* ---------------- bwt/mtf.rs ----------------
  * rcz_mtf_encode_streams replaces `mtf::Encoder<W>::write` (mtf.rs:118-125: `MTF::encode` per byte, alphabetical start
  * list), rcz_mtf_decode_streams replaces `mtf::Decoder<R>::read` (mtf.rs:155-168: `MTF::decode` per byte).  One

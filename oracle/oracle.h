@@ -114,6 +114,15 @@ int orc_ari_encode(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t
 int orc_ari_decode(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* out_len,
                    size_t* consumed_read, size_t* consumed_finish);
 
+/* ---- bwt -> dc -> ari composition (pipeline.cpp; the composition and container are this project's, the stages the reference's) ---- */
+int orc_bda_encode_block(const uint8_t* in, size_t n, uint32_t chunk, uint8_t* out, size_t cap, size_t* out_len, uint32_t* origin);
+int orc_bda_decode_block(const uint8_t* in, size_t in_len, size_t n, uint32_t chunk, uint8_t* out, size_t* out_len);
+int orc_bda_encode_blocks_mt(const uint8_t* in_base, const uint64_t* in_off, const uint64_t* n, uint32_t chunk, uint8_t* out_base,
+                             const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len, uint32_t* origin, int32_t* status,
+                             size_t nblocks, int nthreads);
+int orc_bda_decode_blocks_mt(const uint8_t* in_base, const uint64_t* in_off, const uint64_t* in_len, uint32_t chunk, uint8_t* out_base,
+                             const uint64_t* out_off, const uint64_t* n, uint64_t* out_len, int32_t* status, size_t nblocks, int nthreads);
+
 /* ---- checksum/adler.rs (used only to cross-check fixtures) ---- */
 uint32_t orc_adler32(const uint8_t* in, size_t n);
 

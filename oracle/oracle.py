@@ -267,3 +267,28 @@ def flate_decode_streams_mt(in_buf, in_off, in_len, out_buf, out_off, out_cap, n
                                       out_buf.ctypes.data_as(C.c_void_p), out_off.ctypes.data_as(C.c_void_p), out_cap.ctypes.data_as(C.c_void_p),
                                       out_len.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p), C.c_size_t(nb), C.c_int(nthreads))
     return out_len, status
+
+
+def bda_encode_blocks_mt(in_buf, in_off, n, chunk, out_buf, out_off, out_cap, nthreads):
+    """bwt -> dc -> ari composition (oracle/pipeline.cpp). Returns (out_len, origin, status)."""
+    nb = len(in_off)
+    in_off, n, out_off, out_cap = map(_desc, (in_off, n, out_off, out_cap))
+    out_len = np.zeros(nb, dtype=np.uint64)
+    origin = np.zeros(nb, dtype=np.uint32)
+    status = np.zeros(nb, dtype=np.int32)
+    lib().orc_bda_encode_blocks_mt(in_buf.ctypes.data_as(C.c_void_p), in_off.ctypes.data_as(C.c_void_p), n.ctypes.data_as(C.c_void_p), C.c_uint32(chunk),
+                                   out_buf.ctypes.data_as(C.c_void_p), out_off.ctypes.data_as(C.c_void_p), out_cap.ctypes.data_as(C.c_void_p),
+                                   out_len.ctypes.data_as(C.c_void_p), origin.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p),
+                                   C.c_size_t(nb), C.c_int(nthreads))
+    return out_len, origin, status
+
+
+def bda_decode_blocks_mt(in_buf, in_off, in_len, chunk, out_buf, out_off, n, nthreads):
+    nb = len(in_off)
+    in_off, in_len, out_off, n = map(_desc, (in_off, in_len, out_off, n))
+    out_len = np.zeros(nb, dtype=np.uint64)
+    status = np.zeros(nb, dtype=np.int32)
+    lib().orc_bda_decode_blocks_mt(in_buf.ctypes.data_as(C.c_void_p), in_off.ctypes.data_as(C.c_void_p), in_len.ctypes.data_as(C.c_void_p), C.c_uint32(chunk),
+                                   out_buf.ctypes.data_as(C.c_void_p), out_off.ctypes.data_as(C.c_void_p), n.ctypes.data_as(C.c_void_p),
+                                   out_len.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p), C.c_size_t(nb), C.c_int(nthreads))
+    return out_len, status

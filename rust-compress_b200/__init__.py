@@ -8,7 +8,7 @@ Layers
   rust-compress_b200/csrc       hand-written CUDA kernels + the ABI implementation
   rust-compress_b200/_abi.py    ctypes binding
   this module                   `Context`: batched per-block calls on numpy (host) or torch (device) buffers
-  .lz4 .bwt .flate .ari .rle .dc   host-side mirrors of the crate's Decoder<R>/Encoder<W> types and free functions
+  rust-compress_b200/host/rcz_stream.hpp   C++ mirrors of the crate's Decoder<R>/Encoder<W> types (the Rust shim is rust/rcz_sys.rs)
 """
 import ctypes as C
 
@@ -104,8 +104,8 @@ class Context:
     def last_stage_ms(self):
         """Per-kernel durations of the most recent multi-kernel batch call (lz4: parse, scan, materialise)."""
         import ctypes
-        buf = (ctypes.c_float * 4)()
-        n = self._lib.rcz_last_stage_ms(self._h, buf, 4)
+        buf = (ctypes.c_float * 8)()
+        n = self._lib.rcz_last_stage_ms(self._h, buf, 8)
         return [float(buf[i]) for i in range(n)]
 
     def _check(self, st, what):
@@ -239,6 +239,29 @@ class Context:
                                             _ptr(status), nb, kind)
         self._check(st, "rcz_dc_decode_blocks")
         return status
+
+    # ---- bwt -> dc -> ari pipeline (BASELINE configs[4]) ------------------------------------------------------
+    def bwt_dc_ari_encode_blocks(self, in_buf, in_off, n_arr, out_buf, out_off, out_cap, ari_chunk=65536, async_=False):
+        """rcz_bwt_dc_ari_encode_blocks.  Returns (out_len, origin, status) arrays."""
+        kind = _kind_of(in_buf, async_)
+        nb = len(in_off)
+        io, na, oo, oc = map(_u64, (in_off, n_arr, out_off, out_cap))
+        out_len, origin, status = self._results(kind, nb, in_buf, [np.uint64, np.uint32, np.int32])
+        st = self._lib.rcz_bwt_dc_ari_encode_blocks(self._h, _ptr(in_buf), _ptr(io), _ptr(na), _ptr(out_buf), _ptr(oo), _ptr(oc),
+                                                    _ptr(out_len), _ptr(origin), _ptr(status), nb, int(ari_chunk), kind)
+        self._check(st, "rcz_bwt_dc_ari_encode_blocks")
+        return out_len, origin, status
+
+    def bwt_dc_ari_decode_blocks(self, in_buf, in_off, in_len, out_buf, out_off, n_arr, ari_chunk=65536, async_=False):
+        """rcz_bwt_dc_ari_decode_blocks.  Returns (out_len, status) arrays."""
+        kind = _kind_of(in_buf, async_)
+        nb = len(in_off)
+        io, il, oo, na = map(_u64, (in_off, in_len, out_off, n_arr))
+        out_len, status = self._results(kind, nb, in_buf, [np.uint64, np.int32])
+        st = self._lib.rcz_bwt_dc_ari_decode_blocks(self._h, _ptr(in_buf), _ptr(io), _ptr(il), _ptr(out_buf), _ptr(oo), _ptr(na),
+                                                    _ptr(out_len), _ptr(status), nb, int(ari_chunk), kind)
+        self._check(st, "rcz_bwt_dc_ari_decode_blocks")
+        return out_len, status
 
     # ---- rle -----------------------------------------------------------------------------------------------
     def rle_decode_streams(self, in_buf, in_off, in_len, out_buf, out_off, out_cap, async_=False):

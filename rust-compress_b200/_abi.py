@@ -43,6 +43,8 @@ SIGNATURES = {
     "rcz_ari_decode_streams": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I]),
     "rcz_dc_encode_blocks": (_I, _BATCH),
     "rcz_dc_decode_blocks": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I]),
+    "rcz_bwt_dc_ari_encode_blocks": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, C.c_uint32, _I]),
+    "rcz_bwt_dc_ari_decode_blocks": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, C.c_uint32, _I]),
     "rcz_rle_decode_streams": (_I, _BATCH),
     "rcz_rle_encode_streams": (_I, _BATCH),
     "rcz_mtf_encode_streams": (_I, _BATCH),

@@ -107,6 +107,7 @@ ari_encode_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restric
         const unsigned long long n = in_len[sidx];
         uint8_t* out = out_base + out_off[sidx];
         const unsigned long long cap = out_cap[sidx];
+        if (n == RCZ_STREAM_SKIP) { if (lane == 0) { out_len[sidx] = 0; status[sidx] = RCZ_OK; } continue; }   // unused slot of a composed call
         Model m; m.init(lane);
         unsigned low = 0, hai = 0xFFFFFFFFu;
         unsigned long long o = 0;
@@ -144,6 +145,7 @@ ari_decode_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restric
         const unsigned long long n = in_len[sidx];
         uint8_t* out = out_base + out_off[sidx];
         const unsigned long long cap = out_cap[sidx];
+        if (n == RCZ_STREAM_SKIP) { if (lane == 0) { out_len[sidx] = 0; status[sidx] = RCZ_OK; if (in_used) in_used[sidx] = 0; } continue; }
         Model m; m.init(lane);
         unsigned low = 0, hai = 0xFFFFFFFFu, code = 0, pending = 4;
         unsigned long long p = 0, o = 0;
@@ -179,6 +181,18 @@ ari_decode_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restric
 
 }  // namespace arik
 
+// all descriptor / result arrays are DEVICE pointers (composed calls: pipeline.cu); only enqueues
+int rcz_ari_launch(rcz_ctx* c, bool decode, const uint8_t* din, const uint64_t* d_in_off, const uint64_t* d_in_len, uint8_t* dout,
+                   const uint64_t* d_out_off, const uint64_t* d_out_cap, uint64_t* d_out_len, uint64_t* d_in_used, int32_t* d_status, size_t n) {
+    if (n == 0) return RCZ_OK;
+    const unsigned grid = (unsigned)std::min<size_t>((n + 3) / 4, (size_t)c->sm_count * 16);
+    if (decode)
+        RCZ_KLAUNCH(c, arik::ari_decode_kernel, grid, arik::NT, 0, din, d_in_off, d_in_len, dout, d_out_off, d_out_cap, d_out_len, d_in_used, d_status, (unsigned)n);
+    else
+        RCZ_KLAUNCH(c, arik::ari_encode_kernel, grid, arik::NT, 0, din, d_in_off, d_in_len, dout, d_out_off, d_out_cap, d_out_len, d_status, (unsigned)n);
+    return RCZ_OK;
+}
+
 static int ari_batch(rcz_ctx* c, bool decode, const void* in_base, const uint64_t* in_off, const uint64_t* in_len, void* out_base,
                      const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len, uint64_t* in_used, int32_t* status, size_t n,
                      int mem_kind) {
@@ -197,15 +211,10 @@ static int ari_batch(rcz_ctx* c, bool decode, const void* in_base, const uint64_
         st = stage_span_in(c, WS_IN, in_base, in_off, in_len, n, 1, &din); if (st) return st;
         st = stage_span_out(c, WS_OUT, out_off, out_cap, n, 1, &dout); if (st) return st;
     }
-    const unsigned grid = (unsigned)std::min<size_t>((n + 3) / 4, (size_t)c->sm_count * 16);
     st = ctx_timer_begin(c); if (st) return st;
-    if (decode)
-        RCZ_KLAUNCH(c, arik::ari_decode_kernel, grid, arik::NT, 0, din, ds.in_ptr<uint64_t>(0), ds.in_ptr<uint64_t>(1), dout, ds.in_ptr<uint64_t>(2),
-                    ds.in_ptr<uint64_t>(3), ds.out_ptr<uint64_t>(0), in_used ? ds.out_ptr<uint64_t>(o_used) : (uint64_t*)nullptr,
-                    ds.out_ptr<int32_t>(1), (unsigned)n);
-    else
-        RCZ_KLAUNCH(c, arik::ari_encode_kernel, grid, arik::NT, 0, din, ds.in_ptr<uint64_t>(0), ds.in_ptr<uint64_t>(1), dout, ds.in_ptr<uint64_t>(2),
-                    ds.in_ptr<uint64_t>(3), ds.out_ptr<uint64_t>(0), ds.out_ptr<int32_t>(1), (unsigned)n);
+    st = rcz_ari_launch(c, decode, din, ds.in_ptr<uint64_t>(0), ds.in_ptr<uint64_t>(1), dout, ds.in_ptr<uint64_t>(2), ds.in_ptr<uint64_t>(3),
+                        ds.out_ptr<uint64_t>(0), (decode && in_used) ? ds.out_ptr<uint64_t>(o_used) : (uint64_t*)nullptr, ds.out_ptr<int32_t>(1), n);
+    if (st) return st;
     st = ctx_timer_end(c); if (st) return st;
     st = ds.download(); if (st) return st;
     if (mem_kind == RCZ_MEM_HOST) {

@@ -45,6 +45,7 @@ struct Blk {
     unsigned max_chains;
     unsigned work0;        // first index of this block's initial work items (K + 1 of them)
     unsigned skip;         // block rejected on the host (status already set)
+    unsigned bad;          // origin supplied on the device (composed calls) and out of range: walked with origin 0, reported MALFORMED
 };
 
 // ------------------------------------------------------------------------------------------ A: histogram
@@ -342,7 +343,7 @@ ibwt_rank_kernel(const Blk* __restrict__ blks, const Desc* __restrict__ desc_bas
             cur = s;
         }
     }
-    if (tid == 0) { out_len[b] = total; status[b] = 0; }
+    if (tid == 0) { out_len[b] = bk.bad ? 0 : total; status[b] = bk.bad ? RCZ_E_MALFORMED : RCZ_OK; }
 }
 
 // ------------------------------------------------------------------------------------------ F: compact
@@ -375,11 +376,20 @@ ibwt_compact_kernel(const Blk* __restrict__ blks, const uint8_t* __restrict__ sc
     }
 }
 
-__global__ void ibwt_init_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned* __restrict__ chain_ctr, unsigned* __restrict__ queue,
-                                 uint64_t* __restrict__ out_len, int32_t* __restrict__ status, const int32_t* __restrict__ host_status) {
+// origin_dev (optional): the origins live in device memory (bwt -> dc -> ari pipeline); they are patched into the block table here,
+// before any other kernel of the group reads it
+__global__ void ibwt_init_kernel(Blk* __restrict__ blks, unsigned nblocks, unsigned* __restrict__ chain_ctr, unsigned* __restrict__ queue,
+                                 uint64_t* __restrict__ out_len, int32_t* __restrict__ status, const int32_t* __restrict__ host_status,
+                                 const uint32_t* __restrict__ origin_dev) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) *queue = 0;
     if (i < nblocks) {
+        if (origin_dev && !blks[i].skip) {
+            const unsigned o = origin_dev[i];
+            const bool ok = o < blks[i].n;                                   // bwt/mod.rs:230 index panic otherwise
+            blks[i].origin = ok ? o : 0u;
+            blks[i].bad = ok ? 0u : 1u;
+        }
         chain_ctr[i] = blks[i].K + 1;
         if (blks[i].skip) { out_len[i] = 0; status[i] = host_status[i]; }
     }
@@ -390,10 +400,17 @@ __global__ void ibwt_init_kernel(const Blk* __restrict__ blks, unsigned nblocks,
 extern "C" int rcz_bwt_decode_blocks(rcz_ctx* c, const void* in_base, const uint64_t* in_off, const uint64_t* n_arr,
                                      const uint32_t* origin, void* out_base, const uint64_t* out_off,
                                      uint64_t* out_len, int32_t* status, size_t nblocks, int mem_kind) {
+    if (nblocks && !origin) return RCZ_E_ARG;
+    return rcz_bwt_decode_run(c, in_base, in_off, n_arr, origin, nullptr, out_base, out_off, out_len, status, nblocks, mem_kind);
+}
+
+int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, const uint64_t* n_arr, const uint32_t* origin,
+                       const uint32_t* origin_dev, void* out_base, const uint64_t* out_off, uint64_t* out_len, int32_t* status,
+                       size_t nblocks, int mem_kind) {
     using namespace ibwt;
     if (!c || rcz_bad_kind(mem_kind)) return RCZ_E_ARG;
     if (nblocks == 0) return RCZ_OK;
-    if (!in_base || !in_off || !n_arr || !origin || !out_base || !out_off || !out_len || !status) return RCZ_E_ARG;
+    if (!in_base || !in_off || !n_arr || (!origin && !origin_dev) || !out_base || !out_off || !out_len || !status) return RCZ_E_ARG;
     if (nblocks > 0x3fffffu) return RCZ_E_ARG;
     rt_set_device(c->device);
 
@@ -424,9 +441,9 @@ extern "C" int rcz_bwt_decode_blocks(rcz_ctx* c, const void* in_base, const uint
         b.chain0 = (unsigned)cur.chains; b.work0 = (unsigned)cur.work;
         b.p_off = (unsigned)cur.p_elems; b.scratch_off = cur.scratch_bytes;
         cur.b1 = i + 1;
-        if (n == 0 || origin[i] >= n) { b.skip = 1; hstatus[i] = RCZ_E_MALFORMED; continue; }   // bwt/mod.rs:230 index panic
+        if (n == 0 || (!origin_dev && origin[i] >= n)) { b.skip = 1; hstatus[i] = RCZ_E_MALFORMED; continue; }   // bwt/mod.rs:230 index panic
         if (n > MAX_N) { b.skip = 1; hstatus[i] = RCZ_E_UNSUPPORTED; continue; }
-        b.n = (unsigned)n; b.origin = origin[i];
+        b.n = (unsigned)n; b.origin = origin_dev ? 0u : origin[i];
         unsigned slog = tune_slog;
         while ((n >> slog) > 65536) ++slog;                   // keep <= 64 Ki sampled rows per block
         b.stride_log2 = slog;
@@ -485,11 +502,12 @@ extern "C" int rcz_bwt_decode_blocks(rcz_ctx* c, const void* in_base, const uint
     for (auto& g : groups) {
         const unsigned nb = (unsigned)(g.b1 - g.b0);
         if (nb == 0) continue;
-        const Blk* dblk = ds.in_ptr<Blk>(i_blk) + g.b0;
+        Blk* dblk = const_cast<Blk*>(ds.in_ptr<Blk>(i_blk)) + g.b0;
         const unsigned* dt2b = ds.in_ptr<unsigned>(i_t2b) + g.tile0_abs;
         uint64_t* d_len = ds.out_ptr<uint64_t>(o_len) + g.b0;
         int32_t* d_st = ds.out_ptr<int32_t>(o_st) + g.b0;
-        RCZ_KLAUNCH(c, ibwt_init_kernel, (nb + 255) / 256, 256, 0, dblk, nb, chain_ctr, queue, d_len, d_st, ds.in_ptr<int32_t>(i_hst) + g.b0);
+        RCZ_KLAUNCH(c, ibwt_init_kernel, (nb + 255) / 256, 256, 0, dblk, nb, chain_ctr, queue, d_len, d_st, ds.in_ptr<int32_t>(i_hst) + g.b0,
+                    origin_dev ? origin_dev + g.b0 : (const uint32_t*)nullptr);
         if (!g.ntiles) continue;
         RCZ_KLAUNCH(c, ibwt_hist_kernel, g.ntiles, NT_TILE, 0, din, dblk, dt2b, tile_hist);
         RCZ_KLAUNCH(c, ibwt_scan_kernel, nb, 256, 0, dblk, tile_hist, cbase);

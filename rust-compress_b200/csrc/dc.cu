@@ -304,6 +304,14 @@ extern "C" int rcz_dc_encode_blocks(rcz_ctx* c, const void* in_base, const uint6
     return RCZ_OK;
 }
 
+int rcz_dc_decode_launch(rcz_ctx* c, const uint32_t* din, const uint64_t* d_in_off, const uint64_t* d_in_len, uint8_t* dout,
+                         const uint64_t* d_out_off, const uint64_t* d_n, int32_t* d_status, size_t nblocks) {
+    if (nblocks == 0) return RCZ_OK;
+    const unsigned grid = (unsigned)std::min<size_t>((nblocks + dck::WPB - 1) / dck::WPB, (size_t)c->sm_count * 16);
+    RCZ_KLAUNCH(c, dck::dc_decode_kernel, grid, dck::NT, 0, din, d_in_off, d_in_len, dout, d_out_off, d_n, d_status, (unsigned)nblocks);
+    return RCZ_OK;
+}
+
 extern "C" int rcz_dc_decode_blocks(rcz_ctx* c, const uint32_t* in_base, const uint64_t* in_off, const uint64_t* in_len, void* out_base,
                                     const uint64_t* out_off, const uint64_t* n_arr, int32_t* status, size_t nblocks, int mem_kind) {
     if (!c || rcz_bad_kind(mem_kind)) return RCZ_E_ARG;
@@ -319,10 +327,10 @@ extern "C" int rcz_dc_decode_blocks(rcz_ctx* c, const uint32_t* in_base, const u
         st = stage_span_in(c, WS_IN, in_base, in_off, in_len, nblocks, 4, &din); if (st) return st;
         st = stage_span_out(c, WS_OUT, out_off, n_arr, nblocks, 1, &dout); if (st) return st;
     }
-    const unsigned grid = (unsigned)std::min<size_t>((nblocks + dck::WPB - 1) / dck::WPB, (size_t)c->sm_count * 16);
     st = ctx_timer_begin(c); if (st) return st;
-    RCZ_KLAUNCH(c, dck::dc_decode_kernel, grid, dck::NT, 0, (const uint32_t*)din, ds.in_ptr<uint64_t>(0), ds.in_ptr<uint64_t>(1), dout,
-                ds.in_ptr<uint64_t>(2), ds.in_ptr<uint64_t>(3), ds.out_ptr<int32_t>(0), (unsigned)nblocks);
+    st = rcz_dc_decode_launch(c, (const uint32_t*)din, ds.in_ptr<uint64_t>(0), ds.in_ptr<uint64_t>(1), dout, ds.in_ptr<uint64_t>(2), ds.in_ptr<uint64_t>(3),
+                              ds.out_ptr<int32_t>(0), nblocks);
+    if (st) return st;
     st = ctx_timer_end(c); if (st) return st;
     st = ds.download(); if (st) return st;
     if (mem_kind == RCZ_MEM_HOST) {

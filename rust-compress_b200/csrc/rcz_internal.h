@@ -5,7 +5,9 @@
 #include <stdio.h>
 #include <vector>
 
-enum { WS_IN = 0, WS_OUT = 1, WS_DESC = 2, WS_A = 3, WS_B = 4, WS_C = 5, WS_D = 6, WS_E = 7, WS_COUNT = 8 };
+// WS_P*: intermediates owned by a composed call (pipeline.cu) that must survive the nested stage calls
+enum { WS_IN = 0, WS_OUT = 1, WS_DESC = 2, WS_A = 3, WS_B = 4, WS_C = 5, WS_D = 6, WS_E = 7, WS_P0 = 8, WS_P1 = 9, WS_P2 = 10, WS_P3 = 11, WS_P4 = 12, WS_COUNT = 13 };
+constexpr int RCZ_MAX_STAGES = 8;
 
 struct rcz_ctx {
     int device = 0;
@@ -15,8 +17,9 @@ struct rcz_ctx {
     uint64_t launches = 0;
     rt_event_t ev0 = 0, ev1 = 0;
     bool ev_valid = false;
-    rt_event_t stage_ev[5] = {};      // stage boundaries of the most recent multi-kernel call
+    rt_event_t stage_ev[RCZ_MAX_STAGES + 1] = {};   // stage boundaries of the most recent multi-kernel call
     int nstage = 0;
+    int nest = 0;                     // > 0 while a composed call (pipeline.cu) drives the stage entry points: they leave the timers alone
     char err[256] = {0};
     struct { void* p; size_t cap; } ws[WS_COUNT] = {};
     void* pinned = nullptr;
@@ -73,14 +76,14 @@ inline int ctx_pinned(rcz_ctx* c, size_t bytes, void** out) {
     return RCZ_OK;
 }
 inline int ctx_stage_mark(rcz_ctx* c, int i) {      // boundary i of the call's kernel sequence (0 = before the first kernel)
-    if (i > 4) return RCZ_OK;
+    if (i > RCZ_MAX_STAGES || c->nest) return RCZ_OK;
     if (!c->stage_ev[i]) RCZ_CK(c, rt_event_create(&c->stage_ev[i]));
     RCZ_CK(c, rt_event_record(c->stage_ev[i], c->stream));
     c->nstage = i;
     return RCZ_OK;
 }
-inline int ctx_timer_begin(rcz_ctx* c) { c->ev_valid = false; c->nstage = 0; RCZ_CK(c, rt_event_record(c->ev0, c->stream)); return RCZ_OK; }
-inline int ctx_timer_end(rcz_ctx* c) { RCZ_CK(c, rt_event_record(c->ev1, c->stream)); c->ev_valid = true; return RCZ_OK; }
+inline int ctx_timer_begin(rcz_ctx* c) { if (c->nest) return RCZ_OK; c->ev_valid = false; c->nstage = 0; RCZ_CK(c, rt_event_record(c->ev0, c->stream)); return RCZ_OK; }
+inline int ctx_timer_end(rcz_ctx* c) { if (c->nest) return RCZ_OK; RCZ_CK(c, rt_event_record(c->ev1, c->stream)); c->ev_valid = true; return RCZ_OK; }
 
 // ------------------------------------------------------------------------------------------------
 // Descriptor staging.  Every batch op has a few per-unit input arrays (offsets, lengths, ...) — always HOST
@@ -163,4 +166,14 @@ inline int unstage_span_out(rcz_ctx* c, void* host_base, const uint8_t* dev_base
     RCZ_CK(c, rt_stream_sync(c->stream));
     return RCZ_OK;
 }
+// ---- entry points with DEVICE descriptor arrays, for composed calls (pipeline.cu); they only enqueue on c->stream
+constexpr unsigned long long RCZ_STREAM_SKIP = ~0ull;     // in_len value of an unused stream slot: out_len = 0, status = OK
+int rcz_ari_launch(rcz_ctx* c, bool decode, const uint8_t* din, const uint64_t* d_in_off, const uint64_t* d_in_len, uint8_t* dout,
+                   const uint64_t* d_out_off, const uint64_t* d_out_cap, uint64_t* d_out_len, uint64_t* d_in_used, int32_t* d_status, size_t n);
+int rcz_dc_decode_launch(rcz_ctx* c, const uint32_t* din, const uint64_t* d_in_off, const uint64_t* d_in_len, uint8_t* dout,
+                         const uint64_t* d_out_off, const uint64_t* d_n, int32_t* d_status, size_t nblocks);
+// inverse BWT with the origins in DEVICE memory (origin_dev != nullptr; origin_host is then ignored); mem_kind as in rcz.h
+int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, const uint64_t* n_arr, const uint32_t* origin_host,
+                       const uint32_t* origin_dev, void* out_base, const uint64_t* out_off, uint64_t* out_len, int32_t* status,
+                       size_t nblocks, int mem_kind);
 inline bool rcz_bad_kind(int k) { return k != RCZ_MEM_HOST && k != RCZ_MEM_DEVICE && k != RCZ_MEM_DEVICE_ASYNC; }
