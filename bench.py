@@ -1,15 +1,21 @@
 #!/usr/bin/env python
-"""bench.py — throughput of the hot path on B200 (BASELINE.json metric: uncompressed GB/s, % of HBM roofline, CPU path beside it).
+"""bench.py — throughput of the hot path on B200 (BASELINE.json metric: uncompressed GB/s per codec, % of HBM roofline, CPU path beside it).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload lz4|bwt_decode]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--codecs lz4,bwt,flate,pipeline]
 
-Default workload = BASELINE.json configs[1]: lz4::Decoder over 256 independent 4 MiB synthetic blocks on one B200
-("lzsyn" generator of SURVEY.md §8d, compressed with liblz4).  One step = one pass of the batch through the C ABI.
+Headline keys = BASELINE.json configs[1]: lz4::Decoder over 256 independent 4 MiB synthetic blocks on one B200 ("lzsyn" generator of
+SURVEY.md §8d, compressed with liblz4).  One step = one pass of the batch through the C ABI.
   value     device-resident: compressed blocks already in HBM, output stays in HBM (CUDA events, max over ranks)
-  e2e       the same call with HOST (pinned) buffers: H2D of the compressed blocks + kernel + D2H of the output
-  roofline  algorithmic bytes (compressed in + decoded out) / average step duration, against MEASURED_PEAKS.json
-With N > 1 (torchrun, one rank per GPU) every rank decodes its own 256 blocks (weak scaling, no data-path collective).
-`--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on the same workload.
+  e2e       the same call with HOST (pinned) buffers: H2D of the compressed blocks + kernels + D2H of the output
+  roofline  algorithmic bytes (compressed in + decoded out) of the dominant kernel / its duration, against MEASURED_PEAKS.json
+With N > 1 (torchrun, one rank per GPU) every rank decodes its own 256 blocks (weak scaling, no data-path collective);
+`value_with_gather` adds the final gather of the decoded shards over NVLink.
+
+`per_codec` carries the other BASELINE configs, measured in the same run, each with value / roofline / cpu_baseline / e2e:
+  bwt_encode, bwt_decode      configs[2]  1 GiB random bytes in 256 blocks of 4 MiB, sharded over the ranks (strong scaling)
+  flate_decode                configs[3]  131,072 raw-DEFLATE streams of 64 KiB (8 GiB), sharded over the ranks (strong scaling)
+  bwt_dc_ari_encode/_decode   configs[4]  256 text blocks of 4 MiB per GPU through the chained pipeline (weak scaling)
+`--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on the same workloads (bounded samples).
 """
 import argparse
 import importlib
@@ -19,6 +25,8 @@ import subprocess
 import sys
 import threading
 import time
+import traceback
+import zlib
 
 import numpy as np
 
@@ -28,10 +36,14 @@ if ROOT not in sys.path:
 
 UNIT = 4 << 20
 COUNT = 256
+FL_UNIT = 65536
+FL_TOTAL = 131072          # configs[3]: 8 GiB of 64 KiB streams
+FL_UNIQUE = 16384          # generated and compressed once (1 GiB), tiled to FL_TOTAL
+ARI_CHUNK = 65536          # configs[4]: ByteEncoder streams of 64 KiB of serialised dc output
 
 
 def traffic_for(kernel):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json), else None."""
+    """DRAM bytes per launch of a kernel from the committed ncu --set full capture (profiles/traffic.json), else None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         return json.load(open(p)).get(kernel)
@@ -92,6 +104,31 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_numa(local):
+    """Run this rank (and therefore first-touch its pinned buffers) on the CPUs of its GPU's NUMA node.  Best effort."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa node unknown (single node)"
+        cl = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+        cpus = set()
+        for part in cl.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "node %d (%d cpus)" % (node, len(cpus))
+    except Exception as e:  # pragma: no cover
+        return "unavailable: %s" % type(e).__name__
+    return "unchanged"
+
+
 # ------------------------------------------------------------------------------------------------- workloads
 def make_lz4(rank, nthreads):
     from tools import gen
@@ -104,20 +141,6 @@ def make_lz4(rank, nthreads):
             "name": "lz4::Decoder over 256 independent 4 MiB synthetic blocks (lzsyn generator, liblz4 LZ4_compress_default)"}
 
 
-def make_bwt_decode(rank, nthreads, count=COUNT):
-    """BASELINE configs[2] decode leg; the L columns come from the device encoder when available, else the oracle (slow)."""
-    from oracle import oracle
-    from tools import gen
-    raw = gen.units("random", gen.unit_seed(3, rank * count), UNIT, count, nthreads=nthreads)
-    off = np.arange(count, dtype=np.uint64) * UNIT
-    n = np.full(count, UNIT, dtype=np.uint64)
-    l_buf = np.zeros(UNIT * count + 64, dtype=np.uint8)
-    origin, st = oracle.bwt_encode_blocks_mt(raw, off, n, l_buf, nthreads)
-    assert (st == 0).all()
-    return {"raw": raw, "L": l_buf, "off": off, "n": n, "origin": origin, "U": UNIT * count, "C": UNIT * count + 8 * count,
-            "name": "bwt::Decoder over %d x 4 MiB random blocks" % count}
-
-
 def config_for(w):
     """The same `config` object on both arms (ours / --impl reference)."""
     nb = len(w.get("in_off", w.get("off")))
@@ -126,7 +149,99 @@ def config_for(w):
             "parallelism": "independent blocks, %d per GPU, no data-path collective" % nb}
 
 
+def make_flate_unique(nthreads, count=FL_UNIQUE):
+    """`count` hexdump-text streams of 64 KiB, each compressed on its own with zlib level 6 as raw DEFLATE."""
+    from concurrent.futures import ThreadPoolExecutor
+    from tools import gen
+    raw = gen.units("hextext", gen.unit_seed(4, 0), FL_UNIT, count, nthreads=nthreads)
+
+    def comp(i):
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        return c.compress(raw[i * FL_UNIT: (i + 1) * FL_UNIT].tobytes()) + c.flush()
+    with ThreadPoolExecutor(max(1, nthreads)) as ex:
+        cs = list(ex.map(comp, range(count), chunksize=64))
+    lens = np.array([len(c) for c in cs], dtype=np.uint64)
+    al = (lens + np.uint64(15)) & ~np.uint64(15)
+    off = np.zeros(count, dtype=np.uint64)
+    off[1:] = np.cumsum(al)[:-1]
+    span = int(al.sum())
+    packed = np.zeros(span, dtype=np.uint8)
+    for i, c in enumerate(cs):
+        packed[int(off[i]): int(off[i]) + len(c)] = np.frombuffer(c, dtype=np.uint8)
+    return raw, packed, off, lens, span
+
+
 # ------------------------------------------------------------------------------------------------- reference arm
+def _timed_cpu(fn, budget_s=8.0, max_reps=6):
+    t0 = time.perf_counter()
+    reps = 0
+    while reps < 1 or (time.perf_counter() - t0 < budget_s and reps < max_reps):
+        fn()
+        reps += 1
+    return (time.perf_counter() - t0) / reps, reps
+
+
+def cpu_legs(cores, which, single):
+    """CPU restatement (oracle/) of every per-codec workload on a bounded sample; `cores` threads (1 = the reference as written)."""
+    from oracle import oracle
+    from tools import gen
+    out = {}
+    kind = {"kind": "port", "cores": cores, "unit": "GB/s"}
+    nb = max(1, cores) * (1 if single else 2)
+    if "bwt" in which:
+        nb_b = min(COUNT, max(2, nb))
+        raw = gen.units("random", gen.unit_seed(3, 0), UNIT, nb_b)
+        off = np.arange(nb_b, dtype=np.uint64) * UNIT
+        n = np.full(nb_b, UNIT, dtype=np.uint64)
+        l_buf = np.zeros(UNIT * nb_b + 64, dtype=np.uint8)
+        res = {}
+
+        def enc():
+            res["o"] = oracle.bwt_encode_blocks_mt(raw, off, n, l_buf, cores)
+        dt, reps = _timed_cpu(enc, 6.0, 3)
+        origin, st = res["o"]
+        assert (st == 0).all()
+        out["bwt_encode"] = dict(kind, value=nb_b * UNIT / dt / 1e9, sample="%d of the 256 random 4 MiB blocks, %d repetitions; oracle compute_suffixes + TransformIterator" % (nb_b, reps))
+        back = np.zeros(UNIT * nb_b + 64, dtype=np.uint8)
+        dt, reps = _timed_cpu(lambda: oracle.bwt_decode_blocks_mt(l_buf, off, n, origin, back, cores), 4.0, 4)
+        assert bytes(back[: UNIT * nb_b]) == raw.tobytes()
+        out["bwt_decode"] = dict(kind, value=nb_b * UNIT / dt / 1e9, sample="%d of the 256 blocks, %d repetitions; oracle compute_inversion_table + InverseIterator" % (nb_b, reps))
+    if "flate" in which:
+        ns = 256 * max(1, cores)
+        raw, packed, off, lens, span = make_flate_unique(max(cores, 4), ns)
+        outb = np.zeros(FL_UNIT * ns + 64, dtype=np.uint8)
+        ooff = np.arange(ns, dtype=np.uint64) * FL_UNIT
+        caps = np.full(ns, FL_UNIT, dtype=np.uint64)
+        res = {}
+
+        def dec():
+            res["o"] = oracle.flate_decode_streams_mt(packed, off, lens, outb, ooff, caps, cores)
+        dt, reps = _timed_cpu(dec, 4.0, 6)
+        assert (res["o"][1] == 0).all() and bytes(outb[: FL_UNIT * ns]) == raw.tobytes()
+        out["flate_decode"] = dict(kind, value=ns * FL_UNIT / dt / 1e9, sample="%d of the 131,072 streams, %d repetitions; oracle flate::Decoder" % (ns, reps))
+    if "pipeline" in which:
+        nb_p = min(COUNT, max(1, cores) if single else max(2, cores))
+        raw = gen.units("hextext", gen.unit_seed(5, 0), UNIT, nb_p)
+        off = np.arange(nb_p, dtype=np.uint64) * UNIT
+        n = np.full(nb_p, UNIT, dtype=np.uint64)
+        cap = 24 + 4 * 260 + 2 * 4 * (256 + UNIT) + 64 * 260
+        cont = np.zeros(cap * nb_p + 64, dtype=np.uint8)
+        coff = np.arange(nb_p, dtype=np.uint64) * cap
+        res = {}
+
+        def enc():
+            res["o"] = oracle.bda_encode_blocks_mt(raw, off, n, ARI_CHUNK, cont, coff, np.full(nb_p, cap, np.uint64), cores)
+        dt, reps = _timed_cpu(enc, 4.0, 2)
+        clen, org, st = res["o"]
+        assert (st == 0).all()
+        out["bwt_dc_ari_encode"] = dict(kind, value=nb_p * UNIT / dt / 1e9, sample="%d text blocks of 4 MiB, %d repetitions; oracle bwt + dc + ByteEncoder (64 KiB streams)" % (nb_p, reps))
+        back = np.zeros(UNIT * nb_p + 64, dtype=np.uint8)
+        dt, reps = _timed_cpu(lambda: oracle.bda_decode_blocks_mt(cont, coff, clen, ARI_CHUNK, back, off, n, cores), 4.0, 3)
+        assert bytes(back[: UNIT * nb_p]) == raw.tobytes()
+        out["bwt_dc_ari_decode"] = dict(kind, value=nb_p * UNIT / dt / 1e9, sample="%d text blocks of 4 MiB, %d repetitions; oracle ByteDecoder + dc + inverse bwt" % (nb_p, reps))
+    return out
+
+
 def run_reference(args):
     """The reference's own CPU implementation of the path = oracle/ (C++ restatement; no rustc in this image), all host threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -150,83 +265,141 @@ def run_reference(args):
             "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
                              "sample": "all 256 blocks per step, C++ restatement of lz4.rs BlockDecoder::decode, one block per thread"},
             "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    which = [c for c in args.codecs.split(",") if c != "lz4"]
+    try:
+        line["per_codec"] = cpu_legs(cores, which, single=False)
+    except Exception as e:  # pragma: no cover
+        line["per_codec"] = {"error": repr(e)}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------- our arm
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Env:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.numa = bind_numa(self.local) if self.world > 1 else "single rank: not bound"
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.rcz = importlib.import_module("rust-compress_b200")
+        self.shard = importlib.import_module("rust-compress_b200.shard")
+        self.ctx = self.rcz.Context(device=self.local)
+        self.ctx.set_stream(torch.cuda.current_stream())
+        self.nthreads = max(1, len(os.sched_getaffinity(0)) // (1 if self.numa.startswith("node") else self.world))
+        self.peak, self.peak_src = peaks()
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    rcz = importlib.import_module("rust-compress_b200")
-    ctx = rcz.Context(device=local)
-    ctx.set_stream(torch.cuda.current_stream())
-    nthreads = max(1, (os.cpu_count() or 1) // world)
-    peak, peak_src = peaks()
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
+    def max_over_ranks(self, x):
+        if self.world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    if args.workload == "lz4":
-        w = make_lz4(rank, nthreads)
-        d_in = torch.from_numpy(w["packed"]).cuda()
-        d_out = torch.zeros(w["U"], dtype=torch.uint8, device="cuda")
-        d_len = None
+    def sum_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
 
-        def step_dev():
-            return ctx.lz4_decode_blocks(d_in, w["in_off"], w["in_len"], d_out, w["out_off"], w["out_cap"], async_=True)
+    def time_dev(self, step, steps, warmup):
+        """W warm-ups, then exactly `steps` steps between barrier + synchronize on both sides; CUDA events; max over ranks (ms per step)."""
+        torch = self.torch
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        self.barrier()
+        return self.max_over_ranks(ms)
 
-        h_in = torch.from_numpy(w["packed"]).pin_memory()
-        h_out = torch.zeros(w["U"] + 64, dtype=torch.uint8).pin_memory()
-        h_in_np, h_out_np = h_in.numpy(), h_out.numpy()
+    def time_host(self, step, steps, warmup=1):
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        self.torch.cuda.synchronize()
+        return self.max_over_ranks((time.perf_counter() - t0) / steps)
 
-        def step_host():
-            return ctx.lz4_decode_blocks(h_in_np, w["in_off"], w["in_len"], h_out_np, w["out_off"], w["out_cap"])
+    def reps_for(self, est_ms, steps, budget_ms=2500.0):
+        return int(max(2, min(steps, budget_ms / max(est_ms, 1e-3))))
 
-        h2d, d2h = int(w["in_off"][-1] + w["in_len"][-1] - w["in_off"][0]), w["U"]
-        metric = "lz4_decode_uncompressed_GBps"
-        kernel_name = "lz4_mat_kernel"
-    elif args.workload == "bwt_decode":
-        w = make_bwt_decode(rank, nthreads, count=args.blocks or 64)
-        d_in = torch.from_numpy(w["L"]).cuda()
-        d_out = torch.zeros(w["U"], dtype=torch.uint8, device="cuda")
+    def pinned(self, arr):
+        t = self.torch.from_numpy(arr).pin_memory()
+        return t, t.numpy()
 
-        def step_dev():
-            return ctx.bwt_decode_blocks(d_in, w["off"], w["n"], w["origin"], d_out, w["off"], async_=True)
+    def gather_time(self, decode_step, shard_tensor, steps):
+        """decode + final gather of the uniform shards (ncclAllGather over NVLink) in one timed region."""
+        torch, dist = self.torch, self.dist
+        flat = torch.empty(shard_tensor.numel() * self.world, dtype=torch.uint8, device="cuda")
 
-        h_in = torch.from_numpy(w["L"]).pin_memory()
-        h_out = torch.zeros(w["U"] + 64, dtype=torch.uint8).pin_memory()
-        h_in_np, h_out_np = h_in.numpy(), h_out.numpy()
+        def step():
+            decode_step()
+            dist.all_gather_into_tensor(flat, shard_tensor)
+        ms = self.time_dev(step, steps, 2)
+        del flat
+        return ms
 
-        def step_host():
-            return ctx.bwt_decode_blocks(h_in_np, w["off"], w["n"], w["origin"], h_out_np, w["off"])
 
-        h2d, d2h = w["U"], w["U"]
-        metric = "bwt_decode_uncompressed_GBps"
-        kernel_name = "ibwt_walk_kernel"
-    else:
-        raise SystemExit("unknown workload " + args.workload)
+def roofline(env, kernel, alg_bytes, kernel_ms, op_ms, extra=None):
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    r = {"bound": "hbm", "achieved": achieved, "peak": env.peak, "unit": "GB/s", "frac": achieved / env.peak, "traffic": traffic_for(kernel),
+         "kernel": kernel, "peak_source": env.peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms, "op_ms": op_ms,
+         "op_frac": alg_bytes / (op_ms * 1e-3) / 1e9 / env.peak}
+    r.update(extra or {})
+    return r
+
+
+def launches_of(ctx, step):
+    """librcz kernel launches of one call"""
+    l0 = ctx.launches
+    step()
+    return ctx.launches - l0
+
+
+def stage_avg(ctx, step, reps=3):
+    kms, stages = [], []
+    for _ in range(reps):
+        step()
+        kms.append(ctx.last_kernel_ms())
+        stages.append(ctx.last_stage_ms())
+    n = min(len(s) for s in stages) if stages else 0
+    return float(np.mean(kms)), [float(np.mean([s[i] for s in stages])) for i in range(n)]
+
+
+def leg_lz4(env, args):
+    torch, dist, ctx, world, rank = env.torch, env.dist, env.ctx, env.world, env.rank
+    w = make_lz4(rank, env.nthreads)
+    d_in = torch.from_numpy(w["packed"]).cuda()
+    d_out = torch.zeros(w["U"], dtype=torch.uint8, device="cuda")
+    res = {}
+
+    def step_dev():
+        res["o"] = ctx.lz4_decode_blocks(d_in, w["in_off"], w["in_len"], d_out, w["out_off"], w["out_cap"], async_=True)
 
     # ---- device-resident timing (value, roofline)
-    for _ in range(max(args.warmup, 3)):
-        res = step_dev()
-    barrier()
-    sampler = ClockSampler(local)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step_dev()
+    env.barrier()
+    sampler = ClockSampler(env.local)
     if rank == 0:
         sampler.start()
     launches0 = ctx.launches
@@ -235,7 +408,7 @@ def run_ours(args):
     e0.record()
     for a, b in evs:
         a.record()
-        res = step_dev()
+        step_dev()
         b.record()
     e1.record()
     torch.cuda.synchronize()
@@ -243,61 +416,55 @@ def run_ours(args):
     step_ms = [a.elapsed_time(b) for a, b in evs]
     launches = ctx.launches - launches0
     clocks = sampler.stop() if rank == 0 else None
-    barrier()
-    ms_per_step = max_over_ranks(total_ms / args.steps)
-    # duration of the kernel(s) alone: CUDA events recorded by librcz on the context's stream around its launches
-    kms, stages = [], []
-    for _ in range(3):
-        step_dev()
-        kms.append(ctx.last_kernel_ms())
-        stages.append(ctx.last_stage_ms())
-    kern_ms = float(np.mean(kms))
-    # ops that launch several kernels per call (lz4: parse, scan, materialise) report every kernel; the roofline is that of the
-    # dominant one, and `op_frac` is the same ratio for the whole call
-    stage_ms = [float(np.mean([st[i] for st in stages])) for i in range(len(stages[0]))] if stages and stages[0] else []
-    step_ms_mean = float(np.mean(step_ms))
-    # final gather of the decoded shards (N > 1): NCCL all-gather over NVLink, timed separately from the decode
+    env.barrier()
+    ms_per_step = env.max_over_ranks(total_ms / args.steps)
+    # duration of the kernels alone: CUDA events recorded by librcz on the context's stream around its launches (parse, scan, materialise)
+    kern_ms, stage_ms = stage_avg(ctx, step_dev)
+    out_len, status = res["o"]
+    assert int((status != 0).sum().item()) == 0, "decode reported errors"
+    assert torch.equal(d_out, torch.from_numpy(w["raw"]).cuda()), "device output differs from the generator's bytes"
+
+    # ---- decode + final gather (N > 1)
     gather = None
     if world > 1:
         flat = torch.empty(w["U"] * world, dtype=torch.uint8, device="cuda")
-        for _ in range(2):
-            dist.all_gather_into_tensor(flat, d_out)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(3):
-            dist.all_gather_into_tensor(flat, d_out)
-        g1.record()
-        torch.cuda.synchronize()
-        gms = max_over_ranks(g0.elapsed_time(g1) / 3)
-        gather = {"collective": "ncclAllGather (uniform shards)", "bytes_per_rank": w["U"], "ms": gms,
-                  "busbw_GBps": w["U"] * (world - 1) / (gms * 1e-3) / 1e9}
+        gms = env.time_dev(lambda: dist.all_gather_into_tensor(flat, d_out), 3, 2)
         del flat
-    out_len, status = res[0], res[1]
-    assert int((status != 0).sum().item() if hasattr(status, "sum") else 0) == 0, "decode reported errors"
-    ok = torch.equal(d_out, torch.from_numpy(w["raw"]).cuda())
-    assert ok, "device output differs from the generator's bytes"
+        both = env.gather_time(step_dev, d_out, max(3, min(args.steps, 10)))
+        gather = {"collective": "ncclAllGather of the uniform 1 GiB shards (torch.distributed, NCCL over NVLink), issued after the decode", "bytes_per_rank": w["U"],
+                  "gather_alone_ms": gms, "busbw_GBps": w["U"] * (world - 1) / (gms * 1e-3) / 1e9, "decode_plus_gather_ms": both,
+                  "value_with_gather": world * w["U"] / (both * 1e-3) / 1e9}
 
-    # ---- end-to-end timing through the host-buffer ABI (e2e)
-    for _ in range(2):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ol, st = step_host()[:2]
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
-    assert (st == 0).all() and bytes(h_out_np[: w["U"]]) == w["raw"].tobytes()
+    # ---- end-to-end timing through the host-buffer ABI (e2e), and the platform's copy ceiling for the same bytes
+    h_in, h_in_np = env.pinned(w["packed"])
+    h_out = torch.zeros(w["U"] + 64, dtype=torch.uint8).pin_memory()
+    h_out_np = h_out.numpy()
+    r2 = {}
+
+    def step_host():
+        r2["o"] = ctx.lz4_decode_blocks(h_in_np, w["in_off"], w["in_len"], h_out_np, w["out_off"], w["out_cap"])
+    e2e_s = env.time_host(step_host, args.steps, 2)
+    assert (r2["o"][1] == 0).all() and bytes(h_out_np[: w["U"]]) == w["raw"].tobytes()
+    h2d, d2h = int(w["in_off"][-1] + w["in_len"][-1] - w["in_off"][0]), w["U"]
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def step_copy():
+        with torch.cuda.stream(s1):
+            d_in[:h2d].copy_(h_in[:h2d], non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out[: w["U"]].copy_(d_out, non_blocking=True)
+        s1.synchronize(); s2.synchronize()
+    ceil_s = env.time_host(step_copy, 5, 2)
 
     # ---- CPU baseline on rank 0 (N == 1 only)
     cpu = None
-    if rank == 0 and world == 1 and args.workload == "lz4":
+    if rank == 0 and world == 1:
         from oracle import oracle
         nb = 64
         out = np.zeros(w["U"] + 64, dtype=np.uint8)
         t0 = time.perf_counter()
         reps = 0
-        while time.perf_counter() - t0 < 12.0 and reps < 12:
+        while time.perf_counter() - t0 < 10.0 and reps < 12:
             oracle.lz4_decode_blocks_mt(w["packed"], w["in_off"][:nb], w["in_len"][:nb], out, w["out_off"][:nb], w["out_cap"][:nb], 1)
             reps += 1
         dt = (time.perf_counter() - t0) / reps
@@ -305,26 +472,267 @@ def run_ours(args):
                "sample": "first %d of the 256 blocks, %d repetitions, single thread (the reference is single-threaded); "
                          "C++ restatement of lz4.rs BlockDecoder::decode (no rustc in this image)" % (nb, reps)}
 
-    if rank == 0:
-        value = world * w["U"] / (ms_per_step * 1e-3) / 1e9
-        alg_bytes = w["C"] + w["U"]
-        dom_ms = max(stage_ms) if stage_ms else kern_ms
-        achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-        line = {"metric": metric, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": config_for(w),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic_for(kernel_name), "kernel": kernel_name, "peak_source": peak_src,
-                             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms, "op_ms": kern_ms,
-                             "op_frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / peak, "stage_ms": stage_ms, "step_ms_events": step_ms_mean},
-                "cpu_baseline": cpu,
-                "e2e": {"value": world * w["U"] / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},
-                "gpu_launches": launches, "clocks": clocks, "host_cores": os.cpu_count()}
-        if gather:
-            line["gather"] = gather
-        print(json.dumps(line))
+    alg_bytes = w["C"] + w["U"]
+    dom_ms = max(stage_ms) if stage_ms else kern_ms
+    line = {"metric": "lz4_decode_uncompressed_GBps", "value": world * w["U"] / (ms_per_step * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": config_for(w),
+            "roofline": roofline(env, "lz4_mat_kernel", alg_bytes, dom_ms, kern_ms, {"stage_ms": stage_ms, "stages": ["lz4_parse_kernel", "lz4_scan_kernel", "lz4_mat_kernel"],
+                                                                                    "step_ms_events": float(np.mean(step_ms))}),
+            "cpu_baseline": cpu,
+            "e2e": {"value": world * w["U"] / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
+                    "ceiling": {"what": "plain pinned cudaMemcpyAsync of the same bytes, H2D and D2H on two streams at once, no kernels; max over ranks",
+                                "ms": ceil_s * 1e3, "GBps": world * w["U"] / ceil_s / 1e9}},
+            "gpu_launches": launches, "clocks": clocks, "host_cores": os.cpu_count()}
+    if gather:
+        line["gather"] = gather
+        line["value_with_gather"] = gather["value_with_gather"]
+    return line
+
+
+def _shard_range(env, total):
+    lo, hi = env.shard.my_range(np.ones(total), env.world, env.rank)
+    return lo, hi
+
+
+def leg_bwt(env, args):
+    """configs[2]: 1 GiB random bytes, 256 blocks of 4 MiB, sharded contiguously over the ranks; encode and decode timed separately."""
+    from tools import gen
+    torch, ctx, world = env.torch, env.ctx, env.world
+    lo, hi = _shard_range(env, COUNT)
+    nb = hi - lo
+    raw = gen.units("random", gen.unit_seed(3, lo), UNIT, nb, nthreads=env.nthreads)
+    off = np.arange(nb, dtype=np.uint64) * UNIT
+    n = np.full(nb, UNIT, dtype=np.uint64)
+    d_raw = torch.from_numpy(raw).cuda()
+    d_l = torch.zeros(UNIT * nb + 64, dtype=torch.uint8, device="cuda")
+    d_back = torch.zeros(UNIT * nb, dtype=torch.uint8, device="cuda")
+    origin, st = ctx.bwt_encode_blocks(d_raw, off, n, d_l, off)
+    assert (st == 0).all()
+    enc = lambda: ctx.bwt_encode_blocks(d_raw, off, n, d_l, off, async_=True)          # noqa: E731
+    dec = lambda: ctx.bwt_decode_blocks(d_l, off, n, origin, d_back, off, async_=True)  # noqa: E731
+    enc(); torch.cuda.synchronize()
+    t0 = time.perf_counter(); enc(); torch.cuda.synchronize(); est_e = (time.perf_counter() - t0) * 1e3
+    reps_e = env.reps_for(est_e, args.steps)
+    ms_e = env.time_dev(enc, reps_e, 1)
+    per_call_e = launches_of(ctx, enc)
+    dec(); torch.cuda.synchronize()
+    t0 = time.perf_counter(); dec(); torch.cuda.synchronize(); est_d = (time.perf_counter() - t0) * 1e3
+    reps_d = env.reps_for(est_d, args.steps)
+    ms_d = env.time_dev(dec, reps_d, 3)
+    per_call_d = launches_of(ctx, dec)
+    assert torch.equal(d_back, d_raw), "decode(encode(x)) != x"
+    kd_ms, kd_stage = stage_avg(ctx, dec)
+    total_U = COUNT * UNIT
+    alg = (2 * UNIT + 8) * nb
+    # e2e: host buffers through the ABI
+    h_raw, h_raw_np = env.pinned(raw)
+    h_l = torch.zeros(UNIT * nb + 64, dtype=torch.uint8).pin_memory()
+    h_back = torch.zeros(UNIT * nb + 64, dtype=torch.uint8).pin_memory()
+    r = {}
+
+    def enc_host():
+        r["e"] = ctx.bwt_encode_blocks(h_raw_np, off, n, h_l.numpy(), off)
+    e2e_e = env.time_host(enc_host, 2, 1)
+    assert (r["e"][1] == 0).all() and (r["e"][0] == origin).all() and torch.equal(h_l[: UNIT * nb], d_l[: UNIT * nb].cpu())
+
+    def dec_host():
+        r["d"] = ctx.bwt_decode_blocks(h_l.numpy(), off, n, origin, h_back.numpy(), off)
+    e2e_d = env.time_host(dec_host, 3, 1)
+    assert (r["d"][1] == 0).all() and bytes(h_back.numpy()[: UNIT * nb]) == raw.tobytes()
+    gather = None
     if world > 1:
-        dist.destroy_process_group()
+        both = env.gather_time(dec, d_back, max(2, reps_d))
+        gather = {"collective": "ncclAllGather of the decoded shards after the decode", "decode_plus_gather_ms": both, "value_with_gather": total_U / (both * 1e-3) / 1e9}
+    cfg = {"workload": "bwt::Encoder / Decoder, 1 GiB random bytes (splitmix64) in 256 blocks of 4 MiB", "blocks_total": COUNT, "blocks_per_gpu": nb,
+           "block_bytes": UNIT, "l2": "inputs larger than L2 (%.2f GiB per GPU per step)" % (2 * UNIT * nb / 2**30), "parallelism": "contiguous block ranges per rank (shard.partition), no data-path collective"}
+    out = {}
+    out["bwt_encode"] = {"config": cfg, "value": total_U / (ms_e * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_e, "steps": reps_e, "scaling": "strong", "dtype": "u8",
+                         "roofline": roofline(env, "bwte::scatter_kernel", alg, ms_e, ms_e, {"note": "op-level figure: the round-0 sort is 8 radix passes (hist, scan, scatter launches each); kernel_ms = the whole call"}),
+                         "e2e": {"value": total_U / e2e_e / 1e9, "unit": "GB/s", "h2d_bytes_per_step": UNIT * nb, "d2h_bytes_per_step": (UNIT + 4) * nb, "ms_per_step": e2e_e * 1e3},
+                         "gpu_launches_per_step": per_call_e}
+    walk_ms = max(kd_stage) if kd_stage else kd_ms
+    out["bwt_decode"] = {"config": cfg, "value": total_U / (ms_d * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_d, "steps": reps_d, "scaling": "strong", "dtype": "u8",
+                         "roofline": roofline(env, "ibwt_walk_kernel", alg, walk_ms, kd_ms, {"stage_ms": kd_stage, "stages": ["hist+scan+scatter", "walk", "rank+compact"]}),
+                         "e2e": {"value": total_U / e2e_d / 1e9, "unit": "GB/s", "h2d_bytes_per_step": (UNIT + 4) * nb, "d2h_bytes_per_step": UNIT * nb, "ms_per_step": e2e_d * 1e3},
+                         "gpu_launches_per_step": per_call_d}
+    if gather:
+        out["bwt_decode"]["gather"] = gather
+        out["bwt_decode"]["value_with_gather"] = gather["value_with_gather"]
+    return out
+
+
+def leg_flate(env, args):
+    """configs[3]: 131,072 raw-DEFLATE streams of 64 KiB (8 GiB), sharded over the ranks.  1 GiB (16,384 streams) is generated and
+    compressed, and tiled to the rank's share."""
+    torch, ctx, world = env.torch, env.ctx, env.world
+    raw, packed, off, lens, span = make_flate_unique(env.nthreads)
+    per_rank = FL_TOTAL // world
+    tiles = max(1, per_rank // FL_UNIQUE)
+    ns = FL_UNIQUE * tiles if per_rank >= FL_UNIQUE else per_rank
+    uniq = min(FL_UNIQUE, ns)
+    if ns < FL_UNIQUE:                                                   # more than 8 ranks: a prefix of the unique set
+        span = int(off[uniq - 1] + ((lens[uniq - 1] + np.uint64(15)) & ~np.uint64(15)))
+    in_off = np.concatenate([off[:uniq] + np.uint64(t * span) for t in range(tiles)])
+    in_len = np.tile(lens[:uniq], tiles)
+    out_off = np.arange(ns, dtype=np.uint64) * FL_UNIT
+    caps = np.full(ns, FL_UNIT, dtype=np.uint64)
+    d_in = torch.from_numpy(packed[:span]).cuda().repeat(tiles)
+    d_in = torch.cat([d_in, torch.zeros(64, dtype=torch.uint8, device="cuda")])
+    d_out = torch.zeros(FL_UNIT * ns, dtype=torch.uint8, device="cuda")
+    C = int(in_len.sum())
+    res = {}
+
+    def dec():
+        res["o"] = ctx.flate_decode_streams(d_in, in_off, in_len, d_out, out_off, caps, async_=True)
+    dec(); torch.cuda.synchronize()
+    t0 = time.perf_counter(); dec(); torch.cuda.synchronize(); est = (time.perf_counter() - t0) * 1e3
+    reps = env.reps_for(est, args.steps)
+    ms = env.time_dev(dec, reps, 3)
+    per_call = launches_of(ctx, dec)
+    assert int((res["o"][1] != 0).sum().item()) == 0
+    d_raw = torch.from_numpy(raw[: FL_UNIT * uniq]).cuda()
+    for t in range(tiles):
+        assert torch.equal(d_out[t * FL_UNIT * uniq: (t + 1) * FL_UNIT * uniq], d_raw), "inflate output differs from the generator's bytes"
+    del d_raw
+    k_ms, _ = stage_avg(ctx, dec, 2)
+    total_U = FL_TOTAL * FL_UNIT
+    # e2e with pinned host buffers of the rank's whole share
+    h_in = torch.from_numpy(packed[:span]).repeat(tiles)
+    h_in = torch.cat([h_in, torch.zeros(64, dtype=torch.uint8)]).pin_memory()
+    h_out = torch.zeros(FL_UNIT * ns + 64, dtype=torch.uint8).pin_memory()
+    r = {}
+
+    def dec_host():
+        r["o"] = ctx.flate_decode_streams(h_in.numpy(), in_off, in_len, h_out.numpy(), out_off, caps)
+    e2e = env.time_host(dec_host, 2, 1)
+    assert (r["o"][1] == 0).all() and bytes(h_out.numpy()[: FL_UNIT * uniq]) == raw[: FL_UNIT * uniq].tobytes()
+    del h_in, h_out
+    gather = None
+    if world > 1:
+        both = env.gather_time(dec, d_out, max(2, reps))
+        gather = {"collective": "ncclAllGather of the decoded shards after the decode", "decode_plus_gather_ms": both, "value_with_gather": total_U / (both * 1e-3) / 1e9}
+    cfg = {"workload": "flate::Decoder, 131,072 raw-DEFLATE streams of 64 KiB hexdump text (zlib level 6, wbits -15); 16,384 streams (1 GiB) generated, tiled %dx per GPU" % tiles,
+           "streams_total": FL_TOTAL, "streams_per_gpu": ns, "stream_bytes": FL_UNIT, "compressed_bytes_per_gpu": C,
+           "l2": "inputs larger than L2 (%.2f GiB per GPU per step)" % ((C + FL_UNIT * ns) / 2**30), "parallelism": "contiguous stream ranges per rank, no data-path collective"}
+    leg = {"config": cfg, "value": total_U / (ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms, "steps": reps, "scaling": "strong", "dtype": "u8",
+           "roofline": roofline(env, "inflate_kernel", C + FL_UNIT * ns, k_ms, k_ms),
+           "e2e": {"value": total_U / e2e / 1e9, "unit": "GB/s", "h2d_bytes_per_step": tiles * span, "d2h_bytes_per_step": FL_UNIT * ns, "ms_per_step": e2e * 1e3},
+           "gpu_launches_per_step": per_call}
+    if gather:
+        leg["gather"] = gather
+        leg["value_with_gather"] = gather["value_with_gather"]
+    return {"flate_decode": leg}
+
+
+def leg_pipeline(env, args):
+    """configs[4]: bwt -> dc -> entropy::ari, 256 text blocks of 4 MiB per GPU, chained on the device."""
+    from tools import gen
+    torch, ctx, world, rank = env.torch, env.ctx, env.world, env.rank
+    nb = int(os.environ.get("RCZ_BENCH_C5_BLOCKS", COUNT))
+    raw = gen.units("hextext", gen.unit_seed(5, rank * nb), UNIT, nb, nthreads=env.nthreads)
+    off = np.arange(nb, dtype=np.uint64) * UNIT
+    n = np.full(nb, UNIT, dtype=np.uint64)
+    cap = 6 * UNIT                                                       # containers of this text come out at ~0.6 x the block
+    coff = np.arange(nb, dtype=np.uint64) * cap
+    caps = np.full(nb, cap, dtype=np.uint64)
+    d_raw = torch.from_numpy(raw).cuda()
+    d_cont = torch.zeros(cap * nb + 64, dtype=torch.uint8, device="cuda")
+    d_back = torch.zeros(UNIT * nb, dtype=torch.uint8, device="cuda")
+    clen, org, st = ctx.bwt_dc_ari_encode_blocks(d_raw, off, n, d_cont, coff, caps, ari_chunk=ARI_CHUNK)
+    assert (st == 0).all()
+    enc = lambda: ctx.bwt_dc_ari_encode_blocks(d_raw, off, n, d_cont, coff, caps, ari_chunk=ARI_CHUNK, async_=True)   # noqa: E731
+    dec = lambda: ctx.bwt_dc_ari_decode_blocks(d_cont, coff, clen, d_back, off, n, ari_chunk=ARI_CHUNK, async_=True)  # noqa: E731
+    t0 = time.perf_counter(); enc(); torch.cuda.synchronize(); est_e = (time.perf_counter() - t0) * 1e3
+    reps_e = env.reps_for(est_e, args.steps, 4000.0)
+    ms_e = env.time_dev(enc, reps_e, 1)
+    per_call_e = launches_of(ctx, enc)
+    ke_ms, ke_stage = stage_avg(ctx, enc, 1)
+    dec(); torch.cuda.synchronize()
+    t0 = time.perf_counter(); dec(); torch.cuda.synchronize(); est_d = (time.perf_counter() - t0) * 1e3
+    reps_d = env.reps_for(est_d, args.steps, 4000.0)
+    ms_d = env.time_dev(dec, reps_d, 1)
+    per_call_d = launches_of(ctx, dec)
+    assert torch.equal(d_back, d_raw), "decode(encode(x)) != x"
+    kd_ms, kd_stage = stage_avg(ctx, dec, 1)
+    Cfin = int(clen.sum())
+    # e2e on host buffers
+    h_raw, h_raw_np = env.pinned(raw)
+    h_cont = torch.zeros(cap * nb + 64, dtype=torch.uint8).pin_memory()
+    h_back = torch.zeros(UNIT * nb + 64, dtype=torch.uint8).pin_memory()
+    r = {}
+
+    def enc_host():
+        r["e"] = ctx.bwt_dc_ari_encode_blocks(h_raw_np, off, n, h_cont.numpy(), coff, caps, ari_chunk=ARI_CHUNK)
+    e2e_e = env.time_host(enc_host, 1, 0)
+    assert (r["e"][2] == 0).all() and (r["e"][0] == clen).all()
+
+    def dec_host():
+        r["d"] = ctx.bwt_dc_ari_decode_blocks(h_cont.numpy(), coff, clen, h_back.numpy(), off, n, ari_chunk=ARI_CHUNK)
+    e2e_d = env.time_host(dec_host, 1, 0)
+    assert (r["d"][1] == 0).all() and bytes(h_back.numpy()[: UNIT * nb]) == raw.tobytes()
+    total_U = world * nb * UNIT
+    cfg = {"workload": "bwt -> dc -> entropy::ari (bzip-style) on %d hexdump-text blocks of 4 MiB per GPU; dc output serialised as u32 LE, ByteEncoder streams of %d bytes" % (nb, ARI_CHUNK),
+           "blocks_per_gpu": nb, "block_bytes": UNIT, "container_bytes_per_gpu": Cfin, "ari_chunk": ARI_CHUNK,
+           "l2": "inputs larger than L2", "parallelism": "independent blocks, %d per GPU, no data-path collective" % nb,
+           "parity": "ari / dc encode bytes are parity-unpinned (the reference tests them by round trip only); every stage equals the oracle's restatement"}
+    e_dom = max(ke_stage) if ke_stage else ke_ms
+    d_dom = max(kd_stage) if kd_stage else kd_ms
+    names_e, names_d = ["bwt", "dc", "ari", "pack"], ["ari", "dc", "bwt"]
+    return {
+        "bwt_dc_ari_encode": {"config": cfg, "value": total_U / (ms_e * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_e, "steps": reps_e, "scaling": "weak", "dtype": "u8",
+                              "roofline": roofline(env, "stage:" + (names_e[int(np.argmax(ke_stage))] if ke_stage else "?"), UNIT * nb + Cfin, e_dom, ke_ms, {"stage_ms": ke_stage, "stages": names_e}),
+                              "e2e": {"value": total_U / e2e_e / 1e9, "unit": "GB/s", "h2d_bytes_per_step": UNIT * nb, "d2h_bytes_per_step": Cfin, "ms_per_step": e2e_e * 1e3},
+                              "gpu_launches_per_step": per_call_e},
+        "bwt_dc_ari_decode": {"config": cfg, "value": total_U / (ms_d * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_d, "steps": reps_d, "scaling": "weak", "dtype": "u8",
+                              "roofline": roofline(env, "stage:" + (names_d[int(np.argmax(kd_stage))] if kd_stage else "?"), UNIT * nb + Cfin, d_dom, kd_ms, {"stage_ms": kd_stage, "stages": names_d}),
+                              "e2e": {"value": total_U / e2e_d / 1e9, "unit": "GB/s", "h2d_bytes_per_step": Cfin, "d2h_bytes_per_step": UNIT * nb, "ms_per_step": e2e_d * 1e3},
+                              "gpu_launches_per_step": per_call_d},
+    }
+
+
+def run_ours(args):
+    env = Env()
+    torch = env.torch
+    codecs = args.codecs.split(",")
+    line = leg_lz4(env, args)
+    line["config"]["numa"] = env.numa
+    per = {}
+    legs = [("bwt", leg_bwt), ("flate", leg_flate), ("pipeline", leg_pipeline)]
+    for name, fn in legs:
+        if name not in codecs:
+            continue
+        torch.cuda.empty_cache()
+        t0 = time.perf_counter()
+        try:
+            got = fn(env, args)
+            for k in got:
+                got[k]["leg_wall_s"] = round(time.perf_counter() - t0, 1)
+            per.update(got)
+            ok = 1.0
+        except Exception as e:  # a failing secondary leg must not take the headline down; it is reported instead
+            traceback.print_exc(file=sys.stderr)
+            per[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+            ok = 0.0
+        if env.world > 1:                                                # keep the ranks in step whatever happened
+            try:
+                env.sum_over_ranks(ok)
+            except Exception:
+                pass
+    if env.rank == 0 and env.world == 1 and per:
+        try:
+            cpu = cpu_legs(1, [c for c in codecs if c != "lz4"], single=True)
+            for k, v in cpu.items():
+                if k in per and "error" not in per[k]:
+                    per[k]["cpu_baseline"] = v
+        except Exception as e:  # pragma: no cover
+            traceback.print_exc(file=sys.stderr)
+            per["cpu_baseline_error"] = repr(e)
+    if env.rank == 0:
+        line["per_codec"] = per
+        print(json.dumps(line))
+    if env.world > 1:
+        env.dist.destroy_process_group()
 
 
 def main():
@@ -333,8 +741,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="lz4")
-    ap.add_argument("--blocks", type=int, default=0)
+    ap.add_argument("--codecs", default="lz4,bwt,flate,pipeline")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

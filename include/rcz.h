@@ -24,7 +24,12 @@
  *                             enqueues work on the context's stream (pipelines, benchmarks).
  *   - device data buffers must come from cudaMalloc-class allocators (the kernels may read up to the
  *     next 16-byte boundary past a block, which always stays inside such an allocation).
- *   - block/stream sizes are limited to < 2 GiB each (in_len, out_cap < 2^31).
+ *   - block/stream sizes are limited to < 2 GiB each: in_len[i], out_cap[i], n[i] < 2^31 and offsets < 2^62, else the call
+ *     returns RCZ_E_ARG (no "unbounded" sentinels).  BWT blocks are limited further, see rcz_bwt_decode_blocks.
+ *   - a unit whose status[i] != RCZ_OK: lz4, bwt and the bwt -> dc -> ari pipeline deliver nothing of it and report
+ *     out_len[i] == 0; flate, zlib, rle, ari and mtf deliver the out_len[i] bytes decoded before the error (the reference's
+ *     Read impls hand out what they have before returning Err); rcz_dc_encode_blocks reports the size it would have
+ *     needed when status[i] == RCZ_E_OUTPUT_FULL.
  */
 #ifndef RCZ_H
 #define RCZ_H
@@ -106,6 +111,8 @@ int64_t rcz_lz4_compression_bound(uint32_t size);
  * rcz_bwt_decode_blocks replaces `compute_inversion_table` + `InverseIterator` (bwt/mod.rs:223-282) as
  * driven by the stream decoder at bwt/mod.rs:388-393: block i = L column in_base[in_off[i] .. +n[i]] with
  * origin[i]; output written to out_base[out_off[i] ..], out_len[i] bytes (== n[i] for a well-formed block).
+ * Limit: n[i] <= 16,777,214 (the link table packs a 24-bit position with the symbol); larger blocks return
+ * RCZ_E_UNSUPPORTED in status[i] (the reference accepts any u32; its own docs suggest 4 MiB, bwt/mod.rs:32).
  * rcz_bwt_encode_blocks replaces `compute_suffixes` + `TransformIterator` (bwt/mod.rs:136-204) as called
  * at bwt/mod.rs:470-475: writes the L column (n[i] bytes) and origin[i]. */
 int rcz_bwt_decode_blocks(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* n,
@@ -126,9 +133,13 @@ int rcz_flate_decode_streams(rcz_ctx* ctx, const void* in_base, const uint64_t* 
 
 /* ---------------- zlib.rs + checksum/adler.rs ----------------
  * rcz_zlib_decode_streams replaces `zlib::Decoder` driven by read_to_end (zlib.rs:55-117): header checks, the DEFLATE
- * stream to its final block (the inflate kernel), Adler-32 of the output (adler.rs:34-44) against the big-endian
- * trailer.  detail[i] (optional) = RCZ_ZL_* for the wrapper's own errors, RCZ_FL_* for inflate's; in_used[i] (optional)
- * = bytes consumed including header and trailer; adler[i] (optional) = checksum of the decoded bytes.
+ * blocks (the inflate kernel), Adler-32 of the output (adler.rs:34-44).  As in the reference the big-endian trailer is read
+ * and compared ONLY when a DEFLATE block decodes to zero bytes (flate's read() returns Ok(0), zlib.rs:106-109) — the stream
+ * ends there; after a non-empty final block `inner.eof()` ends the stream first (zlib.rs:104-105) and a missing or wrong
+ * trailer goes unnoticed.  Callers that want the check compare adler[i] with the trailer themselves.
+ * detail[i] (optional) = RCZ_ZL_* for the wrapper's own errors, RCZ_FL_* for inflate's; in_used[i] (optional) = bytes
+ * consumed (header, DEFLATE bytes, and the 4 trailer bytes when they were read); adler[i] (optional) = checksum of the
+ * decoded bytes.
  * rcz_adler32_streams is `checksum::adler::State32::{feed,result}` over independent byte ranges. */
 int rcz_zlib_decode_streams(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
                             void* out_base, const uint64_t* out_off, const uint64_t* out_cap,

@@ -224,7 +224,7 @@ extern "C" int orc_flate_decode_streams_mt(const uint8_t* in_base, const uint64_
 }
 
 // zlib.rs:55-126  zlib::Decoder as driven by read_to_end: two header bytes (validate_header, zlib.rs:55-84), the DEFLATE
-// stream to its final block, then the big-endian Adler-32 of the output (zlib.rs:106-117; checksum/adler.rs:34-44).
+// stream block by block, and the big-endian Adler-32 trailer only where the reference reads it (zlib.rs:104-117; checksum/adler.rs:34-44).
 // detail: ORC_ZL_* for the wrapper's own errors, ORC_FL_* when the inner flate::Decoder failed.
 extern "C" uint32_t orc_adler32(const uint8_t* in, size_t n);
 extern "C" int orc_zlib_decode(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* out_len, size_t* consumed,
@@ -241,13 +241,29 @@ extern "C" int orc_zlib_decode(const uint8_t* in, size_t n, uint8_t* out, size_t
     else if (flg & 0x20) zd = ORC_ZL_PRESET_DICTIONARY;                       // zlib.rs:72-77
     else if ((((unsigned)cmf << 8) + flg) % 31 != 0) zd = ORC_ZL_BAD_HEADER_CHECKSUM;   // zlib.rs:79-84
     if (zd) { if (detail) *detail = zd; if (consumed) *consumed = 2; return ORC_E_INVALID_INPUT; }
-    size_t got = 0, used = 0; int fd = 0;
-    const int st = orc_flate_decode(in + 2, n - 2, out, cap, &got, &used, &fd);
+    // zlib.rs:99-124 under read_to_end.  Every read() hands out (part of) one DEFLATE block; once the inner decoder has drained its
+    // final block `self.inner.eof()` answers Ok(0) at zlib.rs:104-105 and the trailer is NEVER read.  The trailer is only read
+    // (zlib.rs:109) when `inner.read` itself returns Ok(0), i.e. when a block decodes to zero bytes (flate.rs:474-476: an empty
+    // final block, or an empty stored block in mid-stream) — from wherever the byte reader then stands.
+    Dec d; d.in = in + 2; d.n = n - 2; d.out = out; d.cap = cap;
+    bool empty_block = false;
+    for (;;) {
+        const size_t before = d.o;
+        if (!d.block()) {
+            *out_len = d.o;
+            if (consumed) *consumed = 2 + d.p;
+            if (detail) *detail = d.e.detail;
+            return d.e.status;
+        }
+        if (d.o == before) { empty_block = true; break; }
+        if (d.eof) break;
+    }
+    const size_t got = d.o, used = d.p;
     *out_len = got;
     if (consumed) *consumed = 2 + used;
-    if (st != ORC_OK) { if (detail) *detail = fd; return st; }
     const uint32_t a = orc_adler32(out, got);
     if (adler) *adler = a;
+    if (!empty_block) return ORC_OK;                                          // zlib.rs:104-105: eof() -> Ok(0), no trailer check
     if (n - 2 - used < 4) return ORC_E_UNEXPECTED_EOF;                        // read_u32::<BigEndian>
     const uint8_t* t = in + 2 + used;
     const uint32_t ck = ((uint32_t)t[0] << 24) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 8) | t[3];

@@ -412,6 +412,7 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
     if (nblocks == 0) return RCZ_OK;
     if (!in_base || !in_off || !n_arr || (!origin && !origin_dev) || !out_base || !out_off || !out_len || !status) return RCZ_E_ARG;
     if (nblocks > 0x3fffffu) return RCZ_E_ARG;
+    for (size_t i = 0; i < nblocks; ++i) if (in_off[i] > (1ull << 62) || out_off[i] > (1ull << 62)) return RCZ_E_ARG;
     rt_set_device(c->device);
 
     // ---- host-side geometry.  Blocks are processed in GROUPS of <= 16 Mi symbols, one kernel sequence per group: the
@@ -499,9 +500,12 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
     const size_t rank_smem = ((size_t)RANK_MAX_HEADS + 2) * 8;
     RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(ibwt_rank_kernel, rank_smem));
     st = ctx_timer_begin(c); if (st) return st;
+    // rcz_last_stage_ms: {partition (hist, scan, scatter), walk, rank + compact} of the FIRST group
+    bool mark = true;
     for (auto& g : groups) {
         const unsigned nb = (unsigned)(g.b1 - g.b0);
         if (nb == 0) continue;
+        if (mark) { st = ctx_stage_mark(c, 0); if (st) return st; }
         Blk* dblk = const_cast<Blk*>(ds.in_ptr<Blk>(i_blk)) + g.b0;
         const unsigned* dt2b = ds.in_ptr<unsigned>(i_t2b) + g.tile0_abs;
         uint64_t* d_len = ds.out_ptr<uint64_t>(o_len) + g.b0;
@@ -512,11 +516,14 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
         RCZ_KLAUNCH(c, ibwt_hist_kernel, g.ntiles, NT_TILE, 0, din, dblk, dt2b, tile_hist);
         RCZ_KLAUNCH(c, ibwt_scan_kernel, nb, 256, 0, dblk, tile_hist, cbase);
         RCZ_KLAUNCH(c, ibwt_scatter_kernel, g.ntiles, NT_TILE, sizeof(ScatterSmem), din, dblk, dt2b, tile_hist, cbase, (unsigned*)wP);
+        if (mark) { st = ctx_stage_mark(c, 1); if (st) return st; }
         const unsigned walk_grid = (unsigned)std::min<unsigned long long>((g.work + 255) / 256, (unsigned long long)c->sm_count * tune_ctas);
         RCZ_KLAUNCH(c, ibwt_walk_kernel, walk_grid, 256, 0, dblk, nb, (unsigned)g.work, (const unsigned*)wP, (uint8_t*)wS, desc, chain_ctr, queue);
+        if (mark) { st = ctx_stage_mark(c, 2); if (st) return st; }
         RCZ_KLAUNCH(c, ibwt_rank_kernel, nb, RANK_NT, rank_smem, dblk, desc, chain_ctr, chain_off, d_len, d_st);
         unsigned cx = (unsigned)std::min<unsigned long long>((g.chains / nb + 7) / 8 + 1, std::max<unsigned long long>(1, (unsigned long long)c->sm_count * 16 / nb));
         RCZ_KLAUNCH(c, ibwt_compact_kernel, dim3(cx, nb), 256, 0, dblk, (const uint8_t*)wS, desc, chain_ctr, chain_off, dout);
+        if (mark) { st = ctx_stage_mark(c, 3); if (st) return st; mark = false; }
     }
     st = ctx_timer_end(c); if (st) return st;
     st = ds.download(); if (st) return st;

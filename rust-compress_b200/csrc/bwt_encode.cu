@@ -317,6 +317,7 @@ extern "C" int rcz_bwt_encode_blocks(rcz_ctx* c, const void* in_base, const uint
     if (!c || rcz_bad_kind(mem_kind)) return RCZ_E_ARG;
     if (nblocks == 0) return RCZ_OK;
     if (!in_base || !in_off || !n_arr || !out_base || !out_off || !origin || !status || nblocks > 0x3fffffu) return RCZ_E_ARG;
+    for (size_t i = 0; i < nblocks; ++i) if (in_off[i] > (1ull << 62) || out_off[i] > (1ull << 62)) return RCZ_E_ARG;
     rt_set_device(c->device);
 
     // ---- geometry; big batches are cut into groups so that the sort workspace (28 B / symbol) stays bounded

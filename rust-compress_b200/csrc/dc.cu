@@ -253,6 +253,7 @@ extern "C" int rcz_dc_encode_blocks(rcz_ctx* c, const void* in_base, const uint6
     if (!c || rcz_bad_kind(mem_kind)) return RCZ_E_ARG;
     if (nblocks == 0) return RCZ_OK;
     if (!in_base || !in_off || !n_arr || !out_base || !out_off || !out_cap || !out_len || !status || nblocks > 0x3fffffu) return RCZ_E_ARG;
+    if (!rcz_spans_ok(in_off, n_arr, nblocks) || !rcz_spans_ok(out_off, out_cap, nblocks, 4)) return RCZ_E_ARG;
     rt_set_device(c->device);
     std::vector<Blk> blks(nblocks);
     std::vector<int32_t> hstatus(nblocks, 0);
@@ -317,6 +318,7 @@ extern "C" int rcz_dc_decode_blocks(rcz_ctx* c, const uint32_t* in_base, const u
     if (!c || rcz_bad_kind(mem_kind)) return RCZ_E_ARG;
     if (nblocks == 0) return RCZ_OK;
     if (!in_base || !in_off || !in_len || !out_base || !out_off || !n_arr || !status || nblocks > 0x7fffffffu) return RCZ_E_ARG;
+    if (!rcz_spans_ok(in_off, in_len, nblocks, 4) || !rcz_spans_ok(out_off, n_arr, nblocks)) return RCZ_E_ARG;
     rt_set_device(c->device);
     DescStager ds(c, mem_kind, nblocks);
     ds.add_in(in_off, nblocks * 8); ds.add_in(in_len, nblocks * 8); ds.add_in(out_off, nblocks * 8); ds.add_in(n_arr, nblocks * 8);

@@ -67,6 +67,7 @@ struct Bits {
 };
 
 enum { F_OK = 0, F_EOF = 1, F_INVALID = 2, F_MALFORMED = 3, F_FULL = 4 };
+constexpr unsigned long long ZL_EMPTY_BLOCK = 1ull << 63;   // zlib mode: in_used flag "the stream ended on a block of zero bytes"
 
 // flate.rs:83-120 HuffmanTree::construct, warp-cooperative.  lens[0..n) in shared memory.  Returns false when the
 // set is over-subscribed (:98-103).  lutbits == 0 builds only count[]/symbol[].
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(NT)
 inflate_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ in_len,
                uint8_t* __restrict__ out_base, const uint64_t* __restrict__ out_off, const uint64_t* __restrict__ out_cap,
                uint64_t* __restrict__ out_len, uint64_t* __restrict__ in_used, int32_t* __restrict__ status, int32_t* __restrict__ detail,
-               unsigned nstreams) {
+               unsigned nstreams, unsigned zlib_mode) {
     RCZ_DYN_SMEM(raw);
     const unsigned lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
     WarpSmem& w = reinterpret_cast<WarpSmem*>(raw)[wi];
@@ -299,7 +300,9 @@ inflate_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__
         s.out = out_base + out_off[sidx];
         s.cap = out_cap[sidx]; s.o = 0; s.detail = 0; s.qn = 0; s.qv = 0;
         int r = F_OK;
+        bool empty_block = false;
         for (;;) {                                                                   // flate.rs:195-206 block
+            const unsigned long long before = s.o;
             s.br.refill();
             const unsigned bfinal = s.br.take(1);
             if (s.br.eof()) { r = F_EOF; break; }
@@ -309,7 +312,9 @@ inflate_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__
             else if (type == 1) r = fixed_block(s, w, lane);
             else if (type == 2) r = dynamic_block(s, w, lane);
             else { s.detail = RCZ_FL_INVALID_BLOCK_CODE; r = F_INVALID; }
-            if (r != F_OK || bfinal) break;
+            if (r != F_OK || bfinal) { empty_block = r == F_OK && s.o == before; break; }
+            // zlib.rs:106-109: under zlib::Decoder a block of zero bytes makes flate's read() return Ok(0) and ends the stream there
+            if (zlib_mode && s.o == before) { empty_block = true; break; }
         }
         flush_lits(s, lane);
         __syncwarp();
@@ -318,7 +323,10 @@ inflate_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__
             status[sidx] = r == F_OK ? RCZ_OK : r == F_EOF ? RCZ_E_UNEXPECTED_EOF : r == F_INVALID ? RCZ_E_INVALID_INPUT
                            : r == F_MALFORMED ? RCZ_E_MALFORMED : RCZ_E_OUTPUT_FULL;
             if (detail) detail[sidx] = r == F_INVALID ? s.detail : 0;
-            if (in_used) { const unsigned long long bp = s.br.bytepos(); in_used[sidx] = (r == F_EOF || bp > n) ? n : bp; }
+            if (in_used) {
+                const unsigned long long bp = s.br.bytepos();
+                in_used[sidx] = ((r == F_EOF || bp > n) ? n : bp) | ((zlib_mode && empty_block) ? ZL_EMPTY_BLOCK : 0ull);
+            }
         }
     }
 }
@@ -332,7 +340,7 @@ extern "C" int rcz_flate_decode_streams(rcz_ctx* c, const void* in_base, const u
     if (n == 0) return RCZ_OK;
     if (!in_base || !in_off || !in_len || !out_base || !out_off || !out_cap || !out_len || !status || n > 0x7fffffffu) return RCZ_E_ARG;
     rt_set_device(c->device);
-    for (size_t i = 0; i < n; ++i) if (in_len[i] >= (1ull << 31)) return RCZ_E_ARG;
+    if (!rcz_spans_ok(in_off, in_len, n) || !rcz_spans_ok(out_off, out_cap, n)) return RCZ_E_ARG;
     DescStager ds(c, mem_kind, n);
     ds.add_in(in_off, n * 8); ds.add_in(in_len, n * 8); ds.add_in(out_off, n * 8); ds.add_in(out_cap, n * 8);
     ds.add_out(out_len, n * 8); ds.add_out(status, n * 4);
@@ -350,7 +358,7 @@ extern "C" int rcz_flate_decode_streams(rcz_ctx* c, const void* in_base, const u
     st = ctx_timer_begin(c); if (st) return st;
     RCZ_KLAUNCH(c, flk::inflate_kernel, grid, flk::NT, smem, din, ds.in_ptr<uint64_t>(0), ds.in_ptr<uint64_t>(1), dout, ds.in_ptr<uint64_t>(2),
                 ds.in_ptr<uint64_t>(3), ds.out_ptr<uint64_t>(0), in_used ? ds.out_ptr<uint64_t>(o_used) : (uint64_t*)nullptr,
-                ds.out_ptr<int32_t>(1), detail ? ds.out_ptr<int32_t>(o_det) : (int32_t*)nullptr, (unsigned)n);
+                ds.out_ptr<int32_t>(1), detail ? ds.out_ptr<int32_t>(o_det) : (int32_t*)nullptr, (unsigned)n, 0u);
     st = ctx_timer_end(c); if (st) return st;
     st = ds.download(); if (st) return st;
     if (mem_kind == RCZ_MEM_HOST) {
@@ -363,7 +371,7 @@ extern "C" int rcz_flate_decode_streams(rcz_ctx* c, const void* in_base, const u
 
 // ======================================================================================================
 // zlib wrapper: zlib.rs:55-117 header checks + the inflate kernel above + Adler-32
-// (checksum/adler.rs:34-44) of the output against the big-endian trailer.
+// (checksum/adler.rs:34-44) of the output; the big-endian trailer is compared exactly where `zlib::Decoder::read` compares it.
 // ======================================================================================================
 namespace zlk {
 
@@ -427,7 +435,7 @@ adler32_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ of
 }
 
 // one warp per stream, after inflate ran on bytes [2, n): header checks first (zlib.rs:55-84), then inflate's own outcome, then
-// the trailer (zlib.rs:106-117)
+// the trailer where the reference reads it (zlib.rs:106-117: only after a block of zero bytes)
 __global__ void __launch_bounds__(NT)
 zlib_finish_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ in_len,
                    const uint8_t* __restrict__ out_base, const uint64_t* __restrict__ out_off, uint64_t* __restrict__ out_len,
@@ -450,10 +458,13 @@ zlib_finish_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restri
             else if (((cmf << 8) + flg) % 31 != 0) zd = RCZ_ZL_BAD_HEADER_CHECKSUM;
             if (zd) { st = RCZ_E_INVALID_INPUT; det = zd; olen = 0; used = 2; }
             else {
-                used = 2 + used_fl[i];
+                used = 2 + (used_fl[i] & ~flk::ZL_EMPTY_BLOCK);
                 if (st == RCZ_OK) {
                     ad = warp_adler32(out_base + out_off[i], olen);
-                    if (len - used < 4) st = RCZ_E_UNEXPECTED_EOF;                                  // read_u32::<BigEndian>
+                    // the reference reads the trailer only when flate's read() returned Ok(0) on a block of zero bytes (zlib.rs:106-109);
+                    // after a non-empty final block `inner.eof()` ends the stream first (zlib.rs:104-105) and the trailer is never looked at
+                    if (!(used_fl[i] & flk::ZL_EMPTY_BLOCK)) {}
+                    else if (len - used < 4) st = RCZ_E_UNEXPECTED_EOF;                             // read_u32::<BigEndian>
                     else {
                         const uint8_t* t = in + used;
                         const unsigned ck = ((unsigned)t[0] << 24) | ((unsigned)t[1] << 16) | ((unsigned)t[2] << 8) | t[3];
@@ -472,7 +483,7 @@ zlib_finish_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restri
 extern "C" int rcz_adler32_streams(rcz_ctx* c, const void* base, const uint64_t* off, const uint64_t* len, uint32_t* adler, size_t n, int mem_kind) {
     if (!c || rcz_bad_kind(mem_kind)) return RCZ_E_ARG;
     if (n == 0) return RCZ_OK;
-    if (!base || !off || !len || !adler || n > 0x7fffffffu) return RCZ_E_ARG;
+    if (!base || !off || !len || !adler || n > 0x7fffffffu || !rcz_spans_ok(off, len, n)) return RCZ_E_ARG;
     rt_set_device(c->device);
     DescStager ds(c, mem_kind, n);
     ds.add_in(off, n * 8); ds.add_in(len, n * 8);
@@ -494,7 +505,7 @@ extern "C" int rcz_zlib_decode_streams(rcz_ctx* c, const void* in_base, const ui
     if (n == 0) return RCZ_OK;
     if (!in_base || !in_off || !in_len || !out_base || !out_off || !out_cap || !out_len || !status || n > 0x7fffffffu) return RCZ_E_ARG;
     rt_set_device(c->device);
-    for (size_t i = 0; i < n; ++i) if (in_len[i] >= (1ull << 31)) return RCZ_E_ARG;
+    if (!rcz_spans_ok(in_off, in_len, n) || !rcz_spans_ok(out_off, out_cap, n)) return RCZ_E_ARG;
     // the DEFLATE stream starts after the two header bytes (zlib.rs:55-57)
     std::vector<uint64_t> off2(n), len2(n);
     for (size_t i = 0; i < n; ++i) { const uint64_t h = in_len[i] < 2 ? in_len[i] : 2; off2[i] = in_off[i] + h; len2[i] = in_len[i] - h; }
@@ -520,7 +531,7 @@ extern "C" int rcz_zlib_decode_streams(rcz_ctx* c, const void* in_base, const ui
     const unsigned grid = (unsigned)std::min<size_t>((n + flk::WPB - 1) / flk::WPB, (size_t)c->sm_count * 12);
     st = ctx_timer_begin(c); if (st) return st;
     RCZ_KLAUNCH(c, flk::inflate_kernel, grid, flk::NT, smem, din, ds.in_ptr<uint64_t>(i_off2), ds.in_ptr<uint64_t>(i_len2), dout, ds.in_ptr<uint64_t>(2),
-                ds.in_ptr<uint64_t>(3), ds.out_ptr<uint64_t>(0), d_used_fl, ds.out_ptr<int32_t>(1), d_det, (unsigned)n);
+                ds.in_ptr<uint64_t>(3), ds.out_ptr<uint64_t>(0), d_used_fl, ds.out_ptr<int32_t>(1), d_det, (unsigned)n, 1u);
     const unsigned grid2 = (unsigned)std::min<size_t>((n + zlk::WPB - 1) / zlk::WPB, (size_t)c->sm_count * 8);
     RCZ_KLAUNCH(c, zlk::zlib_finish_kernel, grid2, zlk::NT, 0, din, ds.in_ptr<uint64_t>(0), ds.in_ptr<uint64_t>(1), dout, ds.in_ptr<uint64_t>(2),
                 ds.out_ptr<uint64_t>(0), d_used_fl, in_used ? ds.out_ptr<uint64_t>(o_used) : (uint64_t*)nullptr, ds.out_ptr<int32_t>(1), d_det,

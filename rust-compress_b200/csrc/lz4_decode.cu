@@ -488,7 +488,8 @@ lz4_scan_kernel(const uint32_t* __restrict__ wbase, const uint32_t* __restrict__
         }
         acc += __shfl_sync(RCZ_FULL, incl, 31);
     }
-    if (lane == 0) { out_len[b] = acc; status[b] = st; blkstate[b] = st; }
+    // nothing of a failed block is materialised (lz4_mat_kernel skips it), so its length is reported as 0 in every mem_kind
+    if (lane == 0) { out_len[b] = st == RCZ_OK ? acc : 0ull; status[b] = st; blkstate[b] = st; }
 }
 
 // ======================================================================================================
@@ -1028,7 +1029,7 @@ extern "C" int rcz_lz4_decode_blocks(rcz_ctx* c, const void* in_base, const uint
     if (!in_base || !in_off || !in_len || !out_base || !out_off || !out_cap || !out_len || !status) return RCZ_E_ARG;
     if (nblocks > 0x7fffffffu) return RCZ_E_ARG;
     rt_set_device(c->device);
-    for (size_t i = 0; i < nblocks; ++i) if (in_len[i] >= (1ull << 31)) return RCZ_E_ARG;
+    if (!rcz_spans_ok(in_off, in_len, nblocks) || !rcz_spans_ok(out_off, out_cap, nblocks)) return RCZ_E_ARG;
     DescStager ds(c, mem_kind, nblocks);
     ds.add_in(in_off, nblocks * 8); ds.add_in(in_len, nblocks * 8); ds.add_in(out_off, nblocks * 8); ds.add_in(out_cap, nblocks * 8);
     ds.add_out(out_len, nblocks * 8); ds.add_out(status, nblocks * 4);

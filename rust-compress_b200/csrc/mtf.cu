@@ -80,6 +80,7 @@ static int mtf_batch(rcz_ctx* c, bool decode, const void* in_base, const uint64_
     if (!c || rcz_bad_kind(mem_kind)) return RCZ_E_ARG;
     if (n == 0) return RCZ_OK;
     if (!in_base || !in_off || !in_len || !out_base || !out_off || !out_cap || !out_len || !status || n > 0x7fffffffu) return RCZ_E_ARG;
+    if (!rcz_spans_ok(in_off, in_len, n) || !rcz_spans_ok(out_off, out_cap, n)) return RCZ_E_ARG;
     rt_set_device(c->device);
     DescStager ds(c, mem_kind, n);
     ds.add_in(in_off, n * 8); ds.add_in(in_len, n * 8); ds.add_in(out_off, n * 8); ds.add_in(out_cap, n * 8);

@@ -272,6 +272,7 @@ extern "C" int rcz_bwt_dc_ari_encode_blocks(rcz_ctx* c, const void* in_base, con
     if (!c || rcz_bad_kind(mem_kind) || !chunk_ok(ari_chunk)) return RCZ_E_ARG;
     if (nblocks == 0) return RCZ_OK;
     if (!in_base || !in_off || !n_arr || !out_base || !out_off || !out_cap || !out_len || !status || nblocks > 0x3fffffu) return RCZ_E_ARG;
+    if (!rcz_spans_ok(in_off, n_arr, nblocks) || !rcz_spans_ok(out_off, out_cap, nblocks)) return RCZ_E_ARG;
     rt_set_device(c->device);
     Geom g;
     int st = geometry(out_off, out_cap, n_arr, nblocks, ari_chunk, g); if (st) return st;
@@ -351,6 +352,7 @@ extern "C" int rcz_bwt_dc_ari_decode_blocks(rcz_ctx* c, const void* in_base, con
     if (!c || rcz_bad_kind(mem_kind) || !chunk_ok(ari_chunk)) return RCZ_E_ARG;
     if (nblocks == 0) return RCZ_OK;
     if (!in_base || !in_off || !in_len || !out_base || !out_off || !n_arr || !out_len || !status || nblocks > 0x3fffffu) return RCZ_E_ARG;
+    if (!rcz_spans_ok(in_off, in_len, nblocks) || !rcz_spans_ok(out_off, n_arr, nblocks)) return RCZ_E_ARG;
     rt_set_device(c->device);
     Geom g;
     int st = geometry(in_off, in_len, n_arr, nblocks, ari_chunk, g); if (st) return st;

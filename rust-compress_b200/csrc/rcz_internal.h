@@ -176,4 +176,13 @@ int rcz_dc_decode_launch(rcz_ctx* c, const uint32_t* din, const uint64_t* d_in_o
 int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, const uint64_t* n_arr, const uint32_t* origin_host,
                        const uint32_t* origin_dev, void* out_base, const uint64_t* out_off, uint64_t* out_len, int32_t* status,
                        size_t nblocks, int mem_kind);
+// Every (off[i], len[i]) pair of a batch call: len < 2^31 units (rcz.h) and off + len representable; `elem` = bytes per unit.
+// A caller's "unbounded" sentinel such as UINT64_MAX would otherwise wrap the span arithmetic of stage_span_in / _out.
+inline bool rcz_spans_ok(const uint64_t* off, const uint64_t* len, size_t n, uint64_t elem = 1) {
+    for (size_t i = 0; i < n; ++i) {
+        if (len[i] >= (1ull << 31)) return false;
+        if (off[i] > (1ull << 62) / elem) return false;
+    }
+    return true;
+}
 inline bool rcz_bad_kind(int k) { return k != RCZ_MEM_HOST && k != RCZ_MEM_DEVICE && k != RCZ_MEM_DEVICE_ASYNC; }

@@ -214,6 +214,12 @@ template <class R> class Decoder {
                                              st.data(), clen.size(), RCZ_MEM_HOST), "rcz_lz4_decode_blocks");
         for (auto& p : pieces) {
             if (p.raw) { out_.buf.insert(out_.buf.end(), p.bytes.begin(), p.bytes.end()); continue; }
+            if (st[p.idx] == RCZ_E_OUTPUT_FULL && ocap[p.idx] < 255ull * clen[p.idx] + 64) {
+                // the BD size is only a reserve hint in the reference (lz4.rs:444-446; grow_output has no limit): a block that decodes to
+                // more than it declares is decoded again on its own with the format's bound
+                try { decode_block(ctx_, comp.data() + slot[p.idx], (size_t)clen[p.idx], out_.buf); continue; }
+                catch (const io_error& e) { pending_ = e; pending_err_ = true; end_seen_ = false; break; }
+            }
             if (st[p.idx] != RCZ_OK) { pending_ = error_from_status(st[p.idx], "lz4::Decoder"); pending_err_ = true; end_seen_ = false; break; }
             out_.buf.insert(out_.buf.end(), dec.begin() + (size_t)ooff[p.idx], dec.begin() + (size_t)(ooff[p.idx] + olen[p.idx]));
         }
@@ -476,7 +482,7 @@ template <class R> class Decoder {                                           // 
     void reset() { decoded_ = false; out_.clear(); in_.clear(); }            // zlib.rs:91-95
     uint32_t checksum() const { return adler_; }                              // hash.result() after the last byte
 
-    // header on the first call (zlib.rs:99-102), then decoded bytes; the trailer is checked when the data runs out (zlib.rs:106-117)
+    // header on the first call (zlib.rs:99-102), then decoded bytes; the trailer is compared only after a block of zero bytes (zlib.rs:104-117)
     size_t read(uint8_t* dst, size_t len) {
         if (!decoded_) decode_all();
         size_t k = out_.take(dst, len);

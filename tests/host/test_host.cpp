@@ -79,6 +79,20 @@ int main(int argc, char** argv) {
             CHECK(read_to_end(d) == input);
         }
     });
+    run("lz4::block larger than the BD size decodes (max_block_size is a reserve hint, lz4.rs:444-446)", [&] {
+        // frame with BD = 64 KiB whose single compressed block holds 100,000 zero bytes: 1 literal + one overlapping match of 99,999
+        bytes blk = {0x1F, 0x00, 0x01, 0x00};
+        for (int i = 0; i < 392; ++i) blk.push_back(0xFF);
+        blk.push_back(20);                                                     // 4 + 15 + 392 * 255 + 20 = 99,999
+        bytes f = {0x04, 0x22, 0x4D, 0x18, 0x60, 0x40, 0x00};
+        const uint32_t n = (uint32_t)blk.size();
+        for (int k = 0; k < 4; ++k) f.push_back((uint8_t)(n >> (8 * k)));
+        f.insert(f.end(), blk.begin(), blk.end());
+        for (int k = 0; k < 4; ++k) f.push_back(0);
+        rcz::lz4::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(f));
+        bytes out = read_to_end(d);
+        CHECK(out.size() == 100000 && out == bytes(100000, 0));
+    });
     run("lz4::decode_block + errors", [&] {
         bytes f = load("ref_test.lz4.3");
         uint32_t n = (uint32_t)f[7] | ((uint32_t)f[8] << 8) | ((uint32_t)f[9] << 16) | ((uint32_t)f[10] << 24);
@@ -237,7 +251,13 @@ int main(int argc, char** argv) {
         bytes b = f; b[0] = 0x68; b[1] = 0x81; CHECK(fails_with(b, RCZ_ZL_UNSUPPORTED_WINDOW));
         bytes c = f; c[0] = 0x78; c[1] = 0xBB; CHECK(fails_with(c, RCZ_ZL_PRESET_DICTIONARY));
         bytes e = f; e[1] ^= 1; CHECK(fails_with(e, RCZ_ZL_BAD_HEADER_CHECKSUM));
-        bytes g = f; g[g.size() - 1] ^= 1; CHECK(fails_with(g, RCZ_ZL_BAD_CHECKSUM));
+        // the trailer is only read after a DEFLATE block of zero bytes (zlib.rs:104-109): a wrong trailer behind a non-empty final block
+        // goes unnoticed, as in the reference; the empty stream `78 9c 03 00 | 00 00 00 01` is where it is compared
+        bytes g = f; g[g.size() - 1] ^= 1;
+        { rcz::zlib::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(g)); CHECK(read_to_end(d) == txt); }
+        bytes h = {0x78, 0x9c, 0x03, 0x00, 0x00, 0x00, 0x00, 0x01};
+        { rcz::zlib::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(h)); CHECK(read_to_end(d).empty()); }
+        h[7] = 0x02; CHECK(fails_with(h, RCZ_ZL_BAD_CHECKSUM));
     });
 
     // ------------------------------------------------------------------------------------------ mtf (bwt/mtf.rs:176-192)

@@ -99,6 +99,8 @@ def _check(ctx, oracle, units, caps, **kw):
         assert got[i][0] == st, (i, got[i][0], st)
         if st == 0:
             assert got[i][1] == ref, "block %d differs" % i
+        else:
+            assert got[i][1] == b"", "block %d failed: out_len must be 0 (rcz.h)" % i
 
 
 @pytest.mark.parametrize("name", CASE_NAMES)

@@ -22,6 +22,14 @@ def _streams(gen):
             d = gen.one(kind, 50 + level, n)
             units.append(zlib.compress(d, level)); caps.append(n); names.append("%s.l%d" % (kind, level))
     units.append(zlib.compress(b"")); caps.append(16); names.append("empty")
+    # streams that end on / contain a block of zero bytes: the only place where the reference reads the trailer (zlib.rs:106-109)
+    co = zlib.compressobj(6)
+    sync = co.compress(gen.one("hextext", 77, 3000)) + co.flush(zlib.Z_SYNC_FLUSH) + co.compress(b"tail") + co.flush()
+    units.append(sync); caps.append(4000); names.append("sync_flush_mid_stream")
+    co = zlib.compressobj(6)
+    body = co.compress(gen.one("hextext", 78, 3000)) + co.flush(zlib.Z_SYNC_FLUSH)
+    d = gen.one("hextext", 78, 3000)
+    units.append(body + zlib.adler32(d).to_bytes(4, "big")); caps.append(4000); names.append("sync_then_valid_trailer")
     good = zlib.compress(gen.one("hextext", 9, 5000), 6)
     bad = [("short0", b""), ("short1", good[:1]), ("bad_method", bytes([0x77, good[1]]) + good[2:]),
            ("bad_window", bytes([0x68, 0x81]) + good[2:]),        # CINFO 6, FCHECK valid: only the window test fails
@@ -59,7 +67,9 @@ def _check(ctx, oracle, gen, device=False):
             got = outb[int(out_off[i]): int(out_off[i]) + int(out_len[i])].tobytes()
             assert got == ref, nm
             assert int(adler[i]) == ad == zlib.adler32(ref), nm
-            assert int(in_used[i]) == used == len(u), nm
+            assert int(in_used[i]) == used, nm
+            # the reference reads the 4 trailer bytes only after a block of zero bytes (zlib.rs:104-109)
+            assert used in (len(u), len(u) - 4, len(u) - 2) or nm.startswith(("fuzz", "sync")), (nm, used, len(u))
         elif st == -1:
             assert int(detail[i]) == det, (nm, int(detail[i]), det)
     assert {0, -1, -2, -5} <= seen                                # ok, InvalidInput, UnexpectedEof, output full all occur
@@ -68,11 +78,29 @@ def _check(ctx, oracle, gen, device=False):
 
 
 def test_oracle_zlib_on_reference_fixtures(oracle):
-    """Pins the restatement: zlib.rs:152-165 (test.z.0-9 -> test.txt), trailer == Adler-32 of the text."""
+    """Pins the restatement: zlib.rs:152-165 (test.z.0-9 -> test.txt); the fixtures' trailer == Adler-32 of the text, and the
+    reference never reads it for them (their final block is not empty: zlib.rs:104-105 answers first)."""
     for i in range(10):
         z = golden("ref_test.z.%d" % i)
         st, out, used, det, ad = oracle.zlib_decode(z, 4096)
-        assert (st, out, used) == (0, TXT, len(z)) and ad == zlib.adler32(TXT) == int.from_bytes(z[-4:], "big")
+        assert (st, out, used) == (0, TXT, len(z) - 4) and ad == zlib.adler32(TXT) == int.from_bytes(z[-4:], "big")
+
+
+def test_oracle_zlib_trailer_rule(oracle, gen):
+    """zlib.rs:99-124: trailer compared only after a block of zero bytes."""
+    d = gen.one("hextext", 9, 5000)
+    good = zlib.compress(d, 6)
+    for mangled in (good[:-1] + bytes([good[-1] ^ 1]), good[:-4], good[:-2]):      # wrong / missing trailer after a non-empty final block
+        st, out, used, det, ad = oracle.zlib_decode(mangled, 6000)
+        assert (st, out, used, ad) == (0, d, len(good) - 4, zlib.adler32(d))
+    empty = zlib.compress(b"")                                                      # one empty final block: trailer is read and checked
+    assert oracle.zlib_decode(empty, 16)[:3] == (0, b"", len(empty))
+    assert oracle.zlib_decode(empty[:-1] + b"\x02", 16)[0] == -1
+    assert oracle.zlib_decode(empty[:-2], 16)[0] == -2
+    co = zlib.compressobj(6)
+    sync = co.compress(d) + co.flush(zlib.Z_SYNC_FLUSH) + co.compress(b"tail") + co.flush()
+    st, out, used, det, ad = oracle.zlib_decode(sync, 6000)                         # the 4 bytes after the empty stored block are not the checksum
+    assert st == -1 and det == 20 and out == d
 
 
 def test_zlib_emu(emu_ctx, oracle, gen):
