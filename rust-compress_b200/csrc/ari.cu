@@ -1,79 +1,114 @@
-// ari.cu — K7/K8: adaptive order-0 range coder, one warp per stream.
+// ari.cu — K7/K8: adaptive order-0 range coder, one THREAD per stream.
 //
 // Replaces /root/reference/src/entropy/ari/table.rs:203-219 (`ByteEncoder::write` + `finish`) and :255-272
 // (`ByteDecoder::read`), i.e. `RangeEncoder::process` (ari/mod.rs:117-150) driven by the 257-symbol frequency table
 // `table::Model` (table.rs:20-122: counts start at 1, `add = (total>>10)+1`, halve-with-round-up at total >= 4096).
 // The chain is strictly serial in the symbol index (adaptive model + carried low/hai), so parallelism is across
-// streams; inside a warp the reference's O(257) linear sums (table.rs:100-117) become warp-shuffle reductions/scans
-// over a frequency table distributed 9 bins per lane.
+// streams.  A stream is one thread: its 257-bin model lives in shared memory (u16 counts, two per word, plus 17 group sums),
+// which turns the reference's O(257) linear sums (table.rs:100-117) into <= 17 + 16 terms, and 32 streams share every issued
+// instruction (the round-1 kernel gave a whole warp to one stream: same chain length, 1/32 of the throughput).
+// Input and output run through per-thread register buffers (aligned 16-byte loads, aligned 4-byte stores).
 #include "rcz_internal.h"
 #include <algorithm>
 
 namespace arik {
 
-constexpr int NT = 128;
+constexpr int NT = 128;                            // streams (threads) per CTA
 constexpr unsigned SYMBOL_MASK = 0xFF000000u;     // ari/mod.rs:59
 constexpr unsigned THRESHOLD = 1u << 14;          // ari/mod.rs:61
 constexpr unsigned CUT = THRESHOLD >> 2;          // table.rs:195
+constexpr int NBIN = 272;                         // 257 bins in 17 groups of 16 (bins 257.. stay 0)
+constexpr int ROW = NBIN / 2 + 9;                 // 32-bit words per stream: 136 of bins (two u16 each) + 9 of group sums; odd => rows spread over all banks
+static_assert(ROW % 2 == 1, "odd row stride");
 
-// frequency table: bin b lives in lane b / 9, slot b % 9
+// table::Model (table.rs:20-122) of ONE stream, owned by one thread, in shared memory: u16 counts packed two per word plus the
+// sums of 17 groups of 16 bins, so that the reference's O(257) linear sums (table.rs:100-117) become <= 17 + 16 terms.
 struct Model {
-    unsigned f[9];
-    unsigned lsum;     // sum of this lane's bins
-    unsigned total;    // warp-uniform
-    __device__ __forceinline__ void init(unsigned lane) {
-        lsum = 0;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) { f[k] = (lane * 9 + k) < 257u ? 1u : 0u; lsum += f[k]; }
+    unsigned* w;        // bins: w[0..136), group sums: w[136..145)
+    unsigned total;
+    __device__ __forceinline__ void init(unsigned* row) {
+        w = row;
+        for (int i = 0; i < 128; ++i) w[i] = 0x00010001u;                 // bins 0..255 = 1
+        w[128] = 0x00000001u;                                             // bin 256 (terminator) = 1, bin 257 = 0
+        for (int i = 129; i < 136; ++i) w[i] = 0;
+        for (int g = 0; g < 8; ++g) w[136 + g] = 0x00100010u;             // groups 0..15: 16 each
+        w[144] = 0x00000001u;                                             // group 16: 1
         total = 257;
     }
-    // table.rs:100-103 get_range: lo = sum of bins below v, hi = lo + f[v]
-    __device__ __forceinline__ void range_of(unsigned v, unsigned lane, unsigned& lo, unsigned& hi) const {
-        const unsigned lv = v / 9, kv = v - lv * 9;
-        unsigned part = 0, fv = 0;
-        if (lane < lv) part = lsum;
-        else if (lane == lv) {
+    // sum of the first k u16 values of the packed array a[0..nw): branch-free (every stream of the warp runs the same instructions)
+    template <int NW>
+    __device__ __forceinline__ unsigned prefix(const unsigned* a, unsigned k) const {
+        unsigned acc = 0;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) { if ((unsigned)k < kv) part += f[k]; if ((unsigned)k == kv) fv = f[k]; }
+        for (int j = 0; j < NW; ++j) {
+            const unsigned x = a[j];
+            const unsigned lo = x & 0xffffu, hi = x >> 16;
+            acc += (k > 2u * j ? lo : 0u) + (k > 2u * j + 1u ? hi : 0u);
         }
-        lo = warp_reduce_add(part);
-        hi = lo + __shfl_sync(RCZ_FULL, fv, (int)lv);
+        return acc;
     }
-    // table.rs:105-117 find_value: first v with cumulative(v+1) > offset
-    __device__ __forceinline__ void find(unsigned offset, unsigned lane, unsigned& v, unsigned& lo, unsigned& hi) const {
-        const unsigned incl = warp_incl_scan_add(lsum);
-        const unsigned excl = incl - lsum;
-        const unsigned hit = __ballot_sync(RCZ_FULL, offset < incl);
-        const unsigned lv = (unsigned)__ffs((int)hit) - 1u;
-        unsigned myv = 0, mylo = 0, myhi = 0;
-        if (lane == lv) {
-            unsigned c = excl; bool found = false;
+    // table.rs:100-103 get_range
+    __device__ __forceinline__ void range_of(unsigned v, unsigned& lo, unsigned& hi) const {
+        const unsigned g = v >> 4, k = v & 15u;
+        lo = prefix<9>(w + 136, g) + prefix<8>(w + 8 * g, k);
+        const unsigned x = w[v >> 1];
+        hi = lo + ((v & 1u) ? x >> 16 : x & 0xffffu);
+    }
+    // table.rs:105-117 find_value: first v with cumulative(v + 1) > offset (offset < total)
+    __device__ __forceinline__ void find(unsigned offset, unsigned& v, unsigned& lo, unsigned& hi) const {
+        unsigned acc = 0, g = 0, base = 0;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                const unsigned nxt = c + f[k];
-                if (!found && offset < nxt) { found = true; myv = lane * 9 + k; mylo = c; myhi = nxt; }
-                c = nxt;
-            }
+        for (int j = 0; j < 9; ++j) {
+            const unsigned x = w[136 + j];
+            unsigned inc = acc + (x & 0xffffu);
+            bool c = inc <= offset; g += c; base = c ? inc : base; acc = inc;
+            if (j < 8) { inc = acc + (x >> 16); c = inc <= offset; g += c; base = c ? inc : base; acc = inc; }
         }
-        v = __shfl_sync(RCZ_FULL, myv, (int)lv);
-        lo = __shfl_sync(RCZ_FULL, mylo, (int)lv);
-        hi = __shfl_sync(RCZ_FULL, myhi, (int)lv);
+        g = g > 16u ? 16u : g;                                            // (offset < total always lands in a group)
+        const unsigned* a = w + 8 * g;
+        unsigned k = 0, lo_ = base, hi_ = base;
+        acc = base;
+        bool open = true;                                                 // still looking for the bin
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const unsigned x = a[j];
+            unsigned f = x & 0xffffu, inc = acc + f;
+            bool hit = open && offset < inc;
+            if (hit) { lo_ = acc; hi_ = inc; k = 2 * j; open = false; }
+            acc = inc;
+            f = x >> 16; inc = acc + f;
+            hit = open && offset < inc;
+            if (hit) { lo_ = acc; hi_ = inc; k = 2 * j + 1; open = false; }
+            acc = inc;
+        }
+        v = 16u * g + k; lo = lo_; hi = hi_;
     }
     // table.rs:69-91 update(value, 10, 1) + downscale
-    __device__ __forceinline__ void update(unsigned v, unsigned lane) {
+    __device__ __forceinline__ void update(unsigned v) {
         const unsigned add = (total >> 10) + 1;
-        const unsigned lv = v / 9, kv = v - lv * 9;
-        if (lane == lv) {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) if ((unsigned)k == kv) f[k] = (f[k] + add) & 0xffffu;   // Frequency = u16
-            lsum += add;
-        }
+        const unsigned sh = (v & 1u) * 16u;
+        unsigned x = w[v >> 1];
+        x = (x & ~(0xffffu << sh)) | ((((x >> sh) + add) & 0xffffu) << sh);   // Frequency = u16
+        w[v >> 1] = x;
+        const unsigned g = v >> 4, gs = (g & 1u) * 16u;
+        w[136 + (g >> 1)] += add << gs;                                   // group sums stay far below 2^16
         total += add;
         if (total >= CUT) {
-            lsum = 0;
+            unsigned tot = 0;
+            for (int g2 = 0; g2 < 17; ++g2) {
+                unsigned gsum = 0;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) { f[k] = (f[k] + 1) >> 1; lsum += f[k]; }
-            total = warp_reduce_add(lsum);
+                for (int j = 0; j < 8; ++j) {
+                    unsigned y = w[8 * g2 + j];
+                    y = ((y + 0x00010001u) >> 1) & 0x7fff7fffu;           // (f + 1) >> 1 on both halves (counts < 2^15: no carry between them)
+                    w[8 * g2 + j] = y;
+                    gsum += (y & 0xffffu) + (y >> 16);
+                }
+                const unsigned s2 = (g2 & 1u) * 16u;
+                w[136 + (g2 >> 1)] = (w[136 + (g2 >> 1)] & ~(0xffffu << s2)) | (gsum << s2);
+                tot += gsum;
+            }
+            total = tot;
         }
     }
 };
@@ -97,41 +132,64 @@ __device__ __forceinline__ void range_step(unsigned& low, unsigned& hai, unsigne
     low = lo; hai = hi;
 }
 
+// sequential byte reader of one thread: aligned 16-byte loads, the next one in flight while the current one is consumed
+struct ByteIn {
+    const uint4* vp; unsigned long long lo, hi; unsigned left;
+    __device__ __forceinline__ void init(const uint8_t* p) {
+        const unsigned mis = (unsigned)((uintptr_t)p & 15u);
+        vp = reinterpret_cast<const uint4*>(p - mis);
+        load();
+        for (unsigned i = 0; i < mis; ++i) shift();
+        left = 16u - mis;
+    }
+    __device__ __forceinline__ void load() { const uint4 q = __ldg(vp); ++vp; lo = (unsigned long long)q.x | ((unsigned long long)q.y << 32); hi = (unsigned long long)q.z | ((unsigned long long)q.w << 32); }
+    __device__ __forceinline__ void shift() { lo = (lo >> 8) | (hi << 56); hi >>= 8; }
+    // the caller guarantees that the byte exists (reads stay inside the 16-byte-aligned span of the stream, see rcz.h)
+    __device__ __forceinline__ unsigned next() {
+        if (left == 0) { load(); left = 16; }
+        const unsigned b = (unsigned)lo & 255u;
+        shift(); --left;
+        return b;
+    }
+};
+
+// sequential byte writer of one thread: head bytes up to the first 4-byte boundary one by one, then aligned 32-bit stores
+struct ByteOut {
+    uint8_t* out; unsigned long long cap, o; unsigned acc, cnt; bool full;
+    __device__ __forceinline__ void init(uint8_t* p, unsigned long long c) { out = p; cap = c; o = 0; acc = 0; cnt = 0; full = false; }
+    __device__ __forceinline__ void put(unsigned b) {
+        if (o >= cap) { if (cnt) flush(); full = true; ++o; return; }             // out_len keeps counting: the size the stream would have needed
+        if (((uintptr_t)(out + o) & 3u) != 0 && cnt == 0) { out[o++] = (uint8_t)b; return; }      // head (or an unaligned stream start)
+        acc |= b << (8u * cnt); ++cnt; ++o;
+        if (cnt == 4) { *reinterpret_cast<unsigned*>(out + o - 4) = acc; acc = 0; cnt = 0; }
+    }
+    __device__ __forceinline__ void flush() { for (unsigned i = 0; i < cnt; ++i) out[o - cnt + i] = (uint8_t)(acc >> (8u * i)); cnt = 0; acc = 0; }
+};
+
 __global__ void __launch_bounds__(NT)
 ari_encode_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ in_len,
                   uint8_t* __restrict__ out_base, const uint64_t* __restrict__ out_off, const uint64_t* __restrict__ out_cap,
                   uint64_t* __restrict__ out_len, int32_t* __restrict__ status, unsigned nstreams) {
-    const unsigned lane = threadIdx.x & 31, wpb = NT / 32;
-    for (unsigned sidx = blockIdx.x * wpb + (threadIdx.x >> 5); sidx < nstreams; sidx += gridDim.x * wpb) {
-        const uint8_t* in = in_base + in_off[sidx];
+    RCZ_DYN_SMEM(raw);
+    unsigned* row = reinterpret_cast<unsigned*>(raw) + threadIdx.x * ROW;
+    for (unsigned sidx = blockIdx.x * NT + threadIdx.x; sidx < nstreams; sidx += gridDim.x * NT) {
         const unsigned long long n = in_len[sidx];
-        uint8_t* out = out_base + out_off[sidx];
-        const unsigned long long cap = out_cap[sidx];
-        if (n == RCZ_STREAM_SKIP) { if (lane == 0) { out_len[sidx] = 0; status[sidx] = RCZ_OK; } continue; }   // unused slot of a composed call
-        Model m; m.init(lane);
+        if (n == RCZ_STREAM_SKIP) { out_len[sidx] = 0; status[sidx] = RCZ_OK; continue; }          // unused slot of a composed call
+        Model m; m.init(row);
+        ByteIn bi; if (n) bi.init(in_base + in_off[sidx]);
+        ByteOut bo; bo.init(out_base + out_off[sidx], out_cap[sidx]);
         unsigned low = 0, hai = 0xFFFFFFFFu;
-        unsigned long long o = 0;
-        bool full = false;
-        for (unsigned long long i = 0; i <= n; i += 32) {
-            const unsigned chunk = (i + lane < n) ? (unsigned)in[i + lane] : 256u;      // 32 symbols per load
-            const unsigned cnt = (unsigned)((n - i) < 32 ? (n - i) + 1 : 32);           // +1: the terminator (table.rs:203-204)
-            for (unsigned k = 0; k < cnt; ++k) {
-                const unsigned v = __shfl_sync(RCZ_FULL, chunk, (int)k);
-                unsigned lo, hi, bytes, nout;
-                m.range_of(v, lane, lo, hi);
-                range_step(low, hai, m.total, lo, hi, bytes, nout);
-                if (lane < nout) {                                                       // ari/mod.rs:223-227
-                    if (o + lane < cap) out[o + lane] = (uint8_t)(bytes >> (8 * (nout - 1 - lane))); else full = true;
-                }
-                o += nout;
-                if (v != 256u) m.update(v, lane);                                        // table.rs:215; no update after the terminator
-            }
-            if (cnt < 32 || i + 32 > n) break;
+        for (unsigned long long i = 0; i <= n; ++i) {
+            const unsigned v = i < n ? bi.next() : 256u;                                          // the terminator follows the data (table.rs:203-204)
+            unsigned lo, hi, bytes, nout;
+            m.range_of(v, lo, hi);
+            range_step(low, hai, m.total, lo, hi, bytes, nout);
+            for (unsigned k = 0; k < nout; ++k) bo.put((bytes >> (8u * (nout - 1u - k))) & 255u);   // ari/mod.rs:223-227
+            if (v != 256u) m.update(v);                                                            // table.rs:215; no update after the terminator
         }
-        if (lane < 4) { if (o + lane < cap) out[o + lane] = (uint8_t)(low >> (8 * (3 - lane))); else full = true; }   // ari/mod.rs:230-237
-        o += 4;
-        full = __any_sync(RCZ_FULL, full);
-        if (lane == 0) { out_len[sidx] = o; status[sidx] = full ? RCZ_E_OUTPUT_FULL : RCZ_OK; }
+        for (unsigned k = 0; k < 4; ++k) bo.put((low >> (8u * (3u - k))) & 255u);                  // ari/mod.rs:230-237
+        bo.flush();
+        out_len[sidx] = bo.o; status[sidx] = bo.full ? RCZ_E_OUTPUT_FULL : RCZ_OK;
     }
 }
 
@@ -139,45 +197,42 @@ __global__ void __launch_bounds__(NT)
 ari_decode_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ in_len,
                   uint8_t* __restrict__ out_base, const uint64_t* __restrict__ out_off, const uint64_t* __restrict__ out_cap,
                   uint64_t* __restrict__ out_len, uint64_t* __restrict__ in_used, int32_t* __restrict__ status, unsigned nstreams) {
-    const unsigned lane = threadIdx.x & 31, wpb = NT / 32;
-    for (unsigned sidx = blockIdx.x * wpb + (threadIdx.x >> 5); sidx < nstreams; sidx += gridDim.x * wpb) {
-        const uint8_t* in = in_base + in_off[sidx];
+    RCZ_DYN_SMEM(raw);
+    unsigned* row = reinterpret_cast<unsigned*>(raw) + threadIdx.x * ROW;
+    for (unsigned sidx = blockIdx.x * NT + threadIdx.x; sidx < nstreams; sidx += gridDim.x * NT) {
         const unsigned long long n = in_len[sidx];
-        uint8_t* out = out_base + out_off[sidx];
-        const unsigned long long cap = out_cap[sidx];
-        if (n == RCZ_STREAM_SKIP) { if (lane == 0) { out_len[sidx] = 0; status[sidx] = RCZ_OK; if (in_used) in_used[sidx] = 0; } continue; }
-        Model m; m.init(lane);
+        if (n == RCZ_STREAM_SKIP) { out_len[sidx] = 0; status[sidx] = RCZ_OK; if (in_used) in_used[sidx] = 0; continue; }
+        Model m; m.init(row);
+        ByteIn bi; if (n) bi.init(in_base + in_off[sidx]);
+        ByteOut bo; bo.init(out_base + out_off[sidx], out_cap[sidx]);
         unsigned low = 0, hai = 0xFFFFFFFFu, code = 0, pending = 4;
-        unsigned long long p = 0, o = 0;
+        unsigned long long p = 0;
         int err = 0;
-        unsigned obuf = 0, ocnt = 0;                       // output bytes are produced one per step: lane k keeps byte k of a 32-byte group
         for (;;) {
             // feed(): ari/mod.rs:271-278 (.unwrap() => panic on a truncated stream)
             if (p + pending > n) { err = RCZ_E_MALFORMED; break; }
-            for (unsigned k = 0; k < pending; ++k) code = (code << 8) + (unsigned)in[p + k];
+            for (unsigned k = 0; k < pending; ++k) code = (code << 8) + bi.next();
             p += pending;
             const unsigned range = (hai - low) / m.total;  // ari/mod.rs:153-159 query()
             if (range == 0) { err = RCZ_E_MALFORMED; break; }
             const unsigned offset = (code - low) / range;
             if (offset >= m.total) { err = RCZ_E_MALFORMED; break; }   // table.rs:106 assert!
             unsigned v, lo, hi, bytes, nout;
-            m.find(offset, lane, v, lo, hi);
+            m.find(offset, v, lo, hi);
             range_step(low, hai, m.total, lo, hi, bytes, nout);        // ari/mod.rs:199: re-run the step to learn the shift
             pending = nout;
             if (v == 256u) break;                                      // table.rs:263-266 terminator
-            m.update(v, lane);
-            if (o >= cap) { err = RCZ_E_OUTPUT_FULL; break; }
-            if (lane == ocnt) obuf = v;
-            ++ocnt; ++o;
-            if (ocnt == 32) { out[o - 32 + lane] = (uint8_t)obuf; ocnt = 0; }
+            m.update(v);
+            if (bo.o >= bo.cap) { err = RCZ_E_OUTPUT_FULL; break; }
+            bo.put(v);
         }
-        if (lane < ocnt) out[o - ocnt + lane] = (uint8_t)obuf;
-        if (lane == 0) {
-            out_len[sidx] = o; status[sidx] = err;
-            if (in_used) in_used[sidx] = p + (err ? 0 : pending);      // incl. the bytes only finish() consumes (ari/mod.rs:289-292)
-        }
+        bo.flush();
+        out_len[sidx] = bo.o; status[sidx] = err;
+        if (in_used) in_used[sidx] = p + (err ? 0 : pending);          // incl. the bytes only finish() consumes (ari/mod.rs:289-292)
     }
 }
+
+constexpr size_t SMEM = (size_t)NT * ROW * 4;
 
 }  // namespace arik
 
@@ -185,11 +240,13 @@ ari_decode_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restric
 int rcz_ari_launch(rcz_ctx* c, bool decode, const uint8_t* din, const uint64_t* d_in_off, const uint64_t* d_in_len, uint8_t* dout,
                    const uint64_t* d_out_off, const uint64_t* d_out_cap, uint64_t* d_out_len, uint64_t* d_in_used, int32_t* d_status, size_t n) {
     if (n == 0) return RCZ_OK;
-    const unsigned grid = (unsigned)std::min<size_t>((n + 3) / 4, (size_t)c->sm_count * 16);
+    RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(arik::ari_decode_kernel, arik::SMEM));
+    RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(arik::ari_encode_kernel, arik::SMEM));
+    const unsigned grid = (unsigned)std::min<size_t>((n + arik::NT - 1) / arik::NT, (size_t)c->sm_count * 3);
     if (decode)
-        RCZ_KLAUNCH(c, arik::ari_decode_kernel, grid, arik::NT, 0, din, d_in_off, d_in_len, dout, d_out_off, d_out_cap, d_out_len, d_in_used, d_status, (unsigned)n);
+        RCZ_KLAUNCH(c, arik::ari_decode_kernel, grid, arik::NT, arik::SMEM, din, d_in_off, d_in_len, dout, d_out_off, d_out_cap, d_out_len, d_in_used, d_status, (unsigned)n);
     else
-        RCZ_KLAUNCH(c, arik::ari_encode_kernel, grid, arik::NT, 0, din, d_in_off, d_in_len, dout, d_out_off, d_out_cap, d_out_len, d_status, (unsigned)n);
+        RCZ_KLAUNCH(c, arik::ari_encode_kernel, grid, arik::NT, arik::SMEM, din, d_in_off, d_in_len, dout, d_out_off, d_out_cap, d_out_len, d_status, (unsigned)n);
     return RCZ_OK;
 }
 

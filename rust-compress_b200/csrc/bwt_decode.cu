@@ -44,6 +44,7 @@ struct Blk {
     unsigned chain0;       // global id of this block's first chain descriptor
     unsigned max_chains;
     unsigned work0;        // first index of this block's initial work items (K + 1 of them)
+    unsigned pf_off, pf_elems;   // link table of the block `prefetch distance` ahead (element offset, element count; 0 = none)
     unsigned skip;         // block rejected on the host (status already set)
     unsigned bad;          // origin supplied on the device (composed calls) and out of range: walked with origin 0, reported MALFORMED
 };
@@ -211,6 +212,16 @@ ibwt_walk_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned total_
                     slotp = scratch_base + scratch_off + (size_t)chain * cap;
                     count = 0; hops = 0;
                     active = true;
+                    // every chain start pulls its share of a LATER block's link table into L2 (sequential 256-byte pieces from HBM), so that
+                    // the random hops of that block hit L2 when the work queue reaches it
+                    if (bk.pf_elems) {
+                        const unsigned per = ((bk.pf_elems + bk.K) / (bk.K + 1) + 3u) & ~3u;            // elements per chain, 16-byte multiple
+                        const unsigned long long e0 = (unsigned long long)chain * per;
+                        if (e0 < bk.pf_elems) {
+                            const unsigned cnt = (unsigned)min((unsigned long long)per, (unsigned long long)bk.pf_elems - e0) & ~3u;
+                            if (cnt) prefetch_l2(P_base + bk.pf_off + e0, cnt * 4u);
+                        }
+                    }
                     if (chain < bk.K && cur == bk.origin) {   // no row links to `origin`: this sampled chain is unreachable,
                         Desc d; d.len = 0; d.succ = SUCC_END;  // and the origin chain (id K) walks the same rows
                         desc[chain] = d;
@@ -234,13 +245,13 @@ ibwt_walk_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned total_
                 else if (k < 12) b2 = (k == 8 ? 0u : b2) | (byte << sh);
                 else b3 = (k == 12 ? 0u : b3) | (byte << sh);
                 ++count; ++hops;
-                if ((count & 15u) == 0) *reinterpret_cast<uint4*>(slotp + count - 16) = make_uint4(b0, b1, b2, b3);
+                if ((count & 15u) == 0) __stcs(reinterpret_cast<uint4*>(slotp + count - 16), make_uint4(b0, b1, b2, b3));   // streaming: keep L2 for the tables
                 const bool at_end = (nxt == END24) || hops > nmax;
                 const bool at_sample = !at_end && (nxt & mask) == 0;
                 if (at_end || at_sample) {
                     if (count & 15u) {
                         if ((count & 15u) <= 4) { b1 = 0; b2 = 0; b3 = 0; } else if ((count & 15u) <= 8) { b2 = 0; b3 = 0; } else if ((count & 15u) <= 12) b3 = 0;
-                        *reinterpret_cast<uint4*>(slotp + (count & ~15u)) = make_uint4(b0, b1, b2, b3);
+                        __stcs(reinterpret_cast<uint4*>(slotp + (count & ~15u)), make_uint4(b0, b1, b2, b3));
                     }
                     Desc d; d.len = count; d.succ = at_end ? SUCC_END : (nxt >> slog);
                     desc[chain] = d;
@@ -461,6 +472,14 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
         cur.work += b.K + 1;
     }
     groups.push_back(cur);
+    // prefetch distance (blocks ahead) of the walk; 0 = off
+    const unsigned pf_dist = getenv("RCZ_IBWT_PREFETCH") ? (unsigned)atoi(getenv("RCZ_IBWT_PREFETCH")) : 2u;
+    if (pf_dist)
+        for (auto& g : groups)
+            for (size_t i = g.b0; i + pf_dist < g.b1; ++i) {
+                const Blk& t = blks[i + pf_dist];
+                if (!blks[i].skip && !t.skip) { blks[i].pf_off = t.p_off; blks[i].pf_elems = (t.n + 3u) & ~3u; }
+            }
     unsigned long long max_p = 0, max_scratch = 0, max_chains = 0; unsigned max_tiles = 0; size_t max_nb = 0;
     for (auto& g : groups) {
         max_p = std::max(max_p, g.p_elems); max_scratch = std::max(max_scratch, g.scratch_bytes); max_chains = std::max(max_chains, g.chains);

@@ -13,9 +13,11 @@
 // and output offset, and the last pass emits the distances.
 //
 // Decode replaces dc.rs:162-233 `decode` fed by `decode_simple`'s closure (dc.rs:236-252).  It is inherently
-// serial in the run index (every distance re-sorts the symbol list), so one warp decodes one block: ranks 0..31
-// of the (symbol, next position) list live in registers (one per lane; the slide of dc.rs:215-218 is a ballot +
-// one shuffle), ranks >= 32 in shared memory; run filling is a warp-wide store.
+// serial in the run index (every distance re-sorts the symbol list): one dependency chain per block, and what counts is
+// the length of that chain per run end.  One warp sets a block up (the sort by first position), then its lane 0 walks the
+// chain with ranks 0..3 of the (next position, symbol) list in registers — the common re-entry ranks, so the chain is a
+// handful of integer instructions with no memory access — ranks >= 4 in shared memory, and the next distance loaded one
+// run ahead.  (Round 1 spread the list over the lanes: 5 shuffles and a ballot per run end, 730 cycles; this is ~10x shorter.)
 #include "rcz_internal.h"
 #include <algorithm>
 
@@ -135,9 +137,7 @@ dc_emit_kernel(const uint8_t* __restrict__ in_base, const Blk* __restrict__ blks
 }
 
 // ---------------------------------------------------------------------------------------------- decode
-struct DecSmem { unsigned long long tail[WPB][256]; };                        // ranks >= 32 of every warp's list
-
-__device__ __forceinline__ unsigned long long ent_pack(unsigned long long next, unsigned sym) { return (next << 8) | sym; }
+struct DecSmem { unsigned nx[WPB][256]; uint8_t sy[WPB][256]; };              // the (next position, symbol) list of every warp's block, by rank
 
 __global__ void __launch_bounds__(NT)
 dc_decode_kernel(const uint32_t* __restrict__ in_base, const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ in_len,
@@ -145,7 +145,6 @@ dc_decode_kernel(const uint32_t* __restrict__ in_base, const uint64_t* __restric
                  int32_t* __restrict__ status, unsigned nblocks) {
     __shared__ DecSmem sm;
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    unsigned long long* tail = sm.tail[w];
     for (unsigned b = blockIdx.x * WPB + w; b < nblocks; b += gridDim.x * WPB) {
         const uint32_t* in = in_base + in_off[b];
         const unsigned long long len = in_len[b], n = n_arr[b];
@@ -173,74 +172,69 @@ dc_decode_kernel(const uint32_t* __restrict__ in_base, const uint64_t* __restric
             }
         }
         __syncwarp();
-        unsigned long long my = ~0ull;                                        // list entry of rank == lane
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            if (init[k] < n) tail[rk[k]] = ent_pack(init[k], lane * 8 + k);   // ranks are a permutation of 0..A-1
-        __syncwarp();
-        if (lane < A) my = tail[lane];
+            if (init[k] < n) { sm.nx[w][rk[k]] = init[k]; sm.sy[w][rk[k]] = (uint8_t)(lane * 8 + k); }   // ranks are a permutation of 0..A-1
         __syncwarp();
         if (A <= 1) {                                                         // dc.rs:180-187
-            const unsigned sym = A ? (unsigned)(__shfl_sync(RCZ_FULL, my, 0) & 255u) : 0u;
+            const unsigned sym = A ? (unsigned)sm.sy[w][0] : 0u;
             for (unsigned long long i = lane; i < n; i += 32) out[i] = (uint8_t)sym;
             if (lane == 0) status[b] = RCZ_OK;
+            __syncwarp();
             continue;
         }
-        // ---- dc.rs:199-229
-        unsigned long long i = 0, di = 0;
+        // ---- dc.rs:199-229.  Every distance re-sorts the list, so the loop is one dependency chain per block: lane 0 walks it with
+        // ranks 0..3 of the list in registers (most run ends of a BWT column re-enter within the first few ranks: no memory access on the
+        // chain), ranks >= 4 in shared memory; the next distance is loaded one run ahead.
         int err = 0;
-        unsigned dreg = 0; unsigned long long dbase = ~0ull;                  // 32 distances at a time
-        while (i < n) {
-            const unsigned long long e0 = __shfl_sync(RCZ_FULL, my, 0), e1 = __shfl_sync(RCZ_FULL, my, 1);
-            const unsigned sym = (unsigned)(e0 & 255u);
-            const unsigned long long stop = e1 >> 8;
-            if (stop > n) { err = RCZ_E_MALFORMED; break; }                   // output[i] index panic
-            for (unsigned long long k = i + lane; k < stop; k += 32) out[k] = (uint8_t)sym;
-            if (stop > i) i = stop;
-            if (di >= ndist) { err = RCZ_E_UNEXPECTED_EOF; break; }           // dc.rs:245-246
-            if ((di & ~31ull) != dbase) { dbase = di & ~31ull; dreg = dbase + lane < ndist ? dist[dbase + lane] : 0u; }
-            const unsigned long long future = stop + __shfl_sync(RCZ_FULL, dreg, (int)(di & 31u));
-            ++di;
-            if (future > n) { err = RCZ_E_MALFORMED; break; }                 // dc.rs:213 assert!
-            // rank = 1 + #{leading r in [1, A) : future + r > next(L[r])}  (dc.rs:215-218)
-            // (the reference stops at the first rank that fails the test: count LEADING hits, not all hits)
-            const unsigned bal = __ballot_sync(RCZ_FULL, lane >= 1 && lane < A && future + lane > (my >> 8)) >> 1;
-            unsigned rank = 1 + ((unsigned)__ffs((int)~bal) - 1u);            // bal has at most 31 bits set
-            if (rank == 32 && A > 32) {
-                for (unsigned r0 = 32; r0 < A; r0 += 32) {
-                    const unsigned r = r0 + lane;
-                    const unsigned bb = __ballot_sync(RCZ_FULL, r < A && future + r > (tail[r] >> 8));
-                    if (bb == RCZ_FULL) { rank += 32; continue; }
-                    rank += (unsigned)__ffs((int)~bb) - 1u;
-                    break;
+        if (lane == 0) {
+            unsigned* nx = sm.nx[w]; uint8_t* sy = sm.sy[w];
+            const unsigned N = (unsigned)n;
+            unsigned n0 = nx[0], n1 = nx[1], n2 = A > 2 ? nx[2] : 0u, n3 = A > 3 ? nx[3] : 0u;
+            unsigned s0 = sy[0], s1 = sy[1], s2 = A > 2 ? sy[2] : 0u, s3 = A > 3 ? sy[3] : 0u;
+            unsigned i = 0;
+            unsigned long long di = 0;
+            unsigned dnext = ndist ? __ldg(dist) : 0u;
+            while (i < N) {
+                const unsigned sym = s0, stop = n1;
+                if (stop > N) { err = RCZ_E_MALFORMED; break; }               // output[i] index panic
+                for (unsigned k = i; k < stop; ++k) out[k] = (uint8_t)sym;
+                if (stop > i) i = stop;
+                if (di >= ndist) { err = RCZ_E_UNEXPECTED_EOF; break; }       // dc.rs:245-246
+                const unsigned d = dnext;
+                ++di;
+                if (di < ndist) dnext = __ldg(dist + di);
+                if (d > N - stop) { err = RCZ_E_MALFORMED; break; }           // dc.rs:213 assert!(future <= n)
+                const unsigned future = stop + d;
+                // rank = 1 + #{leading r in [1, A) : future + r > next(list[r])}   (dc.rs:215-218)
+                const bool c1 = future + 1u > n1;                              // A >= 2
+                const bool c2 = c1 && A > 2u && future + 2u > n2;
+                const bool c3 = c2 && A > 3u && future + 3u > n3;
+                if (!c3) {
+                    if (!c1) { n0 = future; }                                  // rank 1: stays in front
+                    else if (!c2) { n0 = n1; s0 = s1; n1 = future + 1u; s1 = sym; }
+                    else { n0 = n1; s0 = s1; n1 = n2; s1 = s2; n2 = future + 2u; s2 = sym; }
+                } else {
+                    unsigned rank = 4;
+                    while (rank < A && future + rank > nx[rank]) ++rank;
+                    n0 = n1; s0 = s1; n1 = n2; s1 = s2; n2 = n3; s2 = s3;
+                    if (rank == 4) { n3 = future + 3u; s3 = sym; }
+                    else {
+                        n3 = nx[4]; s3 = sy[4];
+                        for (unsigned r = 4; r + 1 < rank; ++r) { nx[r] = nx[r + 1]; sy[r] = sy[r + 1]; }
+                        nx[rank - 1] = future + rank - 1u; sy[rank - 1] = (uint8_t)sym;
+                    }
                 }
             }
-            const unsigned long long fresh = ent_pack(future + rank - 1, sym);
-            const unsigned long long up = __shfl_down_sync(RCZ_FULL, my, 1);
-            if (rank <= 32) {
-                if (lane + 1 < rank) my = up; else if (lane + 1 == rank) my = fresh;
-            } else {
-                const unsigned long long v32 = tail[32];
-                my = lane < 31 ? up : v32;
-                __syncwarp();                                                 // tail[32] is read before anyone rewrites it
-                for (unsigned r0 = 32; r0 + 1 < rank; r0 += 32) {             // tail[r] = tail[r+1] for r in [32, rank-1)
-                    const unsigned r = r0 + lane;
-                    const unsigned long long t = (r + 1 < rank) ? tail[r + 1] : 0ull;
-                    __syncwarp();
-                    if (r + 1 < rank) tail[r] = t;
-                    __syncwarp();
-                }
-                if (lane == 0) tail[rank - 1] = fresh;
-                __syncwarp();
+            if (!err) {                                                       // dc.rs:230-231 assert_eq!
+                nx[0] = n0; nx[1] = n1; if (A > 2) nx[2] = n2; if (A > 3) nx[3] = n3;
+                bool bad = i != N;
+                for (unsigned r = 0; r < A; ++r) bad |= nx[r] < N || nx[r] >= N + A;
+                if (bad) err = RCZ_E_MALFORMED;
             }
-        }
-        if (!err) {                                                           // dc.rs:230-231 assert_eq!
-            bool bad = lane < A && lane < 32 && ((my >> 8) < n || (my >> 8) >= n + A);
-            for (unsigned r = 32 + lane; r < A; r += 32) bad |= (tail[r] >> 8) < n || (tail[r] >> 8) >= n + A;
-            if (__any_sync(RCZ_FULL, bad) || i != n) err = RCZ_E_MALFORMED;
+            status[b] = err;
         }
         __syncwarp();
-        if (lane == 0) status[b] = err;
     }
 }
 
