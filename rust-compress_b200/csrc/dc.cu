@@ -14,10 +14,11 @@
 //
 // Decode replaces dc.rs:162-233 `decode` fed by `decode_simple`'s closure (dc.rs:236-252).  It is inherently
 // serial in the run index (every distance re-sorts the symbol list): one dependency chain per block, and what counts is
-// the length of that chain per run end.  One warp sets a block up (the sort by first position), then its lane 0 walks the
-// chain with ranks 0..3 of the (next position, symbol) list in registers — the common re-entry ranks, so the chain is a
-// handful of integer instructions with no memory access — ranks >= 4 in shared memory, and the next distance loaded one
-// run ahead.  (Round 1 spread the list over the lanes: 5 shuffles and a ballot per run end, 730 cycles; this is ~10x shorter.)
+// the length of that chain per run end.  One warp decodes one block: lane r holds rank r of the (next position, symbol)
+// list in two 32-bit registers, so the slide of dc.rs:215-218 costs one ballot + one shuffle at any rank (a BWT column of
+// hexdump text re-enters at rank ~14 on average: a scalar loop with the top four ranks in registers was measured 3x
+// slower than the warp form); ranks >= 32 live in shared memory; the distances arrive 32 at a time, the next group in
+// flight while one is used.
 #include "rcz_internal.h"
 #include <algorithm>
 
@@ -183,58 +184,68 @@ dc_decode_kernel(const uint32_t* __restrict__ in_base, const uint64_t* __restric
             __syncwarp();
             continue;
         }
-        // ---- dc.rs:199-229.  Every distance re-sorts the list, so the loop is one dependency chain per block: lane 0 walks it with
-        // ranks 0..3 of the list in registers (most run ends of a BWT column re-enter within the first few ranks: no memory access on the
-        // chain), ranks >= 4 in shared memory; the next distance is loaded one run ahead.
+        // ---- dc.rs:199-229.  Every distance re-sorts the list, so the loop is one dependency chain per block and what counts is its
+        // length per run end.  Lane r holds rank r of the list (two 32-bit registers); the slide of dc.rs:215-218 is one ballot + one
+        // shuffle whatever the rank (BWT columns of text re-enter at rank ~14 on average, far beyond what a scalar loop keeps in
+        // registers); ranks >= 32 live in shared memory.  All positions are 32-bit (n < 2^31).
+        const unsigned N = (unsigned)n;
+        unsigned* tnx = sm.nx[w]; uint8_t* tsy = sm.sy[w];
+        unsigned nx = lane < A ? tnx[lane] : 0xFFFFFFFFu, sy = lane < A ? (unsigned)tsy[lane] : 0u;
+        __syncwarp();
         int err = 0;
-        if (lane == 0) {
-            unsigned* nx = sm.nx[w]; uint8_t* sy = sm.sy[w];
-            const unsigned N = (unsigned)n;
-            unsigned n0 = nx[0], n1 = nx[1], n2 = A > 2 ? nx[2] : 0u, n3 = A > 3 ? nx[3] : 0u;
-            unsigned s0 = sy[0], s1 = sy[1], s2 = A > 2 ? sy[2] : 0u, s3 = A > 3 ? sy[3] : 0u;
-            unsigned i = 0;
-            unsigned long long di = 0;
-            unsigned dnext = ndist ? __ldg(dist) : 0u;
-            while (i < N) {
-                const unsigned sym = s0, stop = n1;
-                if (stop > N) { err = RCZ_E_MALFORMED; break; }               // output[i] index panic
-                for (unsigned k = i; k < stop; ++k) out[k] = (uint8_t)sym;
-                if (stop > i) i = stop;
-                if (di >= ndist) { err = RCZ_E_UNEXPECTED_EOF; break; }       // dc.rs:245-246
-                const unsigned d = dnext;
-                ++di;
-                if (di < ndist) dnext = __ldg(dist + di);
-                if (d > N - stop) { err = RCZ_E_MALFORMED; break; }           // dc.rs:213 assert!(future <= n)
-                const unsigned future = stop + d;
-                // rank = 1 + #{leading r in [1, A) : future + r > next(list[r])}   (dc.rs:215-218)
-                const bool c1 = future + 1u > n1;                              // A >= 2
-                const bool c2 = c1 && A > 2u && future + 2u > n2;
-                const bool c3 = c2 && A > 3u && future + 3u > n3;
-                if (!c3) {
-                    if (!c1) { n0 = future; }                                  // rank 1: stays in front
-                    else if (!c2) { n0 = n1; s0 = s1; n1 = future + 1u; s1 = sym; }
-                    else { n0 = n1; s0 = s1; n1 = n2; s1 = s2; n2 = future + 2u; s2 = sym; }
-                } else {
-                    unsigned rank = 4;
-                    while (rank < A && future + rank > nx[rank]) ++rank;
-                    n0 = n1; s0 = s1; n1 = n2; s1 = s2; n2 = n3; s2 = s3;
-                    if (rank == 4) { n3 = future + 3u; s3 = sym; }
-                    else {
-                        n3 = nx[4]; s3 = sy[4];
-                        for (unsigned r = 4; r + 1 < rank; ++r) { nx[r] = nx[r + 1]; sy[r] = sy[r + 1]; }
-                        nx[rank - 1] = future + rank - 1u; sy[rank - 1] = (uint8_t)sym;
-                    }
+        unsigned i = 0;
+        unsigned long long di = 0;
+        unsigned dreg = lane < ndist ? __ldg(dist + lane) : 0u;               // distances [32g, 32g + 32) of the current group, one per lane
+        unsigned dnxt = 32ull + lane < ndist ? __ldg(dist + 32 + lane) : 0u;  // the next group, in flight while this one is used
+        while (i < N) {
+            const unsigned stop = __shfl_sync(RCZ_FULL, nx, 1), sym = __shfl_sync(RCZ_FULL, sy, 0);
+            const unsigned up_nx = __shfl_down_sync(RCZ_FULL, nx, 1), up_sy = __shfl_down_sync(RCZ_FULL, sy, 1);
+            if (stop > N) { err = RCZ_E_MALFORMED; break; }                   // output[i] index panic
+            for (unsigned k = i + lane; k < stop; k += 32) out[k] = (uint8_t)sym;
+            if (stop > i) i = stop;
+            if (di >= ndist) { err = RCZ_E_UNEXPECTED_EOF; break; }           // dc.rs:245-246
+            const unsigned d = __shfl_sync(RCZ_FULL, dreg, (int)(di & 31u));
+            ++di;
+            if ((di & 31u) == 0) { dreg = dnxt; dnxt = di + 32 + lane < ndist ? __ldg(dist + di + 32 + lane) : 0u; }
+            if (d > N - stop) { err = RCZ_E_MALFORMED; break; }               // dc.rs:213 assert!(future <= n)
+            const unsigned future = stop + d;
+            // rank = 1 + #{leading r in [1, A) : future + r > next(list[r])}  (dc.rs:215-218; the reference stops at the first rank that
+            // fails the test: count LEADING hits, not all hits)
+            const unsigned bal = __ballot_sync(RCZ_FULL, lane >= 1 && lane < A && future + lane > nx) >> 1;
+            unsigned rank = (unsigned)__ffs((int)~bal);                       // 1 + leading hits; bal has at most 31 bits set
+            if (rank == 32 && A > 32) {
+                for (unsigned r0 = 32; r0 < A; r0 += 32) {
+                    const unsigned r = r0 + lane;
+                    const unsigned bb = __ballot_sync(RCZ_FULL, r < A && future + r > tnx[r]);
+                    if (bb == RCZ_FULL) { rank += 32; continue; }
+                    rank += (unsigned)__ffs((int)~bb) - 1u;
+                    break;
                 }
             }
-            if (!err) {                                                       // dc.rs:230-231 assert_eq!
-                nx[0] = n0; nx[1] = n1; if (A > 2) nx[2] = n2; if (A > 3) nx[3] = n3;
-                bool bad = i != N;
-                for (unsigned r = 0; r < A; ++r) bad |= nx[r] < N || nx[r] >= N + A;
-                if (bad) err = RCZ_E_MALFORMED;
+            if (rank <= 32) {
+                if (lane + 1 < rank) { nx = up_nx; sy = up_sy; } else if (lane + 1 == rank) { nx = future + rank - 1u; sy = sym; }
+            } else {
+                const unsigned v32n = tnx[32], v32s = tsy[32];
+                if (lane < 31) { nx = up_nx; sy = up_sy; } else { nx = v32n; sy = v32s; }
+                __syncwarp();                                                 // entry 32 is read before anyone rewrites it
+                for (unsigned r0 = 32; r0 + 1 < rank; r0 += 32) {             // tail[r] = tail[r+1] for r in [32, rank-1)
+                    const unsigned r = r0 + lane;
+                    const unsigned tn = (r + 1 < rank) ? tnx[r + 1] : 0u, ts = (r + 1 < rank) ? (unsigned)tsy[r + 1] : 0u;
+                    __syncwarp();
+                    if (r + 1 < rank) { tnx[r] = tn; tsy[r] = (uint8_t)ts; }
+                    __syncwarp();
+                }
+                if (lane == 0) { tnx[rank - 1] = future + rank - 1u; tsy[rank - 1] = (uint8_t)sym; }
+                __syncwarp();
             }
-            status[b] = err;
+        }
+        if (!err) {                                                           // dc.rs:230-231 assert_eq!
+            bool bad = lane < A && (nx < N || nx >= N + A);
+            for (unsigned r = 32 + lane; r < A; r += 32) bad |= tnx[r] < N || tnx[r] >= N + A;
+            if (__any_sync(RCZ_FULL, bad) || i != N) err = RCZ_E_MALFORMED;
         }
         __syncwarp();
+        if (lane == 0) status[b] = err;
     }
 }
 

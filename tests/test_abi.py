@@ -20,6 +20,21 @@ def test_header_and_binding_agree():
     assert _declared() == sorted(abi.SIGNATURES)
 
 
+def test_rust_shim_declares_every_symbol():
+    """rust/rcz_sys.rs (uncompiled: no rustc in this image) must carry one `extern "C"` declaration per function of rcz.h, with the
+    same number of parameters."""
+    rs = open(os.path.join(ROOT, "rust", "rcz_sys.rs")).read()
+    ext = rs[rs.index('extern "C" {'): rs.index("\n}\n", rs.index('extern "C" {'))]
+    decl = dict((m.group(1), m.group(2)) for m in re.finditer(r"pub fn (rcz_[a-z0-9_]+)\(([^)]*)\)", ext))
+    assert sorted(decl) == _declared()
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "rcz.h")).read(), flags=re.S)
+    for name, args in decl.items():
+        m = re.search(r"\b%s\s*\(([^)]*)\)" % name, hdr)
+        c_args = [a for a in m.group(1).split(",") if a.strip() and a.strip() != "void"]
+        rs_args = [a for a in args.split(",") if a.strip()]
+        assert len(c_args) == len(rs_args), name
+
+
 def test_librcz_exports_every_declared_symbol():
     build = importlib.import_module("rust-compress_b200.build")
     lib = C.CDLL(build.build())
