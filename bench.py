@@ -509,7 +509,9 @@ def leg_bwt(env, args):
     d_back = torch.zeros(UNIT * nb, dtype=torch.uint8, device="cuda")
     origin, st = ctx.bwt_encode_blocks(d_raw, off, n, d_l, off)
     assert (st == 0).all()
-    enc = lambda: ctx.bwt_encode_blocks(d_raw, off, n, d_l, off, async_=True)          # noqa: E731
+    # RCZ_MEM_DEVICE (not _ASYNC): the call reads one counter per doubling round and stops as soon as every block is sorted; the blind
+    # _ASYNC form would enqueue all ~20 rounds (1,950 launches, most of them empty) for data that resolves in round 0
+    enc = lambda: ctx.bwt_encode_blocks(d_raw, off, n, d_l, off)                       # noqa: E731
     dec = lambda: ctx.bwt_decode_blocks(d_l, off, n, origin, d_back, off, async_=True)  # noqa: E731
     enc(); torch.cuda.synchronize()
     t0 = time.perf_counter(); enc(); torch.cuda.synchronize(); est_e = (time.perf_counter() - t0) * 1e3

@@ -116,13 +116,21 @@ ibwt_scatter_kernel(const uint8_t* __restrict__ in_base, const Blk* __restrict__
 
     for (unsigned i = tid; i < (NT_TILE / 32) * 256; i += NT_TILE) (&sm.wcnt[0][0])[i] = 0;
     __syncthreads();
-    // pass A: per-warp symbol counts
+    // pass A: per-warp symbol counts, and for every symbol its rank among the equal symbols of the warp's 1024-symbol span
+    // (count before this group of 32 + rank inside the group: 8 ballots, done ONCE and kept in registers, two ranks per register)
+    unsigned rb[WSPAN / 64];
+#pragma unroll
     for (unsigned g = 0; g < WSPAN / 32; ++g) {
         const unsigned i = lo + w * WSPAN + g * 32 + lane;
         const bool valid = i < hi;
         const unsigned s = valid ? (unsigned)L[i] : 0u;
         const unsigned m = warp_match_u8(s, valid);
-        if (valid && (m & ((1u << lane) - 1u)) == 0) sm.wcnt[w][s] += (unsigned)__popc(m);   // one add per distinct symbol
+        const unsigned r = __popc(m & ((1u << lane) - 1u));
+        unsigned old = 0;
+        if (valid && r == 0) { old = sm.wcnt[w][s]; sm.wcnt[w][s] = old + (unsigned)__popc(m); }   // one add per distinct symbol
+        old = __shfl_sync(RCZ_FULL, old, m ? __ffs((int)m) - 1 : 0);
+        const unsigned v = old + r;                                           // < 1024 + 32
+        if (g & 1) rb[g >> 1] |= v << 16; else rb[g >> 1] = v;
         __syncwarp();
     }
     __syncthreads();
@@ -140,19 +148,15 @@ ibwt_scatter_kernel(const uint8_t* __restrict__ in_base, const Blk* __restrict__
         sm.gbase[tid] = cbase[(size_t)bi * 256 + tid] + tile_hist[(size_t)tile * 256 + tid] - sb;
     }
     __syncthreads();
-    // pass C: stable ranking, 32 symbols at a time per warp (warp_match_u8 groups equal symbols)
+    // pass C: place (the symbols come back from L1; no ballots, no warp-level ordering left)
+#pragma unroll
     for (unsigned g = 0; g < WSPAN / 32; ++g) {
         const unsigned i = lo + w * WSPAN + g * 32 + lane;
-        const bool valid = i < hi;
-        const unsigned s = valid ? (unsigned)L[i] : 0u;
-        const unsigned m = warp_match_u8(s, valid);
-        const unsigned r = __popc(m & ((1u << lane) - 1u));
-        unsigned base = 0;
-        if (valid) base = sm.wcnt[w][s];
-        __syncwarp();
-        if (valid && r == 0) sm.wcnt[w][s] = base + __popc(m);
-        __syncwarp();
-        if (valid) sm.sorted[sm.symbase[s] + base + r] = (i << 8) | s;
+        if (i < hi) {
+            const unsigned s = (unsigned)L[i];
+            const unsigned v = (g & 1) ? rb[g >> 1] >> 16 : rb[g >> 1] & 0xffffu;
+            sm.sorted[sm.symbase[s] + sm.wcnt[w][s] + v] = (i << 8) | s;
+        }
     }
     __syncthreads();
     // pass D: write out; runs of equal symbols are contiguous in P. origin-first rule of bwt/mod.rs:230-236.
@@ -186,6 +190,9 @@ ibwt_walk_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned total_
     unsigned cur = 0, count = 0, chain = 0, mask = 0, slog = 0, cap = 0, hops = 0, nmax = 0, maxch = 0;
     unsigned long long scratch_off = 0;
     unsigned b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+    // block of the lane's previous work item: consecutive tickets almost always stay inside it, so the block table is searched
+    // (and the dozen per-block values reloaded) only when a ticket leaves [w_lo, w_hi)
+    unsigned w_lo = 1, w_hi = 0, bK = 0, borigin = 0, pf_off = 0, pf_elems = 0;
 
     for (;;) {
         // ---- refill idle lanes with new chains (warp-aggregated ticket)
@@ -199,31 +206,34 @@ ibwt_walk_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned total_
                 const unsigned wi = base + __popc(need & ((1u << lane) - 1u));
                 if (wi >= total_work) done = true;
                 else {
-                    unsigned lo = 0, hi = nblocks;            // last block with work0 <= wi
-                    while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (blks[mid].work0 <= wi) lo = mid; else hi = mid; }
-                    const Blk bk = blks[lo];
-                    chain = wi - bk.work0;
-                    P = P_base + bk.p_off;
-                    desc = desc_base + bk.chain0;
-                    ctr = chain_ctr + lo;
-                    scratch_off = bk.scratch_off;
-                    slog = bk.stride_log2; mask = (1u << slog) - 1u; cap = bk.cap; nmax = bk.n; maxch = bk.max_chains;
-                    cur = chain < bk.K ? (chain << slog) : bk.origin;
+                    if (wi < w_lo || wi >= w_hi) {
+                        unsigned lo = 0, hi = nblocks;            // last block with work0 <= wi
+                        while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (blks[mid].work0 <= wi) lo = mid; else hi = mid; }
+                        const Blk bk = blks[lo];
+                        w_lo = bk.work0; w_hi = bk.work0 + bk.K + 1; bK = bk.K; borigin = bk.origin;
+                        P = P_base + bk.p_off;
+                        desc = desc_base + bk.chain0;
+                        ctr = chain_ctr + lo;
+                        scratch_off = bk.scratch_off;
+                        slog = bk.stride_log2; mask = (1u << slog) - 1u; cap = bk.cap; nmax = bk.n; maxch = bk.max_chains;
+                        pf_off = bk.pf_off; pf_elems = bk.pf_elems;
+                    }
+                    chain = wi - w_lo;
+                    cur = chain < bK ? (chain << slog) : borigin;
                     slotp = scratch_base + scratch_off + (size_t)chain * cap;
                     count = 0; hops = 0;
                     active = true;
-                    // every chain start pulls its share of a LATER block's link table into L2 (sequential 256-byte pieces from HBM), so that
-                    // the random hops of that block hit L2 when the work queue reaches it
-                    if (bk.pf_elems) {
-                        const unsigned per = ((bk.pf_elems + bk.K) / (bk.K + 1) + 3u) & ~3u;            // elements per chain, 16-byte multiple
+                    // (optional) every chain start pulls its share of a LATER block's link table into L2
+                    if (pf_elems) {
+                        const unsigned per = ((pf_elems + bK) / (bK + 1) + 3u) & ~3u;                   // elements per chain, 16-byte multiple
                         const unsigned long long e0 = (unsigned long long)chain * per;
-                        if (e0 < bk.pf_elems) {
-                            const unsigned cnt = (unsigned)min((unsigned long long)per, (unsigned long long)bk.pf_elems - e0) & ~3u;
-                            if (cnt) prefetch_l2(P_base + bk.pf_off + e0, cnt * 4u);
+                        if (e0 < pf_elems) {
+                            const unsigned cnt = (unsigned)min((unsigned long long)per, (unsigned long long)pf_elems - e0) & ~3u;
+                            if (cnt) prefetch_l2(P_base + pf_off + e0, cnt * 4u);
                         }
                     }
-                    if (chain < bk.K && cur == bk.origin) {   // no row links to `origin`: this sampled chain is unreachable,
-                        Desc d; d.len = 0; d.succ = SUCC_END;  // and the origin chain (id K) walks the same rows
+                    if (chain < bK && cur == borigin) {            // no row links to `origin`: this sampled chain is unreachable,
+                        Desc d; d.len = 0; d.succ = SUCC_END;      // and the origin chain (id K) walks the same rows
                         desc[chain] = d;
                         active = false;
                     }
@@ -233,7 +243,7 @@ ibwt_walk_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned total_
         if (__all_sync(RCZ_FULL, done)) break;
         // ---- a burst of hops between refill checks
 #pragma unroll 1
-        for (int it = 0; it < 16; ++it) {
+        for (int it = 0; it < 8; ++it) {
             if (active) {
                 const unsigned e = __ldcg(P + cur);             // L2 only: an L1 miss would pull the whole 128-byte line for one 4-byte entry
                 const unsigned byte = e & 255u, nxt = e >> 8;
@@ -274,16 +284,15 @@ ibwt_walk_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned total_
 }
 
 // ------------------------------------------------------------------------------------------ E: rank chains
-// Sampled list ranking once more, one level up (one CTA per block): every 16th chain descriptor (and the origin chain) is a
+// Sampled list ranking once more, one level up (one CTA per block): every 2^HEAD_LOG2-th chain descriptor (and the origin chain) is a
 // HEAD; a head walks the chain list to the next head summing lengths (pass 1), the <= nch/16 + 1 heads are ranked by Wyllie
 // pointer jumping in shared memory ((distance to END << 32) | next head), and a second walk hands every chain its output
 // offset (pass 2).  Work is O(nch) instead of O(nch log nch); the descriptors (8 B each) stay L2 resident.
-constexpr unsigned HEAD_LOG2 = 4;
 constexpr unsigned RANK_MAX_HEADS = 24576;                    // 8 B each in shared memory
 
 __global__ void __launch_bounds__(RANK_NT, 1)
 ibwt_rank_kernel(const Blk* __restrict__ blks, const Desc* __restrict__ desc_base, const unsigned* __restrict__ chain_ctr,
-                 unsigned* __restrict__ chain_off, uint64_t* __restrict__ out_len, int32_t* __restrict__ status) {
+                 unsigned* __restrict__ chain_off, uint64_t* __restrict__ out_len, int32_t* __restrict__ status, unsigned HEAD_LOG2) {
     RCZ_DYN_SMEM(raw);
     unsigned long long* node = reinterpret_cast<unsigned long long*>(raw);
     volatile unsigned long long* vnode = node;
@@ -294,7 +303,7 @@ ibwt_rank_kernel(const Blk* __restrict__ blks, const Desc* __restrict__ desc_bas
     unsigned* coff = chain_off + bk.chain0;
     unsigned nch = chain_ctr[b];
     if (nch > bk.max_chains) nch = bk.max_chains;
-    const unsigned nreg = (nch + (1u << HEAD_LOG2) - 1) >> HEAD_LOG2;   // heads at chain ids 0, 16, 32, ...
+    const unsigned nreg = (nch + (1u << HEAD_LOG2) - 1) >> HEAD_LOG2;   // heads at chain ids 0, 2^HEAD_LOG2, ...
     const unsigned H = nreg + 1;                                        // + the origin chain (id K); SENT = H
     const unsigned SENT = H, mask = (1u << HEAD_LOG2) - 1u, K = bk.K;
     for (unsigned i = tid; i < nch; i += RANK_NT) coff[i] = OFF_INVALID;
@@ -358,12 +367,12 @@ ibwt_rank_kernel(const Blk* __restrict__ blks, const Desc* __restrict__ desc_bas
 }
 
 // ------------------------------------------------------------------------------------------ F: compact
-// blockIdx.y = block, one warp per chain: lane l moves bytes [4l, 4l+4) of every 128-byte piece (aligned 4-byte loads from
-// the chain slot, byte stores to the arbitrarily aligned final position; neighbouring lanes hit neighbouring bytes)
+// blockIdx.y = block, one THREAD per chain (chains are a few dozen bytes with dense sampling): aligned 16-byte loads from the chain's
+// slot, then head bytes up to the destination's 4-byte boundary, 32-bit words put together with funnel shifts, tail bytes.
 __global__ void __launch_bounds__(256)
 ibwt_compact_kernel(const Blk* __restrict__ blks, const uint8_t* __restrict__ scratch_base, const Desc* __restrict__ desc_base,
                     const unsigned* __restrict__ chain_ctr, const unsigned* __restrict__ chain_off, uint8_t* __restrict__ out_base) {
-    const unsigned lane = threadIdx.x & 31, wpb = blockDim.x >> 5, b = blockIdx.y;
+    const unsigned b = blockIdx.y;
     const Blk bk = blks[b];
     if (bk.skip) return;
     unsigned nch = chain_ctr[b];
@@ -371,18 +380,29 @@ ibwt_compact_kernel(const Blk* __restrict__ blks, const uint8_t* __restrict__ sc
     const Desc* desc = desc_base + bk.chain0;
     const unsigned* coff = chain_off + bk.chain0;
     uint8_t* out = out_base + bk.out_off;
-    for (unsigned g = blockIdx.x * wpb + (threadIdx.x >> 5); g < nch; g += gridDim.x * wpb) {
+    for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < nch; g += gridDim.x * blockDim.x) {
         const unsigned off = coff[g];
         if (off == OFF_INVALID) continue;
         const unsigned len = desc[g].len;
         const uint8_t* src = scratch_base + bk.scratch_off + (size_t)g * bk.cap;
         uint8_t* dst = out + off;
-        for (unsigned base = 4 * lane; base < len; base += 128) {
-            const unsigned v = *reinterpret_cast<const unsigned*>(src + base);
-            dst[base] = (uint8_t)v;
-            if (base + 1 < len) dst[base + 1] = (uint8_t)(v >> 8);
-            if (base + 2 < len) dst[base + 2] = (uint8_t)(v >> 16);
-            if (base + 3 < len) dst[base + 3] = (uint8_t)(v >> 24);
+        for (unsigned base = 0; base < len; base += 16) {                       // 16 source bytes -> dst + base
+            const uint4 q = __ldcs(reinterpret_cast<const uint4*>(src + base));  // read once: streaming
+            const unsigned m = len - base < 16u ? len - base : 16u;
+            const unsigned wv[5] = {q.x, q.y, q.z, q.w, 0u};
+            uint8_t* d = dst + base;
+            const unsigned head = (unsigned)((4u - ((uintptr_t)d & 3u)) & 3u);
+            if (m >= 4u + head) {
+                unsigned done = 0;
+                for (; done < head; ++done) d[done] = (uint8_t)(q.x >> (8u * done));
+                const unsigned sh = 8u * head;                                   // words from byte `head` on: (w[i] >> sh) | (w[i+1] << (32 - sh))
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (done + 4u <= m) { *reinterpret_cast<unsigned*>(d + done) = __funnelshift_r(wv[i], wv[i + 1], sh); done += 4; }
+                for (; done < m; ++done) d[done] = (uint8_t)(wv[done >> 2] >> (8u * (done & 3u)));
+            } else {
+                for (unsigned k = 0; k < m; ++k) d[k] = (uint8_t)(wv[k >> 2] >> (8u * (k & 3u)));
+            }
         }
     }
 }
@@ -431,7 +451,7 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
     // n dependent random hops per block hit the 126 MB L2 instead of HBM (measured with tools/micro/gather_bench.cu:
     // ~285 G hops/s for a <= 64 MiB working set vs ~73 G hops/s from HBM).  All offsets in Blk are group-relative and the
     // workspaces are reused by every group.  RCZ_IBWT_* are tuning overrides for tools/ibwt_sweep.sh.
-    const unsigned tune_slog = getenv("RCZ_IBWT_SLOG") ? (unsigned)atoi(getenv("RCZ_IBWT_SLOG")) : 6u;
+    const unsigned tune_slog = getenv("RCZ_IBWT_SLOG") ? (unsigned)atoi(getenv("RCZ_IBWT_SLOG")) : 4u;
     const unsigned tune_ctas = getenv("RCZ_IBWT_WALK_CTAS") ? (unsigned)atoi(getenv("RCZ_IBWT_WALK_CTAS")) : 4u;
     const unsigned long long group_syms = getenv("RCZ_IBWT_GROUP_SYMS") ? strtoull(getenv("RCZ_IBWT_GROUP_SYMS"), nullptr, 10) : (1ull << 30);
     struct Group { size_t b0, b1; unsigned tile0_abs, ntiles; unsigned long long p_elems, scratch_bytes, chains, work; };
@@ -440,6 +460,7 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
     std::vector<unsigned> tile2blk;
     std::vector<Group> groups;
     Group cur{0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned hlog = 4;
     for (size_t i = 0; i < nblocks; ++i) {
         const unsigned long long n = n_arr[i];
         if (cur.b1 > cur.b0 && cur.p_elems && cur.p_elems + n > group_syms) {
@@ -457,12 +478,12 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
         if (n > MAX_N) { b.skip = 1; hstatus[i] = RCZ_E_UNSUPPORTED; continue; }
         b.n = (unsigned)n; b.origin = origin_dev ? 0u : origin[i];
         unsigned slog = tune_slog;
-        while ((n >> slog) > 65536) ++slog;                   // keep <= 64 Ki sampled rows per block
+        while ((n >> slog) > (1u << 19)) ++slog;              // keep <= 512 Ki sampled rows per block
         b.stride_log2 = slog;
         b.K = (unsigned)((n + (1ull << slog) - 1) >> slog);
-        b.cap = 2u << slog;
+        b.cap = std::max(32u, 4u << slog);                    // bytes per chain slot: P(chain longer than 4 strides) = e^-4
         b.max_chains = b.K + 1 + (unsigned)(n / b.cap) + 1;   // every row is walked at most once => <= n/cap continuations
-        if ((b.max_chains >> HEAD_LOG2) + 2 > RANK_MAX_HEADS) { b.skip = 1; hstatus[i] = RCZ_E_UNSUPPORTED; continue; }
+        while (((b.max_chains >> hlog) + 3) > RANK_MAX_HEADS) ++hlog;   // one head sampling for the whole call
         b.ntiles = (unsigned)((n + TB - 1) / TB);
         for (unsigned t = 0; t < b.ntiles; ++t) tile2blk.push_back((unsigned)(i - cur.b0));
         cur.ntiles += b.ntiles;
@@ -473,7 +494,7 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
     }
     groups.push_back(cur);
     // prefetch distance (blocks ahead) of the walk; 0 = off
-    const unsigned pf_dist = getenv("RCZ_IBWT_PREFETCH") ? (unsigned)atoi(getenv("RCZ_IBWT_PREFETCH")) : 2u;
+    const unsigned pf_dist = getenv("RCZ_IBWT_PREFETCH") ? (unsigned)atoi(getenv("RCZ_IBWT_PREFETCH")) : 0u;
     if (pf_dist)
         for (auto& g : groups)
             for (size_t i = g.b0; i + pf_dist < g.b1; ++i) {
@@ -539,8 +560,8 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
         const unsigned walk_grid = (unsigned)std::min<unsigned long long>((g.work + 255) / 256, (unsigned long long)c->sm_count * tune_ctas);
         RCZ_KLAUNCH(c, ibwt_walk_kernel, walk_grid, 256, 0, dblk, nb, (unsigned)g.work, (const unsigned*)wP, (uint8_t*)wS, desc, chain_ctr, queue);
         if (mark) { st = ctx_stage_mark(c, 2); if (st) return st; }
-        RCZ_KLAUNCH(c, ibwt_rank_kernel, nb, RANK_NT, rank_smem, dblk, desc, chain_ctr, chain_off, d_len, d_st);
-        unsigned cx = (unsigned)std::min<unsigned long long>((g.chains / nb + 7) / 8 + 1, std::max<unsigned long long>(1, (unsigned long long)c->sm_count * 16 / nb));
+        RCZ_KLAUNCH(c, ibwt_rank_kernel, nb, RANK_NT, rank_smem, dblk, desc, chain_ctr, chain_off, d_len, d_st, hlog);
+        unsigned cx = (unsigned)std::min<unsigned long long>((g.chains / nb + 255) / 256 + 1, std::max<unsigned long long>(1, (unsigned long long)c->sm_count * 32 / nb));
         RCZ_KLAUNCH(c, ibwt_compact_kernel, dim3(cx, nb), 256, 0, dblk, (const uint8_t*)wS, desc, chain_ctr, chain_off, dout);
         if (mark) { st = ctx_stage_mark(c, 3); if (st) return st; mark = false; }
     }
