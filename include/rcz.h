@@ -30,6 +30,8 @@
  *     out_len[i] == 0; flate, zlib, rle, ari and mtf deliver the out_len[i] bytes decoded before the error (the reference's
  *     Read impls hand out what they have before returning Err); rcz_dc_encode_blocks reports the size it would have
  *     needed when status[i] == RCZ_E_OUTPUT_FULL.
+ *   - only out_len[i] bytes of a unit's output region are meaningful; the rest of the region (up to out_cap[i]) is
+ *     unspecified after the call (the pipelined host path of lz4 copies whole regions down without waiting for the lengths).
  */
 #ifndef RCZ_H
 #define RCZ_H

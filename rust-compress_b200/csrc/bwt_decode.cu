@@ -14,9 +14,9 @@
 //                    cur = P[cur]>>8 until it meets the next sampled row (or END), packing the emitted bytes
 //                    16 at a time into a chain-local scratch slot; over-long chains are split on the fly
 //                    (continuation slots come from an atomic ticket) so no chain is walked twice
-//   E  ibwt_rank     per block: the chain descriptors are ranked by sampled list ranking again (every 16th chain is a
-//                    head; heads are ranked by Wyllie pointer jumping in shared memory) -> output offset of every chain
-//   F  ibwt_compact  chain-local bytes -> final positions (coalesced copies)
+//   E  ibwt_heads / ibwt_headrank   the chain descriptors are ranked by sampled list ranking again (every 32nd chain is a head: one
+//                    thread per head walks to the next head; heads are ranked per block by Wyllie pointer jumping in shared memory)
+//   F  ibwt_place    one thread per head walks its chains once more and copies their bytes to their final positions
 //
 // The walk starts at `origin`, emits F[cur] (== L[table[cur]-1], bwt/mod.rs:270-279) per hop, and ends at the END
 // entry — exactly the reference's iterator, so a block that is not a valid BWT yields the same (shorter) output.
@@ -45,6 +45,7 @@ struct Blk {
     unsigned max_chains;
     unsigned work0;        // first index of this block's initial work items (K + 1 of them)
     unsigned pf_off, pf_elems;   // link table of the block `prefetch distance` ahead (element offset, element count; 0 = none)
+    unsigned head0;        // first slot of this block's head nodes (ranking of the chain descriptors)
     unsigned skip;         // block rejected on the host (status already set)
     unsigned bad;          // origin supplied on the device (composed calls) and out of range: walked with origin 0, reported MALFORMED
 };
@@ -80,11 +81,13 @@ ibwt_scan_kernel(const Blk* __restrict__ blks, unsigned* __restrict__ tile_hist,
     const Blk bk = blks[b];
     unsigned run = 0;
     if (!bk.skip)
-        for (unsigned t = 0; t < bk.ntiles; ++t) {
-            const size_t idx = (size_t)(bk.tile0 + t) * 256 + c;
-            const unsigned hcnt = tile_hist[idx];
-            tile_hist[idx] = run;
-            run += hcnt;
+        for (unsigned t0 = 0; t0 < bk.ntiles; t0 += 16) {                 // 16 independent loads in flight, then the running sums
+            unsigned hc[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) hc[k] = t0 + k < bk.ntiles ? tile_hist[(size_t)(bk.tile0 + t0 + k) * 256 + c] : 0u;
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                if (t0 + k < bk.ntiles) { tile_hist[(size_t)(bk.tile0 + t0 + k) * 256 + c] = run; run += hc[k]; }
         }
     unsigned total;
     const unsigned ex = block_excl_scan_add<256>(run, scratch, &total);
@@ -283,49 +286,70 @@ ibwt_walk_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned total_
     }
 }
 
-// ------------------------------------------------------------------------------------------ E: rank chains
-// Sampled list ranking once more, one level up (one CTA per block): every 2^HEAD_LOG2-th chain descriptor (and the origin chain) is a
-// HEAD; a head walks the chain list to the next head summing lengths (pass 1), the <= nch/16 + 1 heads are ranked by Wyllie
-// pointer jumping in shared memory ((distance to END << 32) | next head), and a second walk hands every chain its output
-// offset (pass 2).  Work is O(nch) instead of O(nch log nch); the descriptors (8 B each) stay L2 resident.
-constexpr unsigned RANK_MAX_HEADS = 24576;                    // 8 B each in shared memory
+// ------------------------------------------------------------------------------------------ E/F: rank the chains, move their bytes
+// Sampled list ranking once more, one level up: every 2^hlog-th chain descriptor (and the origin chain) is a HEAD.
+//   ibwt_heads_kernel    one thread per head, all blocks at once: walk the chain list to the next head summing lengths
+//   ibwt_headrank_kernel one CTA per block: the <= nch / 2^hlog + 1 heads are ranked by Wyllie pointer jumping in shared memory
+//                        ((distance to END << 32) | next head) -> output offset of every head
+//   ibwt_place_kernel    one thread per head again: walk the same chains and copy their bytes from the chain slots to their final
+//                        offsets (aligned 16-byte loads; head bytes, funnel-shifted 32-bit words, tail bytes)
+// The two walks are O(nch) dependent 8-byte loads spread over ~10 K threads per block — latency is hidden by parallelism instead of
+// being paid by one CTA per block (the round-1 kernel: 1.5 ms per wave of blocks once chains became short and numerous).
+constexpr unsigned RANK_MAX_HEADS = 12288;                    // 8 B each in shared memory: two CTAs per SM
 
-__global__ void __launch_bounds__(RANK_NT, 1)
-ibwt_rank_kernel(const Blk* __restrict__ blks, const Desc* __restrict__ desc_base, const unsigned* __restrict__ chain_ctr,
-                 unsigned* __restrict__ chain_off, uint64_t* __restrict__ out_len, int32_t* __restrict__ status, unsigned HEAD_LOG2) {
+struct HeadGeom { unsigned nch, nreg, H, K, mask, hlog; };
+__device__ __forceinline__ HeadGeom head_geom(const Blk& bk, const unsigned* chain_ctr, unsigned b, unsigned hlog) {
+    HeadGeom g;
+    g.nch = chain_ctr[b];
+    if (g.nch > bk.max_chains) g.nch = bk.max_chains;
+    g.nreg = (g.nch + (1u << hlog) - 1) >> hlog;              // heads at chain ids 0, 2^hlog, ...
+    g.H = g.nreg + 1;                                         // + the origin chain (id K); SENT = H
+    g.K = bk.K; g.mask = (1u << hlog) - 1u; g.hlog = hlog;
+    return g;
+}
+
+__global__ void __launch_bounds__(256)
+ibwt_heads_kernel(const Blk* __restrict__ blks, const Desc* __restrict__ desc_base, const unsigned* __restrict__ chain_ctr,
+                  unsigned long long* __restrict__ node_base, unsigned hlog) {
+    const unsigned b = blockIdx.y;
+    const Blk bk = blks[b];
+    if (bk.skip) return;
+    const HeadGeom g = head_geom(bk, chain_ctr, b, hlog);
+    const Desc* desc = desc_base + bk.chain0;
+    unsigned long long* node = node_base + bk.head0;
+    for (unsigned h = blockIdx.x * blockDim.x + threadIdx.x; h < g.H; h += gridDim.x * blockDim.x) {
+        unsigned cur = h < g.nreg ? h << hlog : g.K;
+        unsigned long long acc = 0;
+        unsigned nxt_head = h;                                          // self-loop unless the walk reaches a head or END
+        if (cur < g.nch) {
+            for (unsigned steps = 0; steps <= g.nch; ++steps) {
+                const Desc d = desc[cur];
+                acc += d.len;
+                const unsigned s = d.succ;
+                if (s == SUCC_END) { nxt_head = g.H; break; }
+                if (s >= g.nch) break;                                  // dangling link: never reaches END
+                if (s == g.K) { nxt_head = g.nreg; break; }
+                if ((s & g.mask) == 0) { nxt_head = s >> hlog; break; }
+                cur = s;
+            }
+        }
+        node[h] = (acc << 32) | nxt_head;
+    }
+}
+
+__global__ void __launch_bounds__(RANK_NT, 2)
+ibwt_headrank_kernel(const Blk* __restrict__ blks, const unsigned* __restrict__ chain_ctr, unsigned long long* __restrict__ node_base,
+                     uint64_t* __restrict__ out_len, int32_t* __restrict__ status, unsigned hlog) {
     RCZ_DYN_SMEM(raw);
     unsigned long long* node = reinterpret_cast<unsigned long long*>(raw);
     volatile unsigned long long* vnode = node;
     const unsigned b = blockIdx.x, tid = threadIdx.x;
     const Blk bk = blks[b];
     if (bk.skip) return;
-    const Desc* desc = desc_base + bk.chain0;
-    unsigned* coff = chain_off + bk.chain0;
-    unsigned nch = chain_ctr[b];
-    if (nch > bk.max_chains) nch = bk.max_chains;
-    const unsigned nreg = (nch + (1u << HEAD_LOG2) - 1) >> HEAD_LOG2;   // heads at chain ids 0, 2^HEAD_LOG2, ...
-    const unsigned H = nreg + 1;                                        // + the origin chain (id K); SENT = H
-    const unsigned SENT = H, mask = (1u << HEAD_LOG2) - 1u, K = bk.K;
-    for (unsigned i = tid; i < nch; i += RANK_NT) coff[i] = OFF_INVALID;
-    // ---- pass 1: head -> (length up to the next head, next head)
-    for (unsigned h = tid; h < H; h += RANK_NT) {
-        unsigned cur = h < nreg ? h << HEAD_LOG2 : K;
-        unsigned long long acc = 0;
-        unsigned nxt_head = h;                                          // self-loop unless the walk reaches a head or END
-        if (cur < nch) {
-            for (unsigned steps = 0; steps <= nch; ++steps) {
-                const Desc d = desc[cur];
-                acc += d.len;
-                const unsigned s = d.succ;
-                if (s == SUCC_END) { nxt_head = SENT; break; }
-                if (s >= nch) break;                                    // dangling link: never reaches END
-                if (s == K) { nxt_head = nreg; break; }
-                if ((s & mask) == 0) { nxt_head = s >> HEAD_LOG2; break; }
-                cur = s;
-            }
-        }
-        node[h] = (acc << 32) | nxt_head;
-    }
+    const HeadGeom g = head_geom(bk, chain_ctr, b, hlog);
+    unsigned long long* gnode = node_base + bk.head0;
+    const unsigned H = g.H, SENT = g.H;
+    for (unsigned i = tid; i < H; i += RANK_NT) node[i] = gnode[i];
     if (tid == 0) node[SENT] = SENT;
     __syncthreads();
     // ---- Wyllie over the heads
@@ -344,65 +368,64 @@ ibwt_rank_kernel(const Blk* __restrict__ blks, const Desc* __restrict__ desc_bas
         }
         if (!__syncthreads_or(pend)) break;
     }
-    const unsigned long long org = node[nreg];
+    const unsigned long long org = node[g.nreg];
     const unsigned total = (unsigned)org == SENT ? (unsigned)(org >> 32) : 0u;   // the origin chain always reaches END
-    // ---- pass 2: offsets of the chains behind every head that reaches END
-    for (unsigned h = tid; h < H; h += RANK_NT) {
-        const unsigned long long a = node[h];
-        if ((unsigned)a != SENT) continue;
-        unsigned cur = h < nreg ? h << HEAD_LOG2 : K;
-        if (cur >= nch) continue;
-        if (h < nreg && cur == K) continue;                             // the origin chain is walked once, as head `nreg`
-        unsigned off = total - (unsigned)(a >> 32);
-        for (unsigned steps = 0; steps <= nch; ++steps) {
-            const Desc d = desc[cur];
-            coff[cur] = off;
-            off += d.len;
-            const unsigned s = d.succ;
-            if (s == SUCC_END || s >= nch || s == K || (s & mask) == 0) break;
-            cur = s;
-        }
+    // head h -> output offset of its first chain (OFF_INVALID when it never reaches END: its chains are not part of the output)
+    for (unsigned i = tid; i < H; i += RANK_NT) {
+        const unsigned long long a = node[i];
+        gnode[i] = (unsigned)a == SENT ? (unsigned long long)(total - (unsigned)(a >> 32)) : (unsigned long long)OFF_INVALID;
     }
     if (tid == 0) { out_len[b] = bk.bad ? 0 : total; status[b] = bk.bad ? RCZ_E_MALFORMED : RCZ_OK; }
 }
 
-// ------------------------------------------------------------------------------------------ F: compact
-// blockIdx.y = block, one THREAD per chain (chains are a few dozen bytes with dense sampling): aligned 16-byte loads from the chain's
-// slot, then head bytes up to the destination's 4-byte boundary, 32-bit words put together with funnel shifts, tail bytes.
+// len bytes from the 16-byte-aligned chain slot to an arbitrarily aligned destination
+__device__ __forceinline__ void copy_chain(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, unsigned len) {
+    for (unsigned base = 0; base < len; base += 16) {
+        const uint4 q = __ldcs(reinterpret_cast<const uint4*>(src + base));      // read once: streaming
+        const unsigned m = len - base < 16u ? len - base : 16u;
+        const unsigned wv[5] = {q.x, q.y, q.z, q.w, 0u};
+        uint8_t* d = dst + base;
+        const unsigned head = (unsigned)((4u - ((uintptr_t)d & 3u)) & 3u);
+        if (m >= 4u + head) {
+            unsigned done = 0;
+            for (; done < head; ++done) d[done] = (uint8_t)(q.x >> (8u * done));
+            const unsigned sh = 8u * head;                                       // words from byte `head` on: (w[i] >> sh) | (w[i+1] << (32 - sh))
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (done + 4u <= m) { *reinterpret_cast<unsigned*>(d + done) = __funnelshift_r(wv[i], wv[i + 1], sh); done += 4; }
+            for (; done < m; ++done) d[done] = (uint8_t)(wv[done >> 2] >> (8u * (done & 3u)));
+        } else {
+            for (unsigned k = 0; k < m; ++k) d[k] = (uint8_t)(wv[k >> 2] >> (8u * (k & 3u)));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
-ibwt_compact_kernel(const Blk* __restrict__ blks, const uint8_t* __restrict__ scratch_base, const Desc* __restrict__ desc_base,
-                    const unsigned* __restrict__ chain_ctr, const unsigned* __restrict__ chain_off, uint8_t* __restrict__ out_base) {
+ibwt_place_kernel(const Blk* __restrict__ blks, const uint8_t* __restrict__ scratch_base, const Desc* __restrict__ desc_base,
+                  const unsigned* __restrict__ chain_ctr, const unsigned long long* __restrict__ node_base, uint8_t* __restrict__ out_base,
+                  unsigned hlog) {
     const unsigned b = blockIdx.y;
     const Blk bk = blks[b];
     if (bk.skip) return;
-    unsigned nch = chain_ctr[b];
-    if (nch > bk.max_chains) nch = bk.max_chains;
+    const HeadGeom g = head_geom(bk, chain_ctr, b, hlog);
     const Desc* desc = desc_base + bk.chain0;
-    const unsigned* coff = chain_off + bk.chain0;
+    const unsigned long long* node = node_base + bk.head0;
+    const uint8_t* scratch = scratch_base + bk.scratch_off;
     uint8_t* out = out_base + bk.out_off;
-    for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < nch; g += gridDim.x * blockDim.x) {
-        const unsigned off = coff[g];
+    for (unsigned h = blockIdx.x * blockDim.x + threadIdx.x; h < g.H; h += gridDim.x * blockDim.x) {
+        unsigned off = (unsigned)node[h];
         if (off == OFF_INVALID) continue;
-        const unsigned len = desc[g].len;
-        const uint8_t* src = scratch_base + bk.scratch_off + (size_t)g * bk.cap;
-        uint8_t* dst = out + off;
-        for (unsigned base = 0; base < len; base += 16) {                       // 16 source bytes -> dst + base
-            const uint4 q = __ldcs(reinterpret_cast<const uint4*>(src + base));  // read once: streaming
-            const unsigned m = len - base < 16u ? len - base : 16u;
-            const unsigned wv[5] = {q.x, q.y, q.z, q.w, 0u};
-            uint8_t* d = dst + base;
-            const unsigned head = (unsigned)((4u - ((uintptr_t)d & 3u)) & 3u);
-            if (m >= 4u + head) {
-                unsigned done = 0;
-                for (; done < head; ++done) d[done] = (uint8_t)(q.x >> (8u * done));
-                const unsigned sh = 8u * head;                                   // words from byte `head` on: (w[i] >> sh) | (w[i+1] << (32 - sh))
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (done + 4u <= m) { *reinterpret_cast<unsigned*>(d + done) = __funnelshift_r(wv[i], wv[i + 1], sh); done += 4; }
-                for (; done < m; ++done) d[done] = (uint8_t)(wv[done >> 2] >> (8u * (done & 3u)));
-            } else {
-                for (unsigned k = 0; k < m; ++k) d[k] = (uint8_t)(wv[k >> 2] >> (8u * (k & 3u)));
-            }
+        unsigned cur = h < g.nreg ? h << hlog : g.K;
+        if (cur >= g.nch) continue;
+        if (h < g.nreg && cur == g.K) continue;                         // the origin chain is walked once, as head `nreg`
+        for (unsigned steps = 0; steps <= g.nch; ++steps) {
+            const Desc d = desc[cur];
+            if (off + d.len > bk.n) break;                              // (a well-formed block never gets here)
+            copy_chain(scratch + (size_t)cur * bk.cap, out + off, d.len);
+            off += d.len;
+            const unsigned s = d.succ;
+            if (s == SUCC_END || s >= g.nch || s == g.K || (s & g.mask) == 0) break;
+            cur = s;
         }
     }
 }
@@ -454,18 +477,18 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
     const unsigned tune_slog = getenv("RCZ_IBWT_SLOG") ? (unsigned)atoi(getenv("RCZ_IBWT_SLOG")) : 4u;
     const unsigned tune_ctas = getenv("RCZ_IBWT_WALK_CTAS") ? (unsigned)atoi(getenv("RCZ_IBWT_WALK_CTAS")) : 4u;
     const unsigned long long group_syms = getenv("RCZ_IBWT_GROUP_SYMS") ? strtoull(getenv("RCZ_IBWT_GROUP_SYMS"), nullptr, 10) : (1ull << 30);
-    struct Group { size_t b0, b1; unsigned tile0_abs, ntiles; unsigned long long p_elems, scratch_bytes, chains, work; };
+    struct Group { size_t b0, b1; unsigned tile0_abs, ntiles; unsigned long long p_elems, scratch_bytes, chains, work, heads; };
     std::vector<Blk> blks(nblocks);
     std::vector<int32_t> hstatus(nblocks, 0);
     std::vector<unsigned> tile2blk;
     std::vector<Group> groups;
-    Group cur{0, 0, 0, 0, 0, 0, 0, 0};
-    unsigned hlog = 4;
+    Group cur{0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned hlog = 5, max_mc = 0;
     for (size_t i = 0; i < nblocks; ++i) {
         const unsigned long long n = n_arr[i];
         if (cur.b1 > cur.b0 && cur.p_elems && cur.p_elems + n > group_syms) {
             groups.push_back(cur);
-            cur = Group{i, i, (unsigned)tile2blk.size(), 0, 0, 0, 0, 0};
+            cur = Group{i, i, (unsigned)tile2blk.size(), 0, 0, 0, 0, 0, 0};
         }
         Blk& b = blks[i];
         memset(&b, 0, sizeof b);
@@ -484,6 +507,7 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
         b.cap = std::max(32u, 4u << slog);                    // bytes per chain slot: P(chain longer than 4 strides) = e^-4
         b.max_chains = b.K + 1 + (unsigned)(n / b.cap) + 1;   // every row is walked at most once => <= n/cap continuations
         while (((b.max_chains >> hlog) + 3) > RANK_MAX_HEADS) ++hlog;   // one head sampling for the whole call
+        max_mc = std::max(max_mc, b.max_chains);
         b.ntiles = (unsigned)((n + TB - 1) / TB);
         for (unsigned t = 0; t < b.ntiles; ++t) tile2blk.push_back((unsigned)(i - cur.b0));
         cur.ntiles += b.ntiles;
@@ -493,6 +517,12 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
         cur.work += b.K + 1;
     }
     groups.push_back(cur);
+    // head nodes of the chain ranking: (max_chains >> hlog) + 3 slots per block, group-relative like the other offsets
+    for (auto& g : groups) {
+        unsigned long long h0 = 0;
+        for (size_t i = g.b0; i < g.b1; ++i) { blks[i].head0 = (unsigned)h0; if (!blks[i].skip) h0 += (blks[i].max_chains >> hlog) + 3; }
+        g.heads = h0;
+    }
     // prefetch distance (blocks ahead) of the walk; 0 = off
     const unsigned pf_dist = getenv("RCZ_IBWT_PREFETCH") ? (unsigned)atoi(getenv("RCZ_IBWT_PREFETCH")) : 0u;
     if (pf_dist)
@@ -501,10 +531,10 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
                 const Blk& t = blks[i + pf_dist];
                 if (!blks[i].skip && !t.skip) { blks[i].pf_off = t.p_off; blks[i].pf_elems = (t.n + 3u) & ~3u; }
             }
-    unsigned long long max_p = 0, max_scratch = 0, max_chains = 0; unsigned max_tiles = 0; size_t max_nb = 0;
+    unsigned long long max_p = 0, max_scratch = 0, max_chains = 0, max_heads = 0; unsigned max_tiles = 0; size_t max_nb = 0;
     for (auto& g : groups) {
         max_p = std::max(max_p, g.p_elems); max_scratch = std::max(max_scratch, g.scratch_bytes); max_chains = std::max(max_chains, g.chains);
-        max_tiles = std::max(max_tiles, g.ntiles); max_nb = std::max(max_nb, g.b1 - g.b0);
+        max_tiles = std::max(max_tiles, g.ntiles); max_nb = std::max(max_nb, g.b1 - g.b0); max_heads = std::max(max_heads, g.heads);
     }
 
     DescStager ds(c, mem_kind, nblocks);
@@ -523,8 +553,8 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
     void *wP, *wS, *wM;
     st = ctx_ws(c, WS_A, (size_t)max_p * 4 + 256, &wP); if (st) return st;
     st = ctx_ws(c, WS_B, (size_t)max_scratch + 256, &wS); if (st) return st;
-    // misc: tile_hist | cbase | desc | chain_off | chain_ctr | queue
-    const size_t sz_hist = (size_t)max_tiles * 256 * 4, sz_cb = max_nb * 256 * 4, sz_desc = (size_t)max_chains * 8, sz_coff = (size_t)max_chains * 4,
+    // misc: tile_hist | cbase | desc | head nodes | chain_ctr | queue
+    const size_t sz_hist = (size_t)max_tiles * 256 * 4, sz_cb = max_nb * 256 * 4, sz_desc = (size_t)max_chains * 8, sz_coff = (size_t)max_heads * 8,
                  sz_ctr = max_nb * 4;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     st = ctx_ws(c, WS_C, al(sz_hist) + al(sz_cb) + al(sz_desc) + al(sz_coff) + al(sz_ctr) + 512, &wM); if (st) return st;
@@ -532,13 +562,13 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
     unsigned* tile_hist = (unsigned*)m; m += al(sz_hist);
     unsigned* cbase = (unsigned*)m; m += al(sz_cb);
     Desc* desc = (Desc*)m; m += al(sz_desc);
-    unsigned* chain_off = (unsigned*)m; m += al(sz_coff);
+    unsigned long long* nodes = (unsigned long long*)m; m += al(sz_coff);
     unsigned* chain_ctr = (unsigned*)m; m += al(sz_ctr);
     unsigned* queue = (unsigned*)m;
 
     RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(ibwt_scatter_kernel, sizeof(ScatterSmem)));
-    const size_t rank_smem = ((size_t)RANK_MAX_HEADS + 2) * 8;
-    RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(ibwt_rank_kernel, rank_smem));
+    const size_t rank_smem = ((size_t)(max_mc >> hlog) + 4) * 8;
+    RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(ibwt_headrank_kernel, rank_smem));
     st = ctx_timer_begin(c); if (st) return st;
     // rcz_last_stage_ms: {partition (hist, scan, scatter), walk, rank + compact} of the FIRST group
     bool mark = true;
@@ -560,9 +590,10 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
         const unsigned walk_grid = (unsigned)std::min<unsigned long long>((g.work + 255) / 256, (unsigned long long)c->sm_count * tune_ctas);
         RCZ_KLAUNCH(c, ibwt_walk_kernel, walk_grid, 256, 0, dblk, nb, (unsigned)g.work, (const unsigned*)wP, (uint8_t*)wS, desc, chain_ctr, queue);
         if (mark) { st = ctx_stage_mark(c, 2); if (st) return st; }
-        RCZ_KLAUNCH(c, ibwt_rank_kernel, nb, RANK_NT, rank_smem, dblk, desc, chain_ctr, chain_off, d_len, d_st, hlog);
-        unsigned cx = (unsigned)std::min<unsigned long long>((g.chains / nb + 255) / 256 + 1, std::max<unsigned long long>(1, (unsigned long long)c->sm_count * 32 / nb));
-        RCZ_KLAUNCH(c, ibwt_compact_kernel, dim3(cx, nb), 256, 0, dblk, (const uint8_t*)wS, desc, chain_ctr, chain_off, dout);
+        const unsigned hx = (unsigned)std::min<unsigned long long>(((max_mc >> hlog) + 3 + 255) / 256, std::max<unsigned long long>(1, (unsigned long long)c->sm_count * 16 / nb));
+        RCZ_KLAUNCH(c, ibwt_heads_kernel, dim3(hx, nb), 256, 0, dblk, desc, chain_ctr, nodes, hlog);
+        RCZ_KLAUNCH(c, ibwt_headrank_kernel, nb, RANK_NT, rank_smem, dblk, chain_ctr, nodes, d_len, d_st, hlog);
+        RCZ_KLAUNCH(c, ibwt_place_kernel, dim3(hx, nb), 256, 0, dblk, (const uint8_t*)wS, desc, chain_ctr, nodes, dout, hlog);
         if (mark) { st = ctx_stage_mark(c, 3); if (st) return st; mark = false; }
     }
     st = ctx_timer_end(c); if (st) return st;

@@ -914,16 +914,24 @@ struct Lz4Job {
 static int lz4_prepare(rcz_ctx* c, DescStager& ds, const uint64_t* in_len, size_t nblocks, const std::vector<size_t>& cut, Lz4Job& job) {
     using namespace lz4k;
     Lz4Plan& pl = job.pl;
-    pl.nw.resize(nblocks); pl.wbase.resize(nblocks + 1);
-    size_t tot = 0;
-    for (size_t i = 0; i < nblocks; ++i) { pl.wbase[i] = (uint32_t)tot; pl.nw[i] = (uint32_t)((in_len[i] + W - 1) / W); tot += pl.nw[i]; }
-    pl.wbase[nblocks] = (uint32_t)tot; pl.totwin = tot;
-    if (tot >= 0x7fffffffull) return RCZ_E_ARG;
     job.cut = cut;
     const size_t nr = cut.size() - 1;
-    pl.tickets.reserve(2 * tot);
-    for (size_t k = 0; k < nr; ++k) { job.tk_off.push_back(pl.tickets.size() / 2); lz4_plan_range(pl, cut[k], cut[k + 1] - cut[k], pl.tickets); }
-    job.tk_off.push_back(pl.tickets.size() / 2);
+    auto& pc = c->lz4_plan;
+    if (pc.in_len.size() == nblocks && pc.cut == cut && memcmp(pc.in_len.data(), in_len, nblocks * 8) == 0) {
+        pl.nw = pc.nw; pl.wbase = pc.wbase; pl.tickets = pc.tickets; pl.totwin = pc.totwin; job.tk_off = pc.tk_off;
+    } else {
+        pl.nw.resize(nblocks); pl.wbase.resize(nblocks + 1);
+        size_t tot0 = 0;
+        for (size_t i = 0; i < nblocks; ++i) { pl.wbase[i] = (uint32_t)tot0; pl.nw[i] = (uint32_t)((in_len[i] + W - 1) / W); tot0 += pl.nw[i]; }
+        pl.wbase[nblocks] = (uint32_t)tot0; pl.totwin = tot0;
+        if (tot0 >= 0x7fffffffull) return RCZ_E_ARG;
+        pl.tickets.reserve(2 * tot0);
+        for (size_t k = 0; k < nr; ++k) { job.tk_off.push_back(pl.tickets.size() / 2); lz4_plan_range(pl, cut[k], cut[k + 1] - cut[k], pl.tickets); }
+        job.tk_off.push_back(pl.tickets.size() / 2);
+        pc.in_len.assign(in_len, in_len + nblocks); pc.cut = cut; pc.tk_off = job.tk_off;
+        pc.nw = pl.nw; pc.wbase = pl.wbase; pc.tickets = pl.tickets; pc.totwin = pl.totwin;
+    }
+    const size_t tot = pl.totwin;
     const size_t i_wb = ds.add_in(pl.wbase.data(), (nblocks + 1) * 4), i_nw = ds.add_in(pl.nw.data(), nblocks * 4);
     const size_t i_tk = ds.add_in(pl.tickets.data(), pl.tickets.size() * 4);
     int st = ds.upload(); if (st) return st;
@@ -986,37 +994,52 @@ static int lz4_host_pipelined(rcz_ctx* c, DescStager& ds, const Lz4Job& job, con
         st = lz4_enqueue_range(c, ks, job, ds, k, din, dout, d_len, d_st); if (st) return st;
         RCZ_CK(c, rt_event_record(c->events[3 * k + 1], ks));
     }
-    // results and output come down on one D2H stream in chunk order; the (tiny) result copy targets a pinned scratch so that
-    // it does not block the host, and the host only waits for it right before it sizes the chunk's output copies
+    // output comes down on one D2H stream in chunk order, each chunk behind its kernels' event and with NO host involvement: the
+    // whole out_cap span of every block is copied (adjacent blocks merged into one copy), so nothing has to wait for the lengths;
+    // the results (out_len, status) follow in one small copy at the end.  Bytes of a block's region beyond out_len[i] are
+    // unspecified afterwards (rcz.h).
     void* pin; st = ctx_pinned(c, nblocks * 12 + 64, &pin); if (st) return st;
     uint64_t* p_len = (uint64_t*)pin; int32_t* p_st = (int32_t*)((uint8_t*)pin + nblocks * 8);
     const rt_stream_t dsm = c->aux[0];
-    size_t issued = 0;                                          // result copies issued so far
-    auto issue_results = [&](size_t k) -> int {
-        const size_t b0 = cut[k], nb = cut[k + 1] - cut[k];
-        RCZ_CK(c, rt_stream_wait_event(dsm, c->events[3 * k + 1]));
-        RCZ_CK(c, rt_d2h(p_len + b0, d_len + b0, nb * 8, dsm));
-        RCZ_CK(c, rt_d2h(p_st + b0, d_st + b0, nb * 4, dsm));
-        RCZ_CK(c, rt_event_record(c->events[3 * k + 2], dsm));
-        return RCZ_OK;
-    };
+    bool all_full = true;
     for (size_t k = 0; k < nchunks; ++k) {
-        while (issued < nchunks && issued <= k + 1) { st = issue_results(issued++); if (st) return st; }   // one chunk ahead
-        RCZ_CK(c, rt_event_sync(c->events[3 * k + 2]));
+        RCZ_CK(c, rt_stream_wait_event(dsm, c->events[3 * k + 1]));
         size_t i = cut[k];
         const size_t e = cut[k + 1];
-        for (size_t q = i; q < e; ++q) { out_len[q] = p_len[q]; status[q] = p_st[q]; }
+        // a chunk whose capacity is out of proportion to its compressed bytes (small blocks in a frame that declares 4 MiB ones) is not
+        // worth copying whole: for it the host waits for the lengths and copies what was decoded
+        uint64_t csum = 0, isum = 0;
+        for (size_t q = i; q < e; ++q) { csum += out_cap[q]; isum += in_len[q]; }
+        if (csum > 8 * isum + (1u << 20)) {
+            all_full = false;
+            RCZ_CK(c, rt_d2h(p_len + i, d_len + i, (e - i) * 8, dsm));
+            RCZ_CK(c, rt_d2h(p_st + i, d_st + i, (e - i) * 4, dsm));
+            RCZ_CK(c, rt_stream_sync(dsm));
+            while (i < e) {
+                if (p_len[i] == 0 || p_st[i] != RCZ_OK) { ++i; continue; }
+                const uint64_t s0 = out_off[i]; uint64_t t = s0 + p_len[i];
+                size_t j = i + 1;
+                while (j < e && p_st[j] == RCZ_OK && (p_len[j] == 0 || out_off[j] == t)) { t += p_len[j]; ++j; }
+                RCZ_CK(c, rt_d2h((uint8_t*)out_base + s0, dout + s0, (size_t)(t - s0), dsm));
+                i = j;
+            }
+            continue;
+        }
         while (i < e) {
-            if (out_len[i] == 0 || status[i] != RCZ_OK) { ++i; continue; }
-            const uint64_t s = out_off[i]; uint64_t t = s + out_len[i];
+            if (out_cap[i] == 0) { ++i; continue; }
+            const uint64_t s0 = out_off[i]; uint64_t t = s0 + out_cap[i];
             size_t j = i + 1;
-            while (j < e && status[j] == RCZ_OK && (out_len[j] == 0 || out_off[j] == t)) { t += out_len[j]; ++j; }
-            RCZ_CK(c, rt_d2h((uint8_t*)out_base + s, dout + s, (size_t)(t - s), dsm));
+            while (j < e && (out_cap[j] == 0 || out_off[j] == t)) { t += out_cap[j]; ++j; }
+            RCZ_CK(c, rt_d2h((uint8_t*)out_base + s0, dout + s0, (size_t)(t - s0), dsm));
             i = j;
         }
     }
+    (void)all_full;
+    RCZ_CK(c, rt_d2h(p_len, d_len, nblocks * 8, dsm));
+    RCZ_CK(c, rt_d2h(p_st, d_st, nblocks * 4, dsm));
     RCZ_CK(c, rt_stream_sync(dsm));
     for (int i = 1; i < 9; ++i) RCZ_CK(c, rt_stream_sync(c->aux[i]));
+    for (size_t q = 0; q < nblocks; ++q) { out_len[q] = p_len[q]; status[q] = p_st[q]; }
     c->ev_valid = false;
     return RCZ_OK;
 }

@@ -26,6 +26,9 @@ struct rcz_ctx {
     size_t pinned_cap = 0;
     rt_stream_t aux[9] = {};          // D2H stream + 8 kernel streams of the pipelined host-buffer path (created on first use)
     std::vector<rt_event_t> events;   // event pool of the pipelined path
+    // lz4: window plan of the most recent call; a caller that decodes batches of the same geometry (same compressed lengths, same
+    // chunking) gets it back without the host recomputing ~70 K tickets
+    struct { std::vector<uint64_t> in_len; std::vector<size_t> cut, tk_off; std::vector<uint32_t> nw, wbase, tickets; size_t totwin = 0; } lz4_plan;
 };
 
 #define RCZ_CK(ctx, expr)                                                                              \
