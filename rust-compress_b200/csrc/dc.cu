@@ -194,19 +194,23 @@ dc_decode_kernel(const uint32_t* __restrict__ in_base, const uint64_t* __restric
         __syncwarp();
         int err = 0;
         unsigned i = 0;
-        unsigned long long di = 0;
-        unsigned dreg = lane < ndist ? __ldg(dist + lane) : 0u;               // distances [32g, 32g + 32) of the current group, one per lane
-        unsigned dnxt = 32ull + lane < ndist ? __ldg(dist + 32 + lane) : 0u;  // the next group, in flight while this one is used
+        const unsigned ND = ndist > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)ndist;   // (a block has at most n < 2^31 run ends)
+        unsigned di = 0;
+        unsigned dreg = lane < ND ? __ldg(dist + lane) : 0u;                  // distances [32g, 32g + 32) of the current group, one per lane
+        unsigned dnxt = 32u + lane < ND ? __ldg(dist + 32 + lane) : 0u;       // the next group, in flight while this one is used
         while (i < N) {
             const unsigned stop = __shfl_sync(RCZ_FULL, nx, 1), sym = __shfl_sync(RCZ_FULL, sy, 0);
             const unsigned up_nx = __shfl_down_sync(RCZ_FULL, nx, 1), up_sy = __shfl_down_sync(RCZ_FULL, sy, 1);
-            if (stop > N) { err = RCZ_E_MALFORMED; break; }                   // output[i] index panic
-            for (unsigned k = i + lane; k < stop; k += 32) out[k] = (uint8_t)sym;
-            if (stop > i) i = stop;
-            if (di >= ndist) { err = RCZ_E_UNEXPECTED_EOF; break; }           // dc.rs:245-246
             const unsigned d = __shfl_sync(RCZ_FULL, dreg, (int)(di & 31u));
+            if (stop > N) { err = RCZ_E_MALFORMED; break; }                   // output[i] index panic
+            if (stop > i) {                                                   // the run [i, stop): almost always a few bytes
+                if (lane < stop - i) out[i + lane] = (uint8_t)sym;
+                if (stop - i > 32u) for (unsigned k = i + 32u + lane; k < stop; k += 32) out[k] = (uint8_t)sym;
+                i = stop;
+            }
+            if (di >= ND) { err = RCZ_E_UNEXPECTED_EOF; break; }              // dc.rs:245-246
             ++di;
-            if ((di & 31u) == 0) { dreg = dnxt; dnxt = di + 32 + lane < ndist ? __ldg(dist + di + 32 + lane) : 0u; }
+            if ((di & 31u) == 0) { dreg = dnxt; dnxt = (unsigned long long)di + 32 + lane < ND ? __ldg(dist + di + 32 + lane) : 0u; }
             if (d > N - stop) { err = RCZ_E_MALFORMED; break; }               // dc.rs:213 assert!(future <= n)
             const unsigned future = stop + d;
             // rank = 1 + #{leading r in [1, A) : future + r > next(list[r])}  (dc.rs:215-218; the reference stops at the first rank that
