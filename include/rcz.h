@@ -106,6 +106,13 @@ const char* rcz_build_info(void);
 int rcz_lz4_decode_blocks(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
                           void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
                           uint64_t* out_len, int32_t* status, size_t nblocks, int mem_kind);
+/* rcz_lz4_encode_blocks replaces `BlockEncoder::encode` / `lz4::encode_block` (lz4.rs:183-311, 616-627): the reference's greedy
+ * single-probe hash compressor, byte for byte (same probe sequence, skip acceleration, rewind, `pos + 12 > len` tail rule).
+ * out_cap[i] must be >= rcz_lz4_compression_bound(in_len[i]) (the reference reserves exactly that, lz4.rs:232-238), else
+ * status[i] = RCZ_E_OUTPUT_FULL.  in_len[i] > 0x7e000000 yields out_len[i] = 0 like the reference (lz4.rs:229-230). */
+int rcz_lz4_encode_blocks(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                          void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
+                          uint64_t* out_len, int32_t* status, size_t nblocks, int mem_kind);
 /* `lz4::compression_bound` (lz4.rs:175-181); -1 == None */
 int64_t rcz_lz4_compression_bound(uint32_t size);
 

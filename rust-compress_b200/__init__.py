@@ -140,6 +140,14 @@ class Context:
         self._check(st, "rcz_lz4_decode_blocks")
         return out_len, status
 
+    def lz4_encode_blocks(self, in_buf, in_off, in_len, out_buf, out_off, out_cap, async_=False):
+        """rcz_lz4_encode_blocks (lz4.rs:226-310, bit-exact).  Returns (out_len, status) arrays."""
+        kind, n, (io, il, oo, oc), out_len, status, _ = self._batch(None, "lz4e", in_buf, in_off, in_len, out_buf, out_off, out_cap, async_=async_)
+        st = self._lib.rcz_lz4_encode_blocks(self._h, _ptr(in_buf), _ptr(io), _ptr(il), _ptr(out_buf), _ptr(oo), _ptr(oc),
+                                             _ptr(out_len), _ptr(status), n, kind)
+        self._check(st, "rcz_lz4_encode_blocks")
+        return out_len, status
+
     # ---- bwt -----------------------------------------------------------------------------------------------
     def bwt_decode_blocks(self, in_buf, in_off, n_arr, origin, out_buf, out_off, async_=False):
         kind = _kind_of(in_buf, async_)

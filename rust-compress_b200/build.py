@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["rcz_ctx.cu", "lz4_decode.cu", "bwt_decode.cu", "bwt_encode.cu", "flate_decode.cu", "ari.cu", "dc.cu", "rle.cu", "mtf.cu", "pipeline.cu"]
+SOURCES = ["rcz_ctx.cu", "lz4_decode.cu", "lz4_encode.cu", "bwt_decode.cu", "bwt_encode.cu", "flate_decode.cu", "ari.cu", "dc.cu", "rle.cu", "mtf.cu", "pipeline.cu"]
 LIB = os.path.join(HERE, "librcz.so")
 LIB_EMU = os.path.join(HERE, "librcz_emu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -19,14 +19,14 @@
 namespace flk {
 
 constexpr int NT = 128, WPB = NT / 32;
-constexpr int LB = 10, DB = 9;                       // primary LUT bits
+constexpr int LB = 9, DB = 8;                        // primary LUT bits (32-bit entries: same shared memory as 10 / 9 bits of 16-bit ones)
 constexpr int MAXBITS = 15, MAXLCODES = 286, MAXDCODES = 30, MAXCODES = 316;   // flate.rs:36-39
 constexpr unsigned HISTORY = 32 * 1024;              // flate.rs:40
 
 struct Tree { unsigned count[16]; unsigned offs[16]; unsigned first[16]; unsigned run[16]; };
 struct WarpSmem {
-    __align__(16) uint16_t llut[1 << LB];
-    __align__(16) uint16_t dlut[1 << DB];
+    __align__(16) uint32_t llut[1 << LB];             // see ll_entry / dd_entry
+    __align__(16) uint32_t dlut[1 << DB];
     uint16_t lsym[288], dsym[32], csym[20];
     Tree lt, dt, ct;
     uint8_t lens[MAXCODES + 4];
@@ -40,44 +40,93 @@ __constant__ uint16_t EXTRADIST[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 
 __constant__ uint8_t EXTRADBITS[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 __constant__ uint8_t CL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-// LSB-first bit reader (flate.rs:250-260).  The reference refills one byte at a time, so its byte position is
-// always ceil(bitpos / 8); `bitpos > endbits` here is its UnexpectedEof.
+// LSB-first bit reader (flate.rs:250-260).  The reference refills one byte at a time, so its byte position is always
+// ceil(bits consumed / 8), and reading past the input is its UnexpectedEof.  Here the buffer is refilled 32 bits at a time from
+// aligned words (the next one already in flight); words past the end read as zero and are counted in `pad`, so "consumed more than
+// the input holds" is simply bc < pad — no 64-bit position is carried through the symbol loop.
 struct Bits {
     const uint8_t* in; const uint8_t* end;
-    const uint32_t* wp;
-    unsigned long long bb; unsigned bc;
-    unsigned long long bitpos, endbits;
-    __device__ __forceinline__ unsigned word() { const unsigned w = ((const uint8_t*)wp < end) ? __ldg(wp) : 0u; ++wp; return w; }
+    const uint32_t* wp;                                  // next word to load
+    unsigned long long bb; unsigned bc;                  // bit buffer, valid + padding bits in it
+    unsigned pad;                                        // padding bits that entered the buffer
+    unsigned nxt;                                        // the word at wp[-1], loaded ahead of its use
+    unsigned long long base_bits;                        // bit position (in the stream) of the first bit of the word at wp0
+    const uint32_t* wp0;
+    __device__ __forceinline__ unsigned fetch() {        // returns the word at wp, masked beyond the end; advances
+        unsigned w = 0;
+        const uint8_t* p = (const uint8_t*)wp;
+        if (p + 4 <= end) w = __ldg(wp);
+        else if (p < end) { w = __ldg(wp) & (0xffffffffu >> (8u * (unsigned)(p + 4 - end))); }
+        ++wp;
+        return w;
+    }
+    __device__ __forceinline__ unsigned padbits_of(const uint8_t* p) const {     // padding bits inside the word that starts at p
+        return p + 4 <= end ? 0u : p >= end ? 32u : 8u * (unsigned)(p + 4 - end);
+    }
     __device__ __forceinline__ void seek(unsigned long long bytepos) {
         const uint8_t* p = in + bytepos;
         const unsigned mis = (unsigned)((uintptr_t)p & 3);
         wp = reinterpret_cast<const uint32_t*>(p - mis);
-        bb = (unsigned long long)word() >> (8 * mis);
+        wp0 = wp;
+        base_bits = (bytepos - mis) * 8;                 // may "underflow" by up to 24 bits below zero at bytepos 0: only differences are used
+        pad = padbits_of((const uint8_t*)wp);             // padding bits (beyond the input's end) that entered the buffer, cumulative
+        bb = (unsigned long long)fetch() >> (8 * mis);
         bc = 32 - 8 * mis;
-        bitpos = bytepos * 8;
+        nxt = fetch();                                    // not in the buffer yet: its padding is counted when it enters (refill)
     }
-    __device__ __forceinline__ void init(const uint8_t* p, unsigned long long n) { in = p; end = p + n; endbits = n * 8; seek(0); }
-    __device__ __forceinline__ void refill() { if (bc <= 32) { bb |= (unsigned long long)word() << bc; bc += 32; } }   // bc >= 33 afterwards
+    __device__ __forceinline__ void init(const uint8_t* p, unsigned long long n) { in = p; end = p + n; seek(0); }
+    __device__ __forceinline__ void refill() {           // bc >= 33 afterwards
+        if (bc <= 32) {
+            bb |= (unsigned long long)nxt << bc; bc += 32;
+            pad += padbits_of((const uint8_t*)(wp - 1));
+            nxt = fetch();
+        }
+    }
     __device__ __forceinline__ unsigned peek(unsigned k) const { return (unsigned)bb & ((1u << k) - 1u); }
-    __device__ __forceinline__ void consume(unsigned k) { bb >>= k; bc -= k; bitpos += k; }
-    __device__ __forceinline__ bool eof() const { return bitpos > endbits; }
-    // bits(cnt) with cnt <= 16; caller has refilled
+    __device__ __forceinline__ void consume(unsigned k) { bb >>= k; bc -= k; }
+    __device__ __forceinline__ bool eof() const { return bc < pad; }
     __device__ __forceinline__ unsigned take(unsigned k) { const unsigned v = peek(k); consume(k); return v; }
-    __device__ __forceinline__ unsigned long long bytepos() const { return (bitpos + 7) >> 3; }
+    // bits consumed so far = bits that entered the buffer - bits still in it
+    __device__ __forceinline__ unsigned long long bitpos() const {
+        return base_bits + 32ull * (unsigned long long)((wp - 1) - wp0) - bc;    // (wp - 1): `nxt` has not entered the buffer
+    }
+    __device__ __forceinline__ unsigned long long endbits() const { return 8ull * (unsigned long long)(end - in); }
+    __device__ __forceinline__ unsigned long long bytepos() const { return (bitpos() + 7) >> 3; }
+    __device__ __forceinline__ void set_bytepos(unsigned long long p) { seek(p); }
 };
 
 enum { F_OK = 0, F_EOF = 1, F_INVALID = 2, F_MALFORMED = 3, F_FULL = 4 };
 constexpr unsigned long long ZL_EMPTY_BLOCK = 1ull << 63;   // zlib mode: in_used flag "the stream ended on a block of zero bytes"
 
+// Look-up entries (32 bit).  bits 0-3: code length (0 = not in the table); bits 4-5: kind; bits 8-11: extra bits; bits 16-31: value.
+//   literal/length table: kind 0 = literal (value = byte), 1 = length (value = base, flate.rs:296), 2 = end of block,
+//                         3 = bad: value 0 -> InvalidHuffmanCode (flate.rs:294, symbols 287.. and the kept off-by-one), 1 -> EXTRALENS[29] index panic
+//   distance table:       kind 0 = distance (value = base, flate.rs:307), 3 = bad (EXTRADIST index panic)
+enum { K_LIT = 0, K_LEN = 1, K_EOB = 2, K_BAD = 3 };
+__device__ __forceinline__ unsigned ll_entry(unsigned sym, unsigned len) {
+    if (sym < 256u) return len | (K_LIT << 4) | (sym << 16);
+    if (sym == 256u) return len | (K_EOB << 4);
+    const unsigned k = sym - 257u;
+    if (k > 29u) return len | (K_BAD << 4);                                              // flate.rs:294 (off-by-one kept)
+    if (k == 29u) return len | (K_BAD << 4) | (1u << 16);                                // EXTRALENS[29] index panic
+    return len | (K_LEN << 4) | ((unsigned)EXTRABITS[k] << 8) | ((unsigned)EXTRALENS[k] << 16);
+}
+__device__ __forceinline__ unsigned dd_entry(unsigned sym, unsigned len) {
+    if (sym >= 30u) return len | (K_BAD << 4);                                           // EXTRADIST index panic
+    return len | ((unsigned)EXTRADBITS[sym] << 8) | ((unsigned)EXTRADIST[sym] << 16);
+}
+
 // flate.rs:83-120 HuffmanTree::construct, warp-cooperative.  lens[0..n) in shared memory.  Returns false when the
-// set is over-subscribed (:98-103).  lutbits == 0 builds only count[]/symbol[].
-__device__ bool build_tree(Tree& t, uint16_t* symtab, uint16_t* lut, int lutbits, const uint8_t* lens, unsigned n) {
+// set is over-subscribed (:98-103).  KIND 0 builds only count[]/symbol[] (code-length tree), 1 the literal/length table, 2 the distance table.
+template <int KIND>
+__device__ bool build_tree(Tree& t, uint16_t* symtab, uint32_t* lut, const uint8_t* lens, unsigned n) {
+    constexpr int lutbits = KIND == 1 ? LB : KIND == 2 ? DB : 0;
     const unsigned lane = threadIdx.x & 31;
     __syncwarp();
     if (lane < 16) t.count[lane] = 0;
     if (lutbits) {
         uint4* l4 = reinterpret_cast<uint4*>(lut);
-        for (unsigned i = lane; i < (2u << lutbits) / 16; i += 32) l4[i] = make_uint4(0, 0, 0, 0);
+        for (unsigned i = lane; i < (4u << lutbits) / 16; i += 32) l4[i] = make_uint4(0, 0, 0, 0);
     }
     __syncwarp();
     for (unsigned s = lane; s < n; s += 32) atomicAdd(&t.count[lens[s]], 1u);
@@ -111,7 +160,7 @@ __device__ bool build_tree(Tree& t, uint16_t* symtab, uint16_t* lut, int lutbits
             if ((int)l <= lutbits) {
                 const unsigned code = t.first[l] + (pos - t.offs[l]);
                 const unsigned rev = __brev(code) >> (32 - l);
-                const uint16_t e = (uint16_t)((s << 4) | l);
+                const unsigned e = KIND == 1 ? ll_entry(s, l) : dd_entry(s, l);
                 for (unsigned j = rev; j < (1u << lutbits); j += 1u << l) lut[j] = e;
             }
         }
@@ -134,70 +183,67 @@ __device__ __forceinline__ int slow_decode(const Tree& t, const uint16_t* symtab
 
 struct St {
     Bits br;
-    uint8_t* out; unsigned long long cap, o;
+    uint8_t* out; unsigned cap, o;      // output cursor: streams and their outputs are < 2 GiB (rcz.h)
     int detail;
-    unsigned qn, qv;                  // literal queue: lane k holds literal k
 };
 
-__device__ __forceinline__ void flush_lits(St& s, unsigned lane) {
-    if (s.qn) { if (lane < s.qn) s.out[s.o - s.qn + lane] = (uint8_t)s.qv; s.qn = 0; }
+// a code that is not in the table: the bit-serial path over count[]/symbol[] (out of line; takes nothing by reference, so the
+// decoder state stays in registers).  Returns the table entry of the decoded symbol, 0 when no code matches within 15 bits.
+template <int KIND>
+__device__ __noinline__ unsigned huff_slow(const Tree* t, const uint16_t* symtab, unsigned bits15) {
+    unsigned l = 0;
+    const int v = slow_decode(*t, symtab, bits15, l);
+    if (v < 0) return 0u;
+    return KIND == 1 ? ll_entry((unsigned)v, l) : dd_entry((unsigned)v, l);
 }
 
-// one Huffman symbol: LUT, else the bit-serial path.  Returns F_* ; symbol in `sym`.
-__device__ __forceinline__ int huff(St& s, const Tree& t, const uint16_t* symtab, const uint16_t* lut, int lutbits, unsigned& sym) {
-    s.br.refill();
-    const unsigned e = lut[s.br.peek(lutbits)];
-    unsigned l = e & 15u;
-    if (l) sym = e >> 4;
-    else {
-        const int v = slow_decode(t, symtab, s.br.peek(15), l);
-        if (v < 0) {
-            if (s.br.bitpos + 15 > s.br.endbits) return F_EOF;
-            s.detail = RCZ_FL_NOT_ENOUGH_BITS; return F_INVALID;
-        }
-        sym = (unsigned)v;
-    }
-    s.br.consume(l);
-    return s.br.eof() ? F_EOF : F_OK;
-}
-
-// flate.rs:262-341 codes
+// flate.rs:262-341 codes.  Every lane of the warp tracks the same bit-reader state (the symbol chain is serial); what the lanes share out
+// is the LZ77 copy.  One table load gives the symbol, its extra-bit count and its base value; literals leave through lane 0.
 __device__ int codes(St& s, WarpSmem& w, unsigned lane) {
     for (;;) {
-        unsigned sym;
-        int r = huff(s, w.lt, w.lsym, w.llut, LB, sym);
-        if (r) return r;
-        if (sym < 256u) {
+        s.br.refill();                                                                  // >= 33 bits: code (<= 15) + length extra (<= 5) ...
+        unsigned e = w.llut[s.br.peek(LB)];
+        if ((e & 15u) == 0) {
+            e = huff_slow<1>(&w.lt, w.lsym, s.br.peek(15));
+            if (!e) { if (s.br.bitpos() + 15 > s.br.endbits()) return F_EOF; s.detail = RCZ_FL_NOT_ENOUGH_BITS; return F_INVALID; }
+        }
+        s.br.consume(e & 15u);
+        if (s.br.eof()) return F_EOF;
+        const unsigned kind = (e >> 4) & 3u;
+        if (kind == K_LIT) {
             if (s.o >= s.cap) return F_FULL;
-            if (lane == s.qn) s.qv = sym;
-            ++s.qn; ++s.o;
-            if (s.qn == 32) flush_lits(s, lane);
-        } else if (sym == 256u) return F_OK;
-        else if (sym < 290u) {
-            const unsigned k = sym - 257u;
-            if (k > 29u) { s.detail = RCZ_FL_INVALID_HUFFMAN_CODE; return F_INVALID; }   // flate.rs:294 (off-by-one kept)
-            if (k == 29u) return F_MALFORMED;                                           // EXTRALENS[29] index panic
-            const unsigned eb = EXTRABITS[k];
-            unsigned len = EXTRALENS[k] + s.br.take(eb);                                // bc >= 33 - 15 after the code: enough for 5 bits
-            if (s.br.eof()) return F_EOF;
-            unsigned ds;
-            r = huff(s, w.dt, w.dsym, w.dlut, DB, ds);
-            if (r) return r;
-            if (ds >= 30u) return F_MALFORMED;                                          // EXTRADIST index panic
-            const unsigned dbits = EXTRADBITS[ds];
-            const unsigned d = EXTRADIST[ds] + s.br.take(dbits);                        // bc >= 18 after the code: enough for 13 bits
-            if (s.br.eof()) return F_EOF;
-            const unsigned long long hist = s.o < HISTORY ? s.o : HISTORY;              // flate.rs:314
-            if (d > hist) { s.detail = RCZ_FL_INVALID_HUFFMAN_CODE; return F_INVALID; }
-            if (len > s.cap - s.o) return F_FULL;
-            flush_lits(s, lane);
-            __syncwarp();
-            const uint8_t* src = s.out + s.o - d;
-            uint8_t* dst = s.out + s.o;
-            for (unsigned j = lane; j < len; j += 32) dst[j] = src[j < d ? j : j % d];   // flate.rs:325-334
-            __syncwarp();
-            s.o += len;
-        } else { s.detail = RCZ_FL_INVALID_HUFFMAN_CODE; return F_INVALID; }
+            if (lane == 0) s.out[s.o] = (uint8_t)(e >> 16);
+            ++s.o;
+            continue;
+        }
+        if (kind == K_EOB) return F_OK;
+        if (kind == K_BAD) { if (e >> 16) return F_MALFORMED; s.detail = RCZ_FL_INVALID_HUFFMAN_CODE; return F_INVALID; }
+        const unsigned len = (e >> 16) + s.br.take((e >> 8) & 15u);                     // flate.rs:296-297
+        if (s.br.eof()) return F_EOF;
+        s.br.refill();                                                                  // distance code (<= 15) + extra (<= 13)
+        unsigned de = w.dlut[s.br.peek(DB)];
+        if ((de & 15u) == 0) {
+            de = huff_slow<2>(&w.dt, w.dsym, s.br.peek(15));
+            if (!de) { if (s.br.bitpos() + 15 > s.br.endbits()) return F_EOF; s.detail = RCZ_FL_NOT_ENOUGH_BITS; return F_INVALID; }
+        }
+        s.br.consume(de & 15u);
+        if (s.br.eof()) return F_EOF;
+        if (((de >> 4) & 3u) == K_BAD) return F_MALFORMED;                              // EXTRADIST index panic
+        const unsigned d = (de >> 16) + s.br.take((de >> 8) & 15u);                     // flate.rs:307-308
+        if (s.br.eof()) return F_EOF;
+        const unsigned hist = s.o < HISTORY ? s.o : HISTORY;                            // flate.rs:314
+        if (d > hist) { s.detail = RCZ_FL_INVALID_HUFFMAN_CODE; return F_INVALID; }
+        if (len > s.cap - s.o) return F_FULL;
+        __syncwarp();                                                                   // lane 0's literal stores are ordered before the copy's loads
+        const uint8_t* src = s.out + s.o - d;
+        uint8_t* dst = s.out + s.o;
+        if (d >= len) {                                                                 // source and destination do not overlap (the common case)
+            for (unsigned j = lane; j < len; j += 32) dst[j] = src[j];
+        } else {
+            for (unsigned j = lane; j < len; j += 32) dst[j] = src[j % d];              // flate.rs:325-334: the d bytes before the match, repeated
+        }
+        __syncwarp();
+        s.o += len;
     }
 }
 
@@ -211,10 +257,10 @@ __device__ int stored(St& s, unsigned lane) {
     if (p + 2 > n) return F_EOF;
     const unsigned nlen = (unsigned)s.br.in[p] | ((unsigned)s.br.in[p + 1] << 8);
     p += 2;
-    if (((~nlen) & 0xffffu) != len) { s.br.bitpos = p * 8; s.detail = RCZ_FL_INVALID_STATIC_SIZE; return F_INVALID; }
+    if (((~nlen) & 0xffffu) != len) { s.br.set_bytepos(p); s.detail = RCZ_FL_INVALID_STATIC_SIZE; return F_INVALID; }
     if (p + len > n) return F_EOF;
-    if (len > s.cap - s.o) { s.br.bitpos = p * 8; return F_FULL; }
-    flush_lits(s, lane);
+    if (len > s.cap - s.o) { s.br.set_bytepos(p); return F_FULL; }
+    __syncwarp();
     for (unsigned j = lane; j < len; j += 32) s.out[s.o + j] = s.br.in[p + j];
     __syncwarp();
     s.o += len;
@@ -226,11 +272,11 @@ __device__ int fixed_block(St& s, WarpSmem& w, unsigned lane) {                 
     __syncwarp();
     for (unsigned i = lane; i < 288; i += 32) w.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
     __syncwarp();
-    build_tree(w.lt, w.lsym, w.llut, LB, w.lens, 288);
+    build_tree<1>(w.lt, w.lsym, w.llut, w.lens, 288);
     __syncwarp();
     if (lane < 30) w.lens[lane] = 5;
     __syncwarp();
-    build_tree(w.dt, w.dsym, w.dlut, DB, w.lens, 30);
+    build_tree<2>(w.dt, w.dsym, w.dlut, w.lens, 30);
     return codes(s, w, lane);
 }
 
@@ -251,7 +297,7 @@ __device__ int dynamic_block(St& s, WarpSmem& w, unsigned lane) {               
         if (lane == 0) w.clen[CL_ORDER[i]] = (uint8_t)v;
     }
     __syncwarp();
-    if (!build_tree(w.ct, w.csym, nullptr, 0, w.clen, 19)) { s.detail = RCZ_FL_INVALID_HUFFMAN_TREE; return F_INVALID; }
+    if (!build_tree<0>(w.ct, w.csym, nullptr, w.clen, 19)) { s.detail = RCZ_FL_INVALID_HUFFMAN_TREE; return F_INVALID; }
     const unsigned total = hlit + hdist;
     unsigned i = 0, prev = 0;
     while (i < total) {
@@ -259,7 +305,7 @@ __device__ int dynamic_block(St& s, WarpSmem& w, unsigned lane) {               
         unsigned l;
         const int v = slow_decode(w.ct, w.csym, s.br.peek(15), l);
         if (v < 0) {
-            if (s.br.bitpos + 15 > s.br.endbits) return F_EOF;
+            if (s.br.bitpos() + 15 > s.br.endbits()) return F_EOF;
             s.detail = RCZ_FL_NOT_ENOUGH_BITS; return F_INVALID;
         }
         s.br.consume(l);
@@ -280,8 +326,8 @@ __device__ int dynamic_block(St& s, WarpSmem& w, unsigned lane) {               
     }
     if (i > total) { s.detail = RCZ_FL_INVALID_HUFFMAN_TREE_HEADER; return F_INVALID; }
     __syncwarp();
-    if (!build_tree(w.lt, w.lsym, w.llut, LB, w.lens, hlit)) { s.detail = RCZ_FL_INVALID_HUFFMAN_TREE; return F_INVALID; }
-    if (!build_tree(w.dt, w.dsym, w.dlut, DB, w.lens + hlit, hdist)) { s.detail = RCZ_FL_INVALID_HUFFMAN_TREE; return F_INVALID; }
+    if (!build_tree<1>(w.lt, w.lsym, w.llut, w.lens, hlit)) { s.detail = RCZ_FL_INVALID_HUFFMAN_TREE; return F_INVALID; }
+    if (!build_tree<2>(w.dt, w.dsym, w.dlut, w.lens + hlit, hdist)) { s.detail = RCZ_FL_INVALID_HUFFMAN_TREE; return F_INVALID; }
     return codes(s, w, lane);
 }
 
@@ -298,11 +344,12 @@ inflate_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__
         const unsigned long long n = in_len[sidx];
         s.br.init(in_base + in_off[sidx], n);
         s.out = out_base + out_off[sidx];
-        s.cap = out_cap[sidx]; s.o = 0; s.detail = 0; s.qn = 0; s.qv = 0;
+        { const unsigned long long c64 = out_cap[sidx]; s.cap = c64 > 0x7fffffffull ? 0x7fffffffu : (unsigned)c64; }
+        s.o = 0; s.detail = 0;
         int r = F_OK;
         bool empty_block = false;
         for (;;) {                                                                   // flate.rs:195-206 block
-            const unsigned long long before = s.o;
+            const unsigned before = s.o;
             s.br.refill();
             const unsigned bfinal = s.br.take(1);
             if (s.br.eof()) { r = F_EOF; break; }
@@ -316,7 +363,6 @@ inflate_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__
             // zlib.rs:106-109: under zlib::Decoder a block of zero bytes makes flate's read() return Ok(0) and ends the stream there
             if (zlib_mode && s.o == before) { empty_block = true; break; }
         }
-        flush_lits(s, lane);
         __syncwarp();
         if (lane == 0) {
             out_len[sidx] = s.o;

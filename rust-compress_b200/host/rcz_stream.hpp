@@ -253,6 +253,68 @@ template <class W> class Encoder {
     void encode_block() { detail::write_u32_le(w_, (uint32_t)buf_.size() | 0x80000000u); w_.write(buf_.data(), buf_.size()); buf_.clear(); }
     W w_; std::vector<uint8_t> buf_; bool wrote_header_ = false; size_t limit_ = 256 * 1024;
 };
+
+// lz4.rs:616-627 encode_block: appends the compressed block to `output`, returns its size (0 when the input is too large)
+inline size_t encode_block(Context& ctx, const uint8_t* input, size_t n, std::vector<uint8_t>& output) {
+    const int64_t bound = compression_bound((uint32_t)n);
+    if (n > 0x7e000000u || bound < 0) return 0;
+    uint64_t off = 0, len = n, cap = (uint64_t)bound, olen = 0; int32_t st = 0;
+    const size_t old = output.size();
+    output.resize(old + (size_t)cap + 64);
+    std::vector<uint8_t> in(input, input + n); in.resize(n + 64);
+    ctx.check(rcz_lz4_encode_blocks(ctx.get(), in.data(), &off, &len, output.data() + old, &off, &cap, &olen, &st, 1, RCZ_MEM_HOST), "rcz_lz4_encode_blocks");
+    output.resize(old + (st == RCZ_OK ? (size_t)olen : 0));
+    if (st != RCZ_OK) throw error_from_status(st, "lz4::encode_block");
+    return (size_t)olen;
+}
+
+// The frame Encoder the reference left as a stub (`compress()` returns false, lz4.rs:543-545: every block goes out raw): same frame
+// layout and block size (FLG 0x60, BD 0x50 = 256 KiB, header checksum byte 0, two zero words at the end, lz4.rs:526,550-575), but
+// every full block is compressed with `encode_block`, `batch_blocks` of them per C-ABI call, and written compressed
+// when that is smaller than the block (else raw, high bit set — what lz4.rs:567-575 does for all of them).
+template <class W> class CompressingEncoder {
+  public:
+    size_t batch_blocks = 64;
+    CompressingEncoder(Context& ctx, W w) : ctx_(ctx), w_(std::move(w)) {}
+    size_t write(const uint8_t* buf, size_t len) {
+        if (!wrote_header_) { detail::write_u32_le(w_, MAGIC); const uint8_t h[3] = {0x60, 0x50, 0}; w_.write(h, 3); wrote_header_ = true; }
+        buf_.insert(buf_.end(), buf, buf + len);
+        while (buf_.size() - done_ >= limit_ * batch_blocks) encode_blocks(batch_blocks);
+        return len;
+    }
+    void flush() { encode_blocks((buf_.size() - done_ + limit_ - 1) / limit_); w_.flush(); }
+    W finish() { flush(); detail::write_u32_le(w_, 0); detail::write_u32_le(w_, 0); return std::move(w_); }
+
+  private:
+    void encode_blocks(size_t nb) {
+        if (nb == 0) return;
+        std::vector<uint64_t> ioff(nb), ilen(nb), ocap(nb), olen(nb);
+        std::vector<int32_t> st(nb);
+        for (size_t i = 0; i < nb; ++i) {
+            ioff[i] = done_ + i * limit_;
+            ilen[i] = std::min(limit_, buf_.size() - (size_t)ioff[i]);
+            ocap[i] = (uint64_t)compression_bound((uint32_t)ilen[i]);
+        }
+        std::vector<uint64_t> ooff = detail::prefix(ocap, 16);
+        std::vector<uint8_t> enc((size_t)(ooff.back() + ocap.back()) + 64);
+        buf_.resize(buf_.size() + 64);
+        ctx_.check(rcz_lz4_encode_blocks(ctx_.get(), buf_.data(), ioff.data(), ilen.data(), enc.data(), ooff.data(), ocap.data(), olen.data(), st.data(), nb,
+                                         RCZ_MEM_HOST), "rcz_lz4_encode_blocks");
+        buf_.resize(buf_.size() - 64);
+        for (size_t i = 0; i < nb; ++i) {
+            if (st[i] == RCZ_OK && olen[i] > 0 && olen[i] < ilen[i]) {
+                detail::write_u32_le(w_, (uint32_t)olen[i]);
+                w_.write(enc.data() + ooff[i], (size_t)olen[i]);
+            } else {
+                detail::write_u32_le(w_, (uint32_t)ilen[i] | 0x80000000u);
+                w_.write(buf_.data() + ioff[i], (size_t)ilen[i]);
+            }
+        }
+        done_ += nb * limit_;
+        if (done_ >= buf_.size()) { buf_.clear(); done_ = 0; }
+    }
+    Context& ctx_; W w_; std::vector<uint8_t> buf_; size_t done_ = 0; bool wrote_header_ = false; size_t limit_ = 256 * 1024;
+};
 }  // namespace lz4
 
 // ================================================================================================ bwt

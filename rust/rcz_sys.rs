@@ -55,6 +55,9 @@ extern "C" {
     pub fn rcz_lz4_decode_blocks(ctx: *mut rcz_ctx, in_base: *const c_void, in_off: *const u64, in_len: *const u64,
                                  out_base: *mut c_void, out_off: *const u64, out_cap: *const u64,
                                  out_len: *mut u64, status: *mut i32, nblocks: usize, mem_kind: c_int) -> c_int;
+    pub fn rcz_lz4_encode_blocks(ctx: *mut rcz_ctx, in_base: *const c_void, in_off: *const u64, in_len: *const u64,
+                                 out_base: *mut c_void, out_off: *const u64, out_cap: *const u64,
+                                 out_len: *mut u64, status: *mut i32, nblocks: usize, mem_kind: c_int) -> c_int;
     pub fn rcz_lz4_compression_bound(size: u32) -> i64;
 
     // ---- bwt/mod.rs:136-204, 223-294

@@ -93,6 +93,26 @@ int main(int argc, char** argv) {
         bytes out = read_to_end(d);
         CHECK(out.size() == 100000 && out == bytes(100000, 0));
     });
+    run("lz4::CompressingEncoder (the stub at lz4.rs:543-545 filled in) round trips through lz4::Decoder", [&] {
+        bytes big; for (int i = 0; i < 300; ++i) big.insert(big.end(), txt.begin(), txt.end());   // > 256 KiB: several blocks
+        bytes noise(300000); uint32_t x = 12345; for (auto& b : noise) { x = x * 1664525u + 1013904223u; b = (uint8_t)(x >> 24); }   // stays raw
+        int idx = 0;
+        for (const bytes& input : {lit("test"), lit(""), txt, big, noise}) {
+            rcz::lz4::CompressingEncoder<rcz::VecWriter> e(ctx, rcz::VecWriter());
+            e.write(input.data(), input.size());
+            bytes enc = e.finish().v;
+            if (idx == 3) CHECK(enc.size() < input.size() / 2);                   // the repeated text compresses
+            if (idx == 4) CHECK(enc.size() >= input.size());                      // the noise goes out raw
+            ++idx;
+            rcz::lz4::Decoder<rcz::SliceReader> d(ctx, rcz::SliceReader(enc));
+            CHECK(read_to_end(d) == input);
+        }
+        bytes out;                                                              // encode_block / decode_block free functions (lz4.rs:602-627)
+        size_t n = rcz::lz4::encode_block(ctx, txt.data(), txt.size(), out);
+        CHECK(n == 2724 && out.size() == 2724);
+        bytes back;
+        CHECK(rcz::lz4::decode_block(ctx, out.data(), out.size(), back) == txt.size() && back == txt);
+    });
     run("lz4::decode_block + errors", [&] {
         bytes f = load("ref_test.lz4.3");
         uint32_t n = (uint32_t)f[7] | ((uint32_t)f[8] << 8) | ((uint32_t)f[9] << 16) | ((uint32_t)f[10] << 24);
