@@ -37,7 +37,7 @@ def main():
     rcz = importlib.import_module("rust-compress_b200")
     opt = {sys.argv[i][2:]: int(sys.argv[i + 1]) for i in range(1, len(sys.argv) - 1) if sys.argv[i].startswith("--")}
     args = [a for a in sys.argv[1:] if not a.startswith("--") and not a.isdigit()]
-    ops = args or ["lz4", "ibwt", "bwt", "flate", "zlib", "mtf", "dc", "ari", "rle"]
+    ops = args or ["lz4", "lz4enc", "ibwt", "bwt", "flate", "zlib", "mtf", "dc", "ari", "rle"]
     nblk, reps = opt.get("blocks", 32), opt.get("reps", 5)
     ctx = rcz.Context(device=0)
     ctx.set_stream(torch.cuda.current_stream())
@@ -63,6 +63,25 @@ def main():
             ms = timed(lambda: ctx.lz4_decode_blocks(d_in, ioff, ilen, d_out, off, n, async_=True), reps)
             assert torch.equal(d_out, torch.from_numpy(raw).cuda())
             report("lz4_decode_" + kind, UNIT * nblk, ms, {"C_bytes": int(ilen.sum()), "stage_ms": ctx.last_stage_ms()})
+    if "lz4enc" in ops:
+        for kind in ("lzsyn", "hextext", "random"):
+            raw = gen.units(kind, gen.unit_seed(2, 0), UNIT, nblk)
+            bound = oracle.lz4_compression_bound(UNIT)
+            stride = (bound + 15) // 16 * 16
+            coff = np.arange(nblk, dtype=np.uint64) * stride
+            d_raw = torch.from_numpy(raw).cuda()
+            d_enc = torch.zeros(stride * nblk + 64, dtype=torch.uint8, device="cuda")
+            r5 = {}
+
+            def le():
+                r5["o"] = ctx.lz4_encode_blocks(d_raw, off, n, d_enc, coff, np.full(nblk, bound, np.uint64))
+            ms = timed(le, max(2, reps // 2))
+            clen, st = r5["o"]
+            assert (st == 0).all()
+            d_back = torch.zeros(UNIT * nblk, dtype=torch.uint8, device="cuda")
+            ctx.lz4_decode_blocks(d_enc, coff, clen, d_back, off, n)
+            assert torch.equal(d_back, d_raw)
+            report("lz4_encode_" + kind, UNIT * nblk, ms, {"C_bytes": int(clen.sum())})
     if "ibwt" in ops or "bwt" in ops:
         for kind in ("random", "hextext"):
             raw = gen.units(kind, gen.unit_seed(3, 0), UNIT, nblk)
