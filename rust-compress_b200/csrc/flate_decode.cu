@@ -100,9 +100,12 @@ constexpr unsigned long long ZL_EMPTY_BLOCK = 1ull << 63;   // zlib mode: in_use
 
 // Look-up entries (32 bit).  bits 0-3: code length (0 = not in the table); bits 4-5: kind; bits 8-11: extra bits; bits 16-31: value.
 //   literal/length table: kind 0 = literal (value = byte), 1 = length (value = base, flate.rs:296), 2 = end of block,
+//                         a literal entry with bit 6 set holds TWO literals whose codes fit the table index together: bits 0-3 = both
+//                         lengths, bits 8-11 = length of the first, bits 16-23 / 24-31 = first / second byte
 //                         3 = bad: value 0 -> InvalidHuffmanCode (flate.rs:294, symbols 287.. and the kept off-by-one), 1 -> EXTRALENS[29] index panic
 //   distance table:       kind 0 = distance (value = base, flate.rs:307), 3 = bad (EXTRADIST index panic)
 enum { K_LIT = 0, K_LEN = 1, K_EOB = 2, K_BAD = 3 };
+constexpr unsigned E_PAIR = 1u << 6;
 __device__ __forceinline__ unsigned ll_entry(unsigned sym, unsigned len) {
     if (sym < 256u) return len | (K_LIT << 4) | (sym << 16);
     if (sym == 256u) return len | (K_EOB << 4);
@@ -166,6 +169,22 @@ __device__ bool build_tree(Tree& t, uint16_t* symtab, uint32_t* lut, const uint8
         }
     }
     __syncwarp();
+    if (KIND == 1) {
+        // second pass: an index whose low bits are a literal code and whose remaining bits decide another literal code gets both.
+        // In-place is safe: a converted entry still tells its first literal (length in bits 8-11, byte in bits 16-23).
+        for (unsigned j = lane; j < (1u << lutbits); j += 32) {
+            const unsigned e1 = lut[j];
+            if ((e1 & 0x70u) != 0 || (e1 & 15u) == 0) continue;                       // not a single literal
+            const unsigned l1 = e1 & 15u;
+            if (l1 >= (unsigned)lutbits) continue;
+            const unsigned e2 = lut[j >> l1];
+            if ((e2 & 0x30u) != 0 || (e2 & 15u) == 0) continue;                       // the next code is not a literal in the table
+            const unsigned l2 = (e2 & E_PAIR) ? (e2 >> 8) & 15u : e2 & 15u;
+            if (l1 + l2 > (unsigned)lutbits) continue;                                // ... or not decided by the bits that are left
+            lut[j] = (l1 + l2) | E_PAIR | (l1 << 8) | (e1 & 0x00ff0000u) | (((e2 >> 16) & 255u) << 24);
+        }
+        __syncwarp();
+    }
     return true;
 }
 
@@ -203,19 +222,37 @@ __device__ int codes(St& s, WarpSmem& w, unsigned lane) {
     for (;;) {
         s.br.refill();                                                                  // >= 33 bits: code (<= 15) + length extra (<= 5) ...
         unsigned e = w.llut[s.br.peek(LB)];
+        // ---- literal batch: while no padding bit has entered the buffer (no EOF possible) and the output has room, up to three table
+        // look-ups (<= 27 of the >= 33 buffered bits), each one or two literals, go out with ONE store (lane k writes byte k)
+        if (s.br.pad == 0 && s.cap - s.o >= 6u) {
+            unsigned long long acc = 0; unsigned cnt = 0, k = 0;
+#pragma unroll
+            for (; k < 3; ++k) {
+                if ((e & 0x30u) != 0 || (e & 15u) == 0) break;                          // not a literal entry of the table
+                s.br.consume(e & 15u);
+                acc |= (unsigned long long)(e >> 16) << (8u * cnt);
+                cnt += 1u + ((e >> 6) & 1u);
+                if (k < 2) e = w.llut[s.br.peek(LB)];                                   // (>= 15 bits are left after two look-ups)
+            }
+            if (cnt) { if (lane < cnt) s.out[s.o + lane] = (uint8_t)(acc >> (8u * lane)); s.o += cnt; }
+            if (k == 3) continue;
+            s.br.refill();                                                              // the symbol that ended the batch takes the careful path
+        }
         if ((e & 15u) == 0) {
             e = huff_slow<1>(&w.lt, w.lsym, s.br.peek(15));
             if (!e) { if (s.br.bitpos() + 15 > s.br.endbits()) return F_EOF; s.detail = RCZ_FL_NOT_ENOUGH_BITS; return F_INVALID; }
         }
-        s.br.consume(e & 15u);
-        if (s.br.eof()) return F_EOF;
         const unsigned kind = (e >> 4) & 3u;
-        if (kind == K_LIT) {
+        if (kind == K_LIT) {                                                            // one literal at a time (a pair entry gives its first)
+            s.br.consume((e & E_PAIR) ? (e >> 8) & 15u : e & 15u);
+            if (s.br.eof()) return F_EOF;
             if (s.o >= s.cap) return F_FULL;
             if (lane == 0) s.out[s.o] = (uint8_t)(e >> 16);
             ++s.o;
             continue;
         }
+        s.br.consume(e & 15u);
+        if (s.br.eof()) return F_EOF;
         if (kind == K_EOB) return F_OK;
         if (kind == K_BAD) { if (e >> 16) return F_MALFORMED; s.detail = RCZ_FL_INVALID_HUFFMAN_CODE; return F_INVALID; }
         const unsigned len = (e >> 16) + s.br.take((e >> 8) & 15u);                     // flate.rs:296-297
