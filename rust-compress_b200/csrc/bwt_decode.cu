@@ -181,16 +181,17 @@ ibwt_scatter_kernel(const uint8_t* __restrict__ in_base, const Blk* __restrict__
 
 // ------------------------------------------------------------------------------------------ D: walk
 struct Desc { unsigned len, succ; };
-constexpr unsigned SLOT_HDR = 8;           // a chain slot = its descriptor (len, successor chain) + `cap` bytes of data: one record, one sector for a short chain
 
 __global__ void __launch_bounds__(256)
 ibwt_walk_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned total_work, const unsigned* __restrict__ P_base,
-                 uint8_t* __restrict__ scratch_base, unsigned* __restrict__ chain_ctr, unsigned* __restrict__ queue) {
+                 uint8_t* __restrict__ scratch_base, Desc* __restrict__ desc_base, unsigned* __restrict__ chain_ctr,
+                 unsigned* __restrict__ queue) {
     const unsigned lane = threadIdx.x & 31;
     bool active = false, done = false;
     // per-chain state
-    const unsigned* P = nullptr; uint8_t* slotp = nullptr; uint8_t* slots = nullptr; unsigned* ctr = nullptr;
+    const unsigned* P = nullptr; uint8_t* slotp = nullptr; Desc* desc = nullptr; unsigned* ctr = nullptr;
     unsigned cur = 0, count = 0, chain = 0, mask = 0, slog = 0, cap = 0, hops = 0, nmax = 0, maxch = 0;
+    unsigned long long scratch_off = 0;
     unsigned b0 = 0, b1 = 0, b2 = 0, b3 = 0;
     // block of the lane's previous work item: consecutive tickets almost always stay inside it, so the block table is searched
     // (and the dozen per-block values reloaded) only when a ticket leaves [w_lo, w_hi)
@@ -214,14 +215,15 @@ ibwt_walk_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned total_
                         const Blk bk = blks[lo];
                         w_lo = bk.work0; w_hi = bk.work0 + bk.K + 1; bK = bk.K; borigin = bk.origin;
                         P = P_base + bk.p_off;
+                        desc = desc_base + bk.chain0;
                         ctr = chain_ctr + lo;
-                        slots = scratch_base + bk.scratch_off;
+                        scratch_off = bk.scratch_off;
                         slog = bk.stride_log2; mask = (1u << slog) - 1u; cap = bk.cap; nmax = bk.n; maxch = bk.max_chains;
                         pf_off = bk.pf_off; pf_elems = bk.pf_elems;
                     }
                     chain = wi - w_lo;
                     cur = chain < bK ? (chain << slog) : borigin;
-                    slotp = slots + (size_t)chain * (cap + SLOT_HDR);
+                    slotp = scratch_base + scratch_off + (size_t)chain * cap;
                     count = 0; hops = 0;
                     active = true;
                     // (optional) every chain start pulls its share of a LATER block's link table into L2
@@ -234,7 +236,8 @@ ibwt_walk_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned total_
                         }
                     }
                     if (chain < bK && cur == borigin) {            // no row links to `origin`: this sampled chain is unreachable,
-                        *reinterpret_cast<uint2*>(slotp) = make_uint2(0u, SUCC_END);   // and the origin chain (id K) walks the same rows
+                        Desc d; d.len = 0; d.succ = SUCC_END;      // and the origin chain (id K) walks the same rows
+                        desc[chain] = d;
                         active = false;
                     }
                 }
@@ -255,29 +258,26 @@ ibwt_walk_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned total_
                 else if (k < 12) b2 = (k == 8 ? 0u : b2) | (byte << sh);
                 else b3 = (k == 12 ? 0u : b3) | (byte << sh);
                 ++count; ++hops;
+                if ((count & 15u) == 0) __stcs(reinterpret_cast<uint4*>(slotp + count - 16), make_uint4(b0, b1, b2, b3));   // streaming: keep L2 for the tables
                 const bool at_end = (nxt == END24) || hops > nmax;
                 const bool at_sample = !at_end && (nxt & mask) == 0;
-                const bool stop = at_end || at_sample;
-                const bool cut = !stop && count == cap;                  // slot full: the chain continues in a fresh slot
-                if ((count & 15u) == 0 || stop || cut) {                  // the 16-byte piece that holds byte count-1 leaves the registers
-                    const unsigned k16 = ((count - 1u) & 15u) + 1u;       // valid bytes in it
-                    if (k16 <= 4) { b1 = 0; b2 = 0; b3 = 0; } else if (k16 <= 8) { b2 = 0; b3 = 0; } else if (k16 <= 12) b3 = 0;
-                    const unsigned po = (count - 1u) & ~15u;              // data offset of the piece
-                    uint8_t* d8 = slotp + SLOT_HDR + po;                  // 8-byte aligned: two 8-byte stores (the second only inside the slot)
-                    *reinterpret_cast<uint2*>(d8) = make_uint2(b0, b1);
-                    if (po + 8u < cap) *reinterpret_cast<uint2*>(d8 + 8) = make_uint2(b2, b3);
-                }
-                if (stop) {
-                    *reinterpret_cast<uint2*>(slotp) = make_uint2(count, at_end ? SUCC_END : (nxt >> slog));
+                if (at_end || at_sample) {
+                    if (count & 15u) {
+                        if ((count & 15u) <= 4) { b1 = 0; b2 = 0; b3 = 0; } else if ((count & 15u) <= 8) { b2 = 0; b3 = 0; } else if ((count & 15u) <= 12) b3 = 0;
+                        __stcs(reinterpret_cast<uint4*>(slotp + (count & ~15u)), make_uint4(b0, b1, b2, b3));
+                    }
+                    Desc d; d.len = count; d.succ = at_end ? SUCC_END : (nxt >> slog);
+                    desc[chain] = d;
                     active = false;
                 } else {
                     cur = nxt;
-                    if (cut) {
+                    if (count == cap) {                       // slot full: continue in a fresh chain slot
                         const unsigned nc = atomicAdd(ctr, 1u);
-                        *reinterpret_cast<uint2*>(slotp) = make_uint2(count, nc < maxch ? nc : SUCC_END);
+                        Desc d; d.len = count; d.succ = nc < maxch ? nc : SUCC_END;
+                        desc[chain] = d;
                         if (nc >= maxch) active = false;      // cannot happen (see max_chains); never write out of bounds
                         chain = nc;
-                        slotp = slots + (size_t)chain * (cap + SLOT_HDR);
+                        slotp = scratch_base + scratch_off + (size_t)chain * cap;
                         count = 0;
                     }
                 }
@@ -309,14 +309,13 @@ __device__ __forceinline__ HeadGeom head_geom(const Blk& bk, const unsigned* cha
 }
 
 __global__ void __launch_bounds__(256)
-ibwt_heads_kernel(const Blk* __restrict__ blks, const uint8_t* __restrict__ scratch_base, const unsigned* __restrict__ chain_ctr,
+ibwt_heads_kernel(const Blk* __restrict__ blks, const Desc* __restrict__ desc_base, const unsigned* __restrict__ chain_ctr,
                   unsigned long long* __restrict__ node_base, unsigned hlog) {
     const unsigned b = blockIdx.y;
     const Blk bk = blks[b];
     if (bk.skip) return;
     const HeadGeom g = head_geom(bk, chain_ctr, b, hlog);
-    const uint8_t* slots = scratch_base + bk.scratch_off;
-    const unsigned stride = bk.cap + SLOT_HDR;
+    const Desc* desc = desc_base + bk.chain0;
     unsigned long long* node = node_base + bk.head0;
     for (unsigned h = blockIdx.x * blockDim.x + threadIdx.x; h < g.H; h += gridDim.x * blockDim.x) {
         unsigned cur = h < g.nreg ? h << hlog : g.K;
@@ -324,9 +323,9 @@ ibwt_heads_kernel(const Blk* __restrict__ blks, const uint8_t* __restrict__ scra
         unsigned nxt_head = h;                                          // self-loop unless the walk reaches a head or END
         if (cur < g.nch) {
             for (unsigned steps = 0; steps <= g.nch; ++steps) {
-                const uint2 d = *reinterpret_cast<const uint2*>(slots + (size_t)cur * stride);   // (len, succ)
-                acc += d.x;
-                const unsigned s = d.y;
+                const Desc d = desc[cur];
+                acc += d.len;
+                const unsigned s = d.succ;
                 if (s == SUCC_END) { nxt_head = g.H; break; }
                 if (s >= g.nch) break;                                  // dangling link: never reaches END
                 if (s == g.K) { nxt_head = g.nreg; break; }
@@ -379,13 +378,10 @@ ibwt_headrank_kernel(const Blk* __restrict__ blks, const unsigned* __restrict__ 
     if (tid == 0) { out_len[b] = bk.bad ? 0 : total; status[b] = bk.bad ? RCZ_E_MALFORMED : RCZ_OK; }
 }
 
-// len bytes from the (8-byte-aligned) data part of a chain slot to an arbitrarily aligned destination
+// len bytes from the 16-byte-aligned chain slot to an arbitrarily aligned destination
 __device__ __forceinline__ void copy_chain(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, unsigned len) {
     for (unsigned base = 0; base < len; base += 16) {
-        const uint2 qa = *reinterpret_cast<const uint2*>(src + base);
-        uint2 qb = make_uint2(0u, 0u);
-        if (len - base > 8u) qb = *reinterpret_cast<const uint2*>(src + base + 8);
-        const uint4 q = make_uint4(qa.x, qa.y, qb.x, qb.y);
+        const uint4 q = __ldcs(reinterpret_cast<const uint4*>(src + base));      // read once: streaming
         const unsigned m = len - base < 16u ? len - base : 16u;
         const unsigned wv[5] = {q.x, q.y, q.z, q.w, 0u};
         uint8_t* d = dst + base;
@@ -405,16 +401,16 @@ __device__ __forceinline__ void copy_chain(const uint8_t* __restrict__ src, uint
 }
 
 __global__ void __launch_bounds__(256)
-ibwt_place_kernel(const Blk* __restrict__ blks, const uint8_t* __restrict__ scratch_base,
+ibwt_place_kernel(const Blk* __restrict__ blks, const uint8_t* __restrict__ scratch_base, const Desc* __restrict__ desc_base,
                   const unsigned* __restrict__ chain_ctr, const unsigned long long* __restrict__ node_base, uint8_t* __restrict__ out_base,
                   unsigned hlog) {
     const unsigned b = blockIdx.y;
     const Blk bk = blks[b];
     if (bk.skip) return;
     const HeadGeom g = head_geom(bk, chain_ctr, b, hlog);
+    const Desc* desc = desc_base + bk.chain0;
     const unsigned long long* node = node_base + bk.head0;
     const uint8_t* scratch = scratch_base + bk.scratch_off;
-    const unsigned stride = bk.cap + SLOT_HDR;
     uint8_t* out = out_base + bk.out_off;
     for (unsigned h = blockIdx.x * blockDim.x + threadIdx.x; h < g.H; h += gridDim.x * blockDim.x) {
         unsigned off = (unsigned)node[h];
@@ -423,12 +419,11 @@ ibwt_place_kernel(const Blk* __restrict__ blks, const uint8_t* __restrict__ scra
         if (cur >= g.nch) continue;
         if (h < g.nreg && cur == g.K) continue;                         // the origin chain is walked once, as head `nreg`
         for (unsigned steps = 0; steps <= g.nch; ++steps) {
-            const uint8_t* slot = scratch + (size_t)cur * stride;
-            const uint2 d = *reinterpret_cast<const uint2*>(slot);       // (len, succ): same sector as the first 24 data bytes
-            if (off + d.x > bk.n) break;                                // (a well-formed block never gets here)
-            copy_chain(slot + SLOT_HDR, out + off, d.x);
-            off += d.x;
-            const unsigned s = d.y;
+            const Desc d = desc[cur];
+            if (off + d.len > bk.n) break;                              // (a well-formed block never gets here)
+            copy_chain(scratch + (size_t)cur * bk.cap, out + off, d.len);
+            off += d.len;
+            const unsigned s = d.succ;
             if (s == SUCC_END || s >= g.nch || s == g.K || (s & g.mask) == 0) break;
             cur = s;
         }
@@ -509,7 +504,7 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
         while ((n >> slog) > (1u << 19)) ++slog;              // keep <= 512 Ki sampled rows per block
         b.stride_log2 = slog;
         b.K = (unsigned)((n + (1ull << slog) - 1) >> slog);
-        b.cap = std::max(24u, (4u << slog) - SLOT_HDR);       // data bytes per chain slot (slot = 8-byte descriptor + data, a multiple of 32): P(longer) ~ e^-3.5
+        b.cap = std::max(32u, 4u << slog);                    // bytes per chain slot: P(chain longer than 4 strides) = e^-4
         b.max_chains = b.K + 1 + (unsigned)(n / b.cap) + 1;   // every row is walked at most once => <= n/cap continuations
         while (((b.max_chains >> hlog) + 3) > RANK_MAX_HEADS) ++hlog;   // one head sampling for the whole call
         max_mc = std::max(max_mc, b.max_chains);
@@ -517,7 +512,7 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
         for (unsigned t = 0; t < b.ntiles; ++t) tile2blk.push_back((unsigned)(i - cur.b0));
         cur.ntiles += b.ntiles;
         cur.p_elems += (n + 63) & ~63ull;
-        cur.scratch_bytes += (unsigned long long)b.max_chains * (b.cap + SLOT_HDR);
+        cur.scratch_bytes += (unsigned long long)b.max_chains * b.cap;
         cur.chains += b.max_chains;
         cur.work += b.K + 1;
     }
@@ -558,14 +553,15 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
     void *wP, *wS, *wM;
     st = ctx_ws(c, WS_A, (size_t)max_p * 4 + 256, &wP); if (st) return st;
     st = ctx_ws(c, WS_B, (size_t)max_scratch + 256, &wS); if (st) return st;
-    // misc: tile_hist | cbase | head nodes | chain_ctr | queue
-    const size_t sz_hist = (size_t)max_tiles * 256 * 4, sz_cb = max_nb * 256 * 4, sz_coff = (size_t)max_heads * 8,
+    // misc: tile_hist | cbase | desc | head nodes | chain_ctr | queue
+    const size_t sz_hist = (size_t)max_tiles * 256 * 4, sz_cb = max_nb * 256 * 4, sz_desc = (size_t)max_chains * 8, sz_coff = (size_t)max_heads * 8,
                  sz_ctr = max_nb * 4;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    st = ctx_ws(c, WS_C, al(sz_hist) + al(sz_cb) + al(sz_coff) + al(sz_ctr) + 512, &wM); if (st) return st;
+    st = ctx_ws(c, WS_C, al(sz_hist) + al(sz_cb) + al(sz_desc) + al(sz_coff) + al(sz_ctr) + 512, &wM); if (st) return st;
     uint8_t* m = (uint8_t*)wM;
     unsigned* tile_hist = (unsigned*)m; m += al(sz_hist);
     unsigned* cbase = (unsigned*)m; m += al(sz_cb);
+    Desc* desc = (Desc*)m; m += al(sz_desc);
     unsigned long long* nodes = (unsigned long long*)m; m += al(sz_coff);
     unsigned* chain_ctr = (unsigned*)m; m += al(sz_ctr);
     unsigned* queue = (unsigned*)m;
@@ -592,12 +588,12 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
         RCZ_KLAUNCH(c, ibwt_scatter_kernel, g.ntiles, NT_TILE, sizeof(ScatterSmem), din, dblk, dt2b, tile_hist, cbase, (unsigned*)wP);
         if (mark) { st = ctx_stage_mark(c, 1); if (st) return st; }
         const unsigned walk_grid = (unsigned)std::min<unsigned long long>((g.work + 255) / 256, (unsigned long long)c->sm_count * tune_ctas);
-        RCZ_KLAUNCH(c, ibwt_walk_kernel, walk_grid, 256, 0, dblk, nb, (unsigned)g.work, (const unsigned*)wP, (uint8_t*)wS, chain_ctr, queue);
+        RCZ_KLAUNCH(c, ibwt_walk_kernel, walk_grid, 256, 0, dblk, nb, (unsigned)g.work, (const unsigned*)wP, (uint8_t*)wS, desc, chain_ctr, queue);
         if (mark) { st = ctx_stage_mark(c, 2); if (st) return st; }
         const unsigned hx = (unsigned)std::min<unsigned long long>(((max_mc >> hlog) + 3 + 255) / 256, std::max<unsigned long long>(1, (unsigned long long)c->sm_count * 16 / nb));
-        RCZ_KLAUNCH(c, ibwt_heads_kernel, dim3(hx, nb), 256, 0, dblk, (const uint8_t*)wS, chain_ctr, nodes, hlog);
+        RCZ_KLAUNCH(c, ibwt_heads_kernel, dim3(hx, nb), 256, 0, dblk, desc, chain_ctr, nodes, hlog);
         RCZ_KLAUNCH(c, ibwt_headrank_kernel, nb, RANK_NT, rank_smem, dblk, chain_ctr, nodes, d_len, d_st, hlog);
-        RCZ_KLAUNCH(c, ibwt_place_kernel, dim3(hx, nb), 256, 0, dblk, (const uint8_t*)wS, chain_ctr, nodes, dout, hlog);
+        RCZ_KLAUNCH(c, ibwt_place_kernel, dim3(hx, nb), 256, 0, dblk, (const uint8_t*)wS, desc, chain_ctr, nodes, dout, hlog);
         if (mark) { st = ctx_stage_mark(c, 3); if (st) return st; mark = false; }
     }
     st = ctx_timer_end(c); if (st) return st;
