@@ -424,7 +424,8 @@ def leg_lz4(env, args):
     assert int((status != 0).sum().item()) == 0, "decode reported errors"
     assert torch.equal(d_out, torch.from_numpy(w["raw"]).cuda()), "device output differs from the generator's bytes"
 
-    # ---- decode + final gather (N > 1)
+    # ---- decode + final gather (N > 1): (a) ncclAllGather after the decode; (b) fused: the materialise kernel stores every output chunk
+    # into the peers' gathered buffers as well (symmetric memory over NVLink / NVSwitch), no separate collective
     gather = None
     if world > 1:
         flat = torch.empty(w["U"] * world, dtype=torch.uint8, device="cuda")
@@ -434,6 +435,36 @@ def leg_lz4(env, args):
         gather = {"collective": "ncclAllGather of the uniform 1 GiB shards (torch.distributed, NCCL over NVLink), issued after the decode", "bytes_per_rank": w["U"],
                   "gather_alone_ms": gms, "busbw_GBps": w["U"] * (world - 1) / (gms * 1e-3) / 1e9, "decode_plus_gather_ms": both,
                   "value_with_gather": world * w["U"] / (both * 1e-3) / 1e9}
+        try:
+            import torch.distributed._symmetric_memory as symm
+            U = w["U"]
+            buf = symm.empty(world * U, dtype=torch.uint8, device="cuda")
+            hdl = symm.rendezvous(buf, dist.group.WORLD)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            mine = buf[rank * U: (rank + 1) * U]
+            peers = [ptrs[p] + rank * U for p in range(world) if p != rank]
+            buf.zero_()
+            env.barrier()
+
+            def step_fused():
+                res["f"] = ctx.lz4_decode_blocks_gather(d_in, w["in_off"], w["in_len"], mine, w["out_off"], w["out_cap"], peers)
+            fms = env.time_dev(step_fused, max(3, min(args.steps, 10)), 2)
+            env.barrier()
+            assert int((res["f"][1] != 0).sum().item()) == 0
+            # every rank's shard must have arrived: byte sums of the received regions against the senders' own sums
+            sums = torch.stack([buf[p * U: (p + 1) * U].to(torch.int64).sum() for p in range(world)])
+            own = d_out.to(torch.int64).sum().reshape(1)
+            allown = torch.empty(world, dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(allown, own)
+            assert torch.equal(sums, allown) and torch.equal(mine, d_out), "fused gather: a peer's shard did not arrive intact"
+            gather["fused"] = {"what": "rcz_lz4_decode_blocks_gather: lz4_mat_kernel stores each 16-byte output chunk to the local buffer and to the same offset of the "
+                                       "%d peers' gathered buffers (torch symmetric memory, P2P stores over NVLink / NVSwitch); no collective call" % (world - 1),
+                               "decode_plus_gather_ms": fms, "value_with_gather": world * U / (fms * 1e-3) / 1e9}
+            gather["value_with_gather"] = max(gather["value_with_gather"], gather["fused"]["value_with_gather"])
+            del buf
+        except Exception as e:  # symmetric memory unavailable on this box / torch build: the NCCL figure stands
+            traceback.print_exc(file=sys.stderr)
+            gather["fused"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
 
     # ---- end-to-end timing through the host-buffer ABI (e2e), and the platform's copy ceiling for the same bytes
     h_in, h_in_np = env.pinned(w["packed"])

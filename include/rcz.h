@@ -106,6 +106,15 @@ const char* rcz_build_info(void);
 int rcz_lz4_decode_blocks(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
                           void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
                           uint64_t* out_len, int32_t* status, size_t nblocks, int mem_kind);
+/* Multi-GPU form of rcz_lz4_decode_blocks (device pointers only): the same decode, and every output byte written at out_base + x is
+ * also written at peer_out_base[p] + x for p < npeers (<= 7) — pointers into the other GPUs' output buffers, mapped into this process
+ * over NVLink / NVSwitch (CUDA IPC or symmetric memory).  With one rank per GPU and every rank passing its own slot of a common layout,
+ * the final gather of the decoded shards is done by the decode kernel's own stores; the caller synchronises the ranks
+ * afterwards (stream sync + barrier) before reading. */
+int rcz_lz4_decode_blocks_gather(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                                 void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
+                                 uint64_t* out_len, int32_t* status, size_t nblocks, int mem_kind,
+                                 void* const* peer_out_base, int npeers);
 /* rcz_lz4_encode_blocks replaces `BlockEncoder::encode` / `lz4::encode_block` (lz4.rs:183-311, 616-627): the reference's greedy
  * single-probe hash compressor, byte for byte (same probe sequence, skip acceleration, rewind, `pos + 12 > len` tail rule).
  * out_cap[i] must be >= rcz_lz4_compression_bound(in_len[i]) (the reference reserves exactly that, lz4.rs:232-238), else

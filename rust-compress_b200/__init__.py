@@ -140,6 +140,15 @@ class Context:
         self._check(st, "rcz_lz4_decode_blocks")
         return out_len, status
 
+    def lz4_decode_blocks_gather(self, in_buf, in_off, in_len, out_buf, out_off, out_cap, peer_ptrs, async_=True):
+        """rcz_lz4_decode_blocks_gather: decode + store every output chunk into the peers' buffers as well (device pointers as ints)."""
+        kind, n, (io, il, oo, oc), out_len, status, _ = self._batch(None, "lz4", in_buf, in_off, in_len, out_buf, out_off, out_cap, async_=async_)
+        arr = (C.c_void_p * max(1, len(peer_ptrs)))(*[int(p) for p in peer_ptrs])
+        st = self._lib.rcz_lz4_decode_blocks_gather(self._h, _ptr(in_buf), _ptr(io), _ptr(il), _ptr(out_buf), _ptr(oo), _ptr(oc),
+                                                    _ptr(out_len), _ptr(status), n, kind, C.cast(arr, C.c_void_p), len(peer_ptrs))
+        self._check(st, "rcz_lz4_decode_blocks_gather")
+        return out_len, status
+
     def lz4_encode_blocks(self, in_buf, in_off, in_len, out_buf, out_off, out_cap, async_=False):
         """rcz_lz4_encode_blocks (lz4.rs:226-310, bit-exact).  Returns (out_len, status) arrays."""
         kind, n, (io, il, oo, oc), out_len, status, _ = self._batch(None, "lz4e", in_buf, in_off, in_len, out_buf, out_off, out_cap, async_=async_)

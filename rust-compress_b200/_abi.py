@@ -33,6 +33,7 @@ SIGNATURES = {
     "rcz_host_free": (_I, [_P]),
     "rcz_build_info": (C.c_char_p, []),
     "rcz_lz4_decode_blocks": (_I, _BATCH),
+    "rcz_lz4_decode_blocks_gather": (_I, _BATCH + [_P, _I]),
     "rcz_lz4_encode_blocks": (_I, _BATCH),
     "rcz_lz4_compression_bound": (C.c_int64, [C.c_uint32]),
     "rcz_bwt_decode_blocks": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I]),

@@ -400,19 +400,30 @@ __device__ __forceinline__ void copy_chain(const uint8_t* __restrict__ src, uint
     }
 }
 
+// Persistent CTAs take (block, 256 heads) tickets in block-major order, so that only a few blocks are in flight at a time: a block's
+// descriptors and chain slots (read in list order = random order) then stay in L2 while its heads are processed, and every 64-byte
+// line that DRAM delivers serves all the chains in it instead of one.
 __global__ void __launch_bounds__(256)
-ibwt_place_kernel(const Blk* __restrict__ blks, const uint8_t* __restrict__ scratch_base, const Desc* __restrict__ desc_base,
-                  const unsigned* __restrict__ chain_ctr, const unsigned long long* __restrict__ node_base, uint8_t* __restrict__ out_base,
-                  unsigned hlog) {
-    const unsigned b = blockIdx.y;
-    const Blk bk = blks[b];
-    if (bk.skip) return;
-    const HeadGeom g = head_geom(bk, chain_ctr, b, hlog);
-    const Desc* desc = desc_base + bk.chain0;
-    const unsigned long long* node = node_base + bk.head0;
-    const uint8_t* scratch = scratch_base + bk.scratch_off;
-    uint8_t* out = out_base + bk.out_off;
-    for (unsigned h = blockIdx.x * blockDim.x + threadIdx.x; h < g.H; h += gridDim.x * blockDim.x) {
+ibwt_place_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned tiles_per_block, const uint8_t* __restrict__ scratch_base,
+                  const Desc* __restrict__ desc_base, const unsigned* __restrict__ chain_ctr, const unsigned long long* __restrict__ node_base,
+                  uint8_t* __restrict__ out_base, unsigned hlog, unsigned* __restrict__ ticket) {
+    __shared__ unsigned s_t;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_t = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const unsigned t = s_t;
+        if (t >= nblocks * tiles_per_block) break;
+        const unsigned b = t / tiles_per_block, tile = t - b * tiles_per_block;
+        const Blk bk = blks[b];
+        if (bk.skip) continue;
+        const HeadGeom g = head_geom(bk, chain_ctr, b, hlog);
+        const unsigned h = tile * 256u + threadIdx.x;
+        if (h >= g.H) continue;
+        const Desc* desc = desc_base + bk.chain0;
+        const unsigned long long* node = node_base + bk.head0;
+        const uint8_t* scratch = scratch_base + bk.scratch_off;
+        uint8_t* out = out_base + bk.out_off;
         unsigned off = (unsigned)node[h];
         if (off == OFF_INVALID) continue;
         unsigned cur = h < g.nreg ? h << hlog : g.K;
@@ -436,7 +447,7 @@ __global__ void ibwt_init_kernel(Blk* __restrict__ blks, unsigned nblocks, unsig
                                  uint64_t* __restrict__ out_len, int32_t* __restrict__ status, const int32_t* __restrict__ host_status,
                                  const uint32_t* __restrict__ origin_dev) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) *queue = 0;
+    if (i == 0) { queue[0] = 0; queue[1] = 0; }      // work tickets of the walk and of the placement
     if (i < nblocks) {
         if (origin_dev && !blks[i].skip) {
             const unsigned o = origin_dev[i];
@@ -475,6 +486,7 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
     // ~285 G hops/s for a <= 64 MiB working set vs ~73 G hops/s from HBM).  All offsets in Blk are group-relative and the
     // workspaces are reused by every group.  RCZ_IBWT_* are tuning overrides for tools/ibwt_sweep.sh.
     const unsigned tune_slog = getenv("RCZ_IBWT_SLOG") ? (unsigned)atoi(getenv("RCZ_IBWT_SLOG")) : 4u;
+    const unsigned tune_place = getenv("RCZ_IBWT_PLACE_CTAS") ? (unsigned)atoi(getenv("RCZ_IBWT_PLACE_CTAS")) : 2u;
     const unsigned tune_ctas = getenv("RCZ_IBWT_WALK_CTAS") ? (unsigned)atoi(getenv("RCZ_IBWT_WALK_CTAS")) : 4u;
     const unsigned long long group_syms = getenv("RCZ_IBWT_GROUP_SYMS") ? strtoull(getenv("RCZ_IBWT_GROUP_SYMS"), nullptr, 10) : (1ull << 30);
     struct Group { size_t b0, b1; unsigned tile0_abs, ntiles; unsigned long long p_elems, scratch_bytes, chains, work, heads; };
@@ -593,7 +605,9 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
         const unsigned hx = (unsigned)std::min<unsigned long long>(((max_mc >> hlog) + 3 + 255) / 256, std::max<unsigned long long>(1, (unsigned long long)c->sm_count * 16 / nb));
         RCZ_KLAUNCH(c, ibwt_heads_kernel, dim3(hx, nb), 256, 0, dblk, desc, chain_ctr, nodes, hlog);
         RCZ_KLAUNCH(c, ibwt_headrank_kernel, nb, RANK_NT, rank_smem, dblk, chain_ctr, nodes, d_len, d_st, hlog);
-        RCZ_KLAUNCH(c, ibwt_place_kernel, dim3(hx, nb), 256, 0, dblk, (const uint8_t*)wS, desc, chain_ctr, nodes, dout, hlog);
+        const unsigned tiles = ((max_mc >> hlog) + 3 + 255) / 256;
+        const unsigned place_grid = std::min<unsigned>(nb * tiles, (unsigned)c->sm_count * tune_place);
+        RCZ_KLAUNCH(c, ibwt_place_kernel, place_grid, 256, 0, dblk, nb, tiles, (const uint8_t*)wS, desc, chain_ctr, nodes, dout, hlog, queue + 1);
         if (mark) { st = ctx_stage_mark(c, 3); if (st) return st; mark = false; }
     }
     st = ctx_timer_end(c); if (st) return st;

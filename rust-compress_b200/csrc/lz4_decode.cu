@@ -496,6 +496,10 @@ lz4_scan_kernel(const uint32_t* __restrict__ wbase, const uint32_t* __restrict__
 // materialise
 // ======================================================================================================
 struct __align__(16) UnitInfo { uint32_t nseq, tot, ob, pad; };
+// Fused gather (multi-GPU): every 16-byte chunk that goes to this GPU's output also goes to the same offset of the output buffers
+// of up to 7 peers (pointers mapped over NVLink / NVSwitch), so the final gather of the decoded shards rides on the decode's own
+// stores instead of following it as a separate collective.  delta[p] = peer base - local base.
+struct PeerOut { long long delta[7]; int n; };
 struct MatSmem {
     __align__(16) uint8_t ring_[32 + RING + 32];     // 32-byte mirrors of the other end on both sides: source windows may overhang
     __align__(16) uint8_t win[2][CHUNK_BYTES];       // compressed window of the current / next unit (literal sources)
@@ -518,6 +522,7 @@ struct MatCtx {
     const SeqEnt* D; const SeqEnt* ds; const uint4* lt; uint32_t* cmask;
     const uint8_t* in; uint8_t* outb; uint8_t* ring; rcz_saddr rings, wins, cmasks;
     unsigned ob, uend, nseq, n, cbase, limw, hb, T0, T1, h, c00, nch, tend;
+    const PeerOut* peer; int npeer;
 };
 __device__ __forceinline__ uint4 mat_desc(const MatCtx& k, unsigned j) {
     return j < (unsigned)DCAP ? *reinterpret_cast<const uint4*>(&k.ds[j]) : __ldg(reinterpret_cast<const uint4*>(&k.D[j]));
@@ -583,7 +588,7 @@ __device__ __noinline__ unsigned far_back(unsigned kk, unsigned off) {
 // fetched with 4-byte loads + funnel shifts (staged compressed window, ring) and OR-ed into the zeroed chunk; per-chunk byte
 // masks order pieces whose source lies inside the tile, and whoever completes a chunk stores its 16 bytes to HBM.
 // All lanes of the warp call it together; lanes with active == false only take part in the votes.
-template <bool DEP, bool LIT>
+template <bool DEP, bool LIT, bool PEERS>
 __device__ __forceinline__ void mat_piece(const MatCtx& k, const uint16_t* sbase, const uint16_t* pseq, unsigned j0, unsigned p, bool active) {
     constexpr unsigned NOCHK = 0xffffu;
     const unsigned T0 = k.T0, T1 = k.T1, c00 = k.c00;
@@ -688,8 +693,13 @@ __device__ __forceinline__ void mat_piece(const MatCtx& k, const uint16_t* sbase
                     const uint4 v = lds128_volatile(k.ring + cro);
                     uint8_t* g = k.outb + T0 - k.h + 16u * cc;                  // pointer arithmetic: T0 - h alone may wrap below zero
                     const unsigned lo = cc ? 0u : k.h;
-                    if (lo == 0 && hi == 16u) *reinterpret_cast<uint4*>(g) = v;
-                    else store_chunk_bytes(g, v, lo, hi);                       // first / last chunk of a unit (rare, out of line)
+                    if (lo == 0 && hi == 16u) {
+                        *reinterpret_cast<uint4*>(g) = v;
+                        if (PEERS) for (int pp = 0; pp < k.npeer; ++pp) *reinterpret_cast<uint4*>(g + k.peer->delta[pp]) = v;
+                    } else {
+                        store_chunk_bytes(g, v, lo, hi);                        // first / last chunk of a unit (rare, out of line)
+                        if (PEERS) for (int pp = 0; pp < k.npeer; ++pp) store_chunk_bytes(g + k.peer->delta[pp], v, lo, hi);
+                    }
                 }
                 done = true; progressed = true;
             }
@@ -717,11 +727,13 @@ __device__ __forceinline__ void mat_prefetch(MatSmem& sm, unsigned w, unsigned w
     }
 }
 
+template <bool PEERS>
 __global__ void __launch_bounds__(MT, 2)
 lz4_mat_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ in_len,
                uint8_t* out_base, const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ wbase, const uint32_t* __restrict__ nwin,
                unsigned nblocks, const WinInfo* __restrict__ winfo, const SeqEnt* __restrict__ seqs,
-               const unsigned long long* __restrict__ obase, const int32_t* __restrict__ blkstate, unsigned* ticket_ctr) {
+               const unsigned long long* __restrict__ obase, const int32_t* __restrict__ blkstate, unsigned* ticket_ctr,
+               const __grid_constant__ PeerOut peers) {
     RCZ_DYN_SMEM(raw);
     MatSmem& sm = *reinterpret_cast<MatSmem*>(raw);
     const unsigned tid = threadIdx.x;
@@ -753,6 +765,7 @@ lz4_mat_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__
         k.ring = sm.ring_ + 32;
         k.rings = saddr_of(k.ring);
         k.lt = sm.lt; k.cmask = sm.cmask; k.cmasks = saddr_of(sm.cmask);
+        k.peer = &peers; k.npeer = PEERS ? peers.n : 0;
         if (tid == 0) { fence_proxy_async_smem(); mat_prefetch(sm, 0, wb, winfo, obase, seqs, k.in, k.n); }
 
         for (unsigned w = 0; w < nw; ++w) {
@@ -832,7 +845,7 @@ lz4_mat_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__
                     for (unsigned i = 0; i < cnt; ++i) sm.pseq[base + i] = (uint16_t)tid;      // piece -> sequence (a few per thread; a long match has one per chunk)
                     __syncthreads();
                     for (unsigned p0 = 0; p0 < P; p0 += MT) {
-                        if (p0 + (tid & ~31u) < P) mat_piece<true, true>(k, sm.sbase, sm.pseq, j0, p0 + tid, p0 + tid < P);    // warp-uniform
+                        if (p0 + (tid & ~31u) < P) mat_piece<true, true, PEERS>(k, sm.sbase, sm.pseq, j0, p0 + tid, p0 + tid < P);    // warp-uniform
                     }
                     if (!__syncthreads_or(more && j0 + MT < k.nseq)) break;
                 }
@@ -871,6 +884,7 @@ static void lz4_plan_range(const Lz4Plan& pl, size_t b0, size_t nb, std::vector<
 }
 
 struct Lz4Dev {
+    lz4k::PeerOut peers;
     const uint32_t *wbase, *nw; const uint2* tickets;
     unsigned long long* chain; unsigned* done; unsigned* ctr; lz4k::WinInfo* winfo; unsigned long long* obase; int32_t* blkstate; lz4k::SeqEnt* seqs;
 };
@@ -896,8 +910,12 @@ static int lz4_enqueue(rcz_ctx* c, rt_stream_t stream, const Lz4Dev& d, size_t r
     if (timed) { int st = ctx_stage_mark(c, 2); if (st) return st; }
     if (ntk) {
         const size_t g2 = std::min<size_t>(nb, (size_t)c->sm_count * 2);
-        RCZ_LAUNCH(lz4_mat_kernel, (unsigned)g2, MT, sizeof(MatSmem), stream, din, in_off, in_len, dout, out_off, d.wbase, d.nw, (unsigned)nb, d.winfo, d.seqs,
-                   d.obase, d.blkstate, ctr + 1);
+        if (d.peers.n)
+            RCZ_LAUNCH(lz4_mat_kernel<true>, (unsigned)g2, MT, sizeof(MatSmem), stream, din, in_off, in_len, dout, out_off, d.wbase, d.nw, (unsigned)nb, d.winfo, d.seqs,
+                       d.obase, d.blkstate, ctr + 1, d.peers);
+        else
+            RCZ_LAUNCH(lz4_mat_kernel<false>, (unsigned)g2, MT, sizeof(MatSmem), stream, din, in_off, in_len, dout, out_off, d.wbase, d.nw, (unsigned)nb, d.winfo, d.seqs,
+                       d.obase, d.blkstate, ctr + 1, d.peers);
         c->launches++;
         RCZ_CK(c, rt_last_error());
     }
@@ -942,12 +960,14 @@ static int lz4_prepare(rcz_ctx* c, DescStager& ds, const uint64_t* in_len, size_
     void* wsb; st = ctx_ws(c, WS_B, tot * (sizeof(WinInfo) + 8) + nblocks * 4 + 64, &wsb); if (st) return st;
     void* wsc; st = ctx_ws(c, WS_C, tot * (size_t)SLOT * sizeof(SeqEnt) + 64, &wsc); if (st) return st;
     Lz4Dev& d = job.dev;
+    memset(&d.peers, 0, sizeof d.peers);
     d.wbase = ds.in_ptr<uint32_t>(i_wb); d.nw = ds.in_ptr<uint32_t>(i_nw); d.tickets = (const uint2*)ds.in_ptr<uint32_t>(i_tk);
     d.chain = (unsigned long long*)ctl; d.done = (unsigned*)((uint8_t*)ctl + tot * 8); d.ctr = (unsigned*)((uint8_t*)ctl + tot * 12 + ((-(long)(tot * 12)) & 7));
     d.winfo = (WinInfo*)wsb; d.obase = (unsigned long long*)((uint8_t*)wsb + tot * sizeof(WinInfo)); d.blkstate = (int32_t*)((uint8_t*)wsb + tot * (sizeof(WinInfo) + 8));
     d.seqs = (SeqEnt*)wsc;
     RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(lz4_parse_kernel, sizeof(ParseSmem)));
-    RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(lz4_mat_kernel, sizeof(MatSmem)));
+    RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(lz4_mat_kernel<false>, sizeof(MatSmem)));
+    RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(lz4_mat_kernel<true>, sizeof(MatSmem)));
     return RCZ_OK;
 }
 // kernels of range k of a prepared job (descriptor arrays in `ds` slots 0..3 = in_off, in_len, out_off, out_cap)
@@ -1044,9 +1064,27 @@ static int lz4_host_pipelined(rcz_ctx* c, DescStager& ds, const Lz4Job& job, con
     return RCZ_OK;
 }
 
+static int lz4_decode_impl(rcz_ctx* c, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                           void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
+                           uint64_t* out_len, int32_t* status, size_t nblocks, int mem_kind, void* const* peer_out_base, int npeers);
+
 extern "C" int rcz_lz4_decode_blocks(rcz_ctx* c, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
                                      void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
                                      uint64_t* out_len, int32_t* status, size_t nblocks, int mem_kind) {
+    return lz4_decode_impl(c, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, nblocks, mem_kind, nullptr, 0);
+}
+
+extern "C" int rcz_lz4_decode_blocks_gather(rcz_ctx* c, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                                            void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
+                                            uint64_t* out_len, int32_t* status, size_t nblocks, int mem_kind,
+                                            void* const* peer_out_base, int npeers) {
+    if (npeers < 0 || npeers > 7 || (npeers && !peer_out_base) || mem_kind == RCZ_MEM_HOST) return RCZ_E_ARG;
+    return lz4_decode_impl(c, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, nblocks, mem_kind, peer_out_base, npeers);
+}
+
+static int lz4_decode_impl(rcz_ctx* c, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                           void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
+                           uint64_t* out_len, int32_t* status, size_t nblocks, int mem_kind, void* const* peer_out_base, int npeers) {
     if (!c || rcz_bad_kind(mem_kind)) return RCZ_E_ARG;
     if (nblocks == 0) return RCZ_OK;
     if (!in_base || !in_off || !in_len || !out_base || !out_off || !out_cap || !out_len || !status) return RCZ_E_ARG;
@@ -1066,6 +1104,8 @@ extern "C" int rcz_lz4_decode_blocks(rcz_ctx* c, const void* in_base, const uint
     cut.push_back(nblocks);
     Lz4Job job;
     int st = lz4_prepare(c, ds, in_len, nblocks, cut, job); if (st) return st;
+    job.dev.peers.n = npeers;
+    for (int p = 0; p < npeers; ++p) job.dev.peers.delta[p] = (long long)((const uint8_t*)peer_out_base[p] - (const uint8_t*)out_base);
     if (pipelined) return lz4_host_pipelined(c, ds, job, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, nblocks);
     const uint8_t* din = (const uint8_t*)in_base; uint8_t* dout = (uint8_t*)out_base;
     if (mem_kind == RCZ_MEM_HOST) {

@@ -5,6 +5,7 @@
 
 #ifdef RCZ_EMU
 #include "simt_emu.h"
+#define __grid_constant__
 #define RCZ_DYN_SMEM(name) unsigned char* name = emu::S().dyn_smem
 #define RCZ_LAUNCH(kern, grid, block, smem, stream, ...) \
     emu::launch(dim3(grid), dim3(block), (smem), [=]() { kern(__VA_ARGS__); })

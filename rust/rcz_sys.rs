@@ -55,6 +55,10 @@ extern "C" {
     pub fn rcz_lz4_decode_blocks(ctx: *mut rcz_ctx, in_base: *const c_void, in_off: *const u64, in_len: *const u64,
                                  out_base: *mut c_void, out_off: *const u64, out_cap: *const u64,
                                  out_len: *mut u64, status: *mut i32, nblocks: usize, mem_kind: c_int) -> c_int;
+    pub fn rcz_lz4_decode_blocks_gather(ctx: *mut rcz_ctx, in_base: *const c_void, in_off: *const u64, in_len: *const u64,
+                                        out_base: *mut c_void, out_off: *const u64, out_cap: *const u64,
+                                        out_len: *mut u64, status: *mut i32, nblocks: usize, mem_kind: c_int,
+                                        peer_out_base: *const *mut c_void, npeers: c_int) -> c_int;
     pub fn rcz_lz4_encode_blocks(ctx: *mut rcz_ctx, in_base: *const c_void, in_off: *const u64, in_len: *const u64,
                                  out_base: *mut c_void, out_off: *const u64, out_cap: *const u64,
                                  out_len: *mut u64, status: *mut i32, nblocks: usize, mem_kind: c_int) -> c_int;

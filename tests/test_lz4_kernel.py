@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from conftest import golden
-from util import run_batch
+from util import out_layout, pack, run_batch
 
 TXT = golden("ref_test.txt")
 
@@ -282,3 +282,19 @@ def test_lz4_gpu_stage_timings(gpu_ctx, gen):
     st = gpu_ctx.last_stage_ms()
     assert len(st) == 3 and all(t > 0 for t in st)
     assert abs(sum(st) - gpu_ctx.last_kernel_ms()) < 0.25 * gpu_ctx.last_kernel_ms() + 0.05
+
+
+def test_lz4_emu_gather_peers(emu_ctx, oracle, gen):
+    """rcz_lz4_decode_blocks_gather: every output byte also lands at the same offset of the peers' buffers (the multi-GPU fused
+    gather; on the emulator the 'peers' are two more host buffers)."""
+    raw = [gen.one("lzsyn", 5, 50000), gen.one("hextext", 6, 33333), b"x" * 70000]
+    units = [gen.lz4_compress(r) for r in raw]
+    inb, in_off, in_len = pack(units, pad_front=5, gap=3, align=16)
+    caps = [len(r) for r in raw]
+    out_off, out_cap, total = out_layout(caps, gap=7)
+    mine, p1, p2 = (np.zeros(total, dtype=np.uint8) for _ in range(3))
+    out_len, status = emu_ctx.lz4_decode_blocks_gather(inb, in_off, in_len, mine, out_off, out_cap, [p1.ctypes.data, p2.ctypes.data], async_="emu-device")
+    assert (status == 0).all()
+    for o, r in zip(out_off, raw):
+        for buf in (mine, p1, p2):
+            assert buf[int(o): int(o) + len(r)].tobytes() == r
