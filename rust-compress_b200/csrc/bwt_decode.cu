@@ -486,7 +486,7 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
     // ~285 G hops/s for a <= 64 MiB working set vs ~73 G hops/s from HBM).  All offsets in Blk are group-relative and the
     // workspaces are reused by every group.  RCZ_IBWT_* are tuning overrides for tools/ibwt_sweep.sh.
     const unsigned tune_slog = getenv("RCZ_IBWT_SLOG") ? (unsigned)atoi(getenv("RCZ_IBWT_SLOG")) : 4u;
-    const unsigned tune_place = getenv("RCZ_IBWT_PLACE_CTAS") ? (unsigned)atoi(getenv("RCZ_IBWT_PLACE_CTAS")) : 2u;
+    const unsigned tune_place = getenv("RCZ_IBWT_PLACE_CTAS") ? (unsigned)atoi(getenv("RCZ_IBWT_PLACE_CTAS")) : 8u;
     const unsigned tune_ctas = getenv("RCZ_IBWT_WALK_CTAS") ? (unsigned)atoi(getenv("RCZ_IBWT_WALK_CTAS")) : 4u;
     const unsigned long long group_syms = getenv("RCZ_IBWT_GROUP_SYMS") ? strtoull(getenv("RCZ_IBWT_GROUP_SYMS"), nullptr, 10) : (1ull << 30);
     struct Group { size_t b0, b1; unsigned tile0_abs, ntiles; unsigned long long p_elems, scratch_bytes, chains, work, heads; };
