@@ -460,6 +460,7 @@ def leg_lz4(env, args):
             gather["fused"] = {"what": "rcz_lz4_decode_blocks_gather: lz4_mat_kernel stores each 16-byte output chunk to the local buffer and to the same offset of the "
                                        "%d peers' gathered buffers (torch symmetric memory, P2P stores over NVLink / NVSwitch); no collective call" % (world - 1),
                                "decode_plus_gather_ms": fms, "value_with_gather": world * U / (fms * 1e-3) / 1e9}
+            gather["nccl_value_with_gather"] = gather["value_with_gather"]
             gather["value_with_gather"] = max(gather["value_with_gather"], gather["fused"]["value_with_gather"])
             del buf
         except Exception as e:  # symmetric memory unavailable on this box / torch build: the NCCL figure stands

@@ -14,7 +14,7 @@ run lz4enc memcheck 400 tests/test_lz4_encode_kernel.py -k "test_lz4_encode_gpu 
 run ibwt memcheck 400 tests/test_bwt_decode_kernel.py -k "gpu_cases"
 run bwt memcheck 600 tests/test_bwt_encode_kernel.py -k "gpu_cases"
 run flate memcheck 600 tests/test_flate_kernel.py tests/test_zlib_kernel.py -k "test_inflate_gpu and True or test_zlib_gpu and True"
-run misc memcheck 600 tests/test_ari_rle_kernels.py tests/test_dc_kernels.py tests/test_mtf_kernel.py -k "True or gpu"
+run misc memcheck 600 tests/test_ari_rle_kernels.py tests/test_dc_kernels.py tests/test_mtf_kernel.py -k "test_ari_gpu and True or test_rle_gpu and True or test_dc_gpu and True or test_mtf_gpu and True"
 run pipeline memcheck 600 tests/test_pipeline.py -k "test_pipeline_gpu and True and 65536"
 run lz4 racecheck 900 tests/test_lz4_kernel.py -k "gpu_window_cases and True"
 run ibwt racecheck 600 tests/test_bwt_decode_kernel.py -k "gpu_cases and True"
