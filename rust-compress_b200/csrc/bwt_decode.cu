@@ -295,7 +295,7 @@ ibwt_walk_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned total_
 //                        offsets (aligned 16-byte loads; head bytes, funnel-shifted 32-bit words, tail bytes)
 // The two walks are O(nch) dependent 8-byte loads spread over ~10 K threads per block — latency is hidden by parallelism instead of
 // being paid by one CTA per block (the round-1 kernel: 1.5 ms per wave of blocks once chains became short and numerous).
-constexpr unsigned RANK_MAX_HEADS = 12288;                    // 8 B each in shared memory: two CTAs per SM
+constexpr unsigned RANK_MAX_HEADS = 12288;                    // 2 x 8 B each in shared memory (read copy, write copy)
 
 struct HeadGeom { unsigned nch, nreg, H, K, mask, hlog; };
 __device__ __forceinline__ HeadGeom head_geom(const Blk& bk, const unsigned* chain_ctr, unsigned b, unsigned hlog) {
@@ -337,37 +337,42 @@ ibwt_heads_kernel(const Blk* __restrict__ blks, const Desc* __restrict__ desc_ba
     }
 }
 
-__global__ void __launch_bounds__(RANK_NT, 2)
+__global__ void __launch_bounds__(RANK_NT, 1)
 ibwt_headrank_kernel(const Blk* __restrict__ blks, const unsigned* __restrict__ chain_ctr, unsigned long long* __restrict__ node_base,
                      uint64_t* __restrict__ out_len, int32_t* __restrict__ status, unsigned hlog) {
     RCZ_DYN_SMEM(raw);
     unsigned long long* node = reinterpret_cast<unsigned long long*>(raw);
-    volatile unsigned long long* vnode = node;
     const unsigned b = blockIdx.x, tid = threadIdx.x;
     const Blk bk = blks[b];
     if (bk.skip) return;
     const HeadGeom g = head_geom(bk, chain_ctr, b, hlog);
     unsigned long long* gnode = node_base + bk.head0;
     const unsigned H = g.H, SENT = g.H;
+    // two copies of the node array: a round reads one and writes the other, so the jumping is race-free (one barrier per round)
+    unsigned long long* nodeB = node + (H + 2);
     for (unsigned i = tid; i < H; i += RANK_NT) node[i] = gnode[i];
-    if (tid == 0) node[SENT] = SENT;
+    if (tid == 0) { node[SENT] = SENT; nodeB[SENT] = SENT; }
     __syncthreads();
     // ---- Wyllie over the heads
     unsigned rounds = 2;
     for (unsigned v = H; v; v >>= 1) ++rounds;
+    unsigned long long* src = node; unsigned long long* dst = nodeB;
     for (unsigned r = 0; r < rounds; ++r) {
         int pend = 0;
         for (unsigned i = tid; i < H; i += RANK_NT) {
-            const unsigned long long a = vnode[i];
+            unsigned long long a = src[i];
             const unsigned s = (unsigned)a;
             if (s != SENT && s != i) {
-                const unsigned long long q = vnode[s];
-                vnode[i] = (((a >> 32) + (q >> 32)) << 32) | (unsigned)q;
+                const unsigned long long q = src[s];
+                a = (((a >> 32) + (q >> 32)) << 32) | (unsigned)q;
                 pend = 1;
             }
+            dst[i] = a;
         }
+        unsigned long long* t2 = src; src = dst; dst = t2;
         if (!__syncthreads_or(pend)) break;
     }
+    node = src;                                                          // the copy the last round wrote
     const unsigned long long org = node[g.nreg];
     const unsigned total = (unsigned)org == SENT ? (unsigned)(org >> 32) : 0u;   // the origin chain always reaches END
     // head h -> output offset of its first chain (OFF_INVALID when it never reaches END: its chains are not part of the output)
@@ -579,7 +584,7 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
     unsigned* queue = (unsigned*)m;
 
     RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(ibwt_scatter_kernel, sizeof(ScatterSmem)));
-    const size_t rank_smem = ((size_t)(max_mc >> hlog) + 4) * 8;
+    const size_t rank_smem = ((size_t)(max_mc >> hlog) + 5) * 8 * 2;     // two copies of the head nodes
     RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(ibwt_headrank_kernel, rank_smem));
     st = ctx_timer_begin(c); if (st) return st;
     // rcz_last_stage_ms: {partition (hist, scan, scatter), walk, rank + compact} of the FIRST group

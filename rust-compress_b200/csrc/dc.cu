@@ -198,20 +198,26 @@ dc_decode_kernel(const uint32_t* __restrict__ in_base, const uint64_t* __restric
         unsigned di = 0;
         unsigned dreg = lane < ND ? __ldg(dist + lane) : 0u;                  // distances [32g, 32g + 32) of the current group, one per lane
         unsigned dnxt = 32u + lane < ND ? __ldg(dist + 32 + lane) : 0u;       // the next group, in flight while this one is used
-        while (i < N) {
-            const unsigned stop = __shfl_sync(RCZ_FULL, nx, 1), sym = __shfl_sync(RCZ_FULL, sy, 0);
+        // The loop body is kept straight-line: with one chain per block the GPU is almost empty, so what counts is the latency of the
+        // dependent instructions from one list state to the next (shuffle -> add -> ballot -> ffs -> select), not their number; the error
+        // tests only set a flag (and clamp, so that nothing goes out of bounds) and are looked at when the loop ends.
+        bool bad = false;
+        while (i < N && di < ND && !bad) {
+            unsigned stop = __shfl_sync(RCZ_FULL, nx, 1);
+            const unsigned sym = __shfl_sync(RCZ_FULL, sy, 0);
             const unsigned up_nx = __shfl_down_sync(RCZ_FULL, nx, 1), up_sy = __shfl_down_sync(RCZ_FULL, sy, 1);
-            const unsigned d = __shfl_sync(RCZ_FULL, dreg, (int)(di & 31u));
-            if (stop > N) { err = RCZ_E_MALFORMED; break; }                   // output[i] index panic
+            unsigned d = __shfl_sync(RCZ_FULL, dreg, (int)(di & 31u));
+            bad = stop > N;                                                   // output[i] index panic
+            stop = stop > N ? N : stop;
+            bad |= d > N - stop;                                              // dc.rs:213 assert!(future <= n)
+            d = d > N - stop ? N - stop : d;
             if (stop > i) {                                                   // the run [i, stop): almost always a few bytes
                 if (lane < stop - i) out[i + lane] = (uint8_t)sym;
                 if (stop - i > 32u) for (unsigned k = i + 32u + lane; k < stop; k += 32) out[k] = (uint8_t)sym;
                 i = stop;
             }
-            if (di >= ND) { err = RCZ_E_UNEXPECTED_EOF; break; }              // dc.rs:245-246
             ++di;
             if ((di & 31u) == 0) { dreg = dnxt; dnxt = (unsigned long long)di + 32 + lane < ND ? __ldg(dist + di + 32 + lane) : 0u; }
-            if (d > N - stop) { err = RCZ_E_MALFORMED; break; }               // dc.rs:213 assert!(future <= n)
             const unsigned future = stop + d;
             // rank = 1 + #{leading r in [1, A) : future + r > next(list[r])}  (dc.rs:215-218; the reference stops at the first rank that
             // fails the test: count LEADING hits, not all hits)
@@ -225,23 +231,33 @@ dc_decode_kernel(const uint32_t* __restrict__ in_base, const uint64_t* __restric
                     rank += (unsigned)__ffs((int)~bb) - 1u;
                     break;
                 }
-            }
-            if (rank <= 32) {
-                if (lane + 1 < rank) { nx = up_nx; sy = up_sy; } else if (lane + 1 == rank) { nx = future + rank - 1u; sy = sym; }
-            } else {
-                const unsigned v32n = tnx[32], v32s = tsy[32];
-                if (lane < 31) { nx = up_nx; sy = up_sy; } else { nx = v32n; sy = v32s; }
-                __syncwarp();                                                 // entry 32 is read before anyone rewrites it
-                for (unsigned r0 = 32; r0 + 1 < rank; r0 += 32) {             // tail[r] = tail[r+1] for r in [32, rank-1)
-                    const unsigned r = r0 + lane;
-                    const unsigned tn = (r + 1 < rank) ? tnx[r + 1] : 0u, ts = (r + 1 < rank) ? (unsigned)tsy[r + 1] : 0u;
+                if (rank > 32) {
+                    const unsigned v32n = tnx[32], v32s = tsy[32];
+                    if (lane < 31) { nx = up_nx; sy = up_sy; } else { nx = v32n; sy = v32s; }
+                    __syncwarp();                                             // entry 32 is read before anyone rewrites it
+                    for (unsigned r0 = 32; r0 + 1 < rank; r0 += 32) {         // tail[r] = tail[r+1] for r in [32, rank-1)
+                        const unsigned r = r0 + lane;
+                        const unsigned tn = (r + 1 < rank) ? tnx[r + 1] : 0u, ts = (r + 1 < rank) ? (unsigned)tsy[r + 1] : 0u;
+                        __syncwarp();
+                        if (r + 1 < rank) { tnx[r] = tn; tsy[r] = (uint8_t)ts; }
+                        __syncwarp();
+                    }
+                    if (lane == 0) { tnx[rank - 1] = future + rank - 1u; tsy[rank - 1] = (uint8_t)sym; }
                     __syncwarp();
-                    if (r + 1 < rank) { tnx[r] = tn; tsy[r] = (uint8_t)ts; }
-                    __syncwarp();
+                    continue;
                 }
-                if (lane == 0) { tnx[rank - 1] = future + rank - 1u; tsy[rank - 1] = (uint8_t)sym; }
-                __syncwarp();
             }
+            const bool below = lane + 1 < rank, at = lane + 1 == rank;        // rank <= 32: everything stays in registers, no branch
+            nx = below ? up_nx : at ? future + rank - 1u : nx;
+            sy = below ? up_sy : at ? sym : sy;
+        }
+        // a flagged step is where the reference panics (its list update is then meaningless and is not looked at); running out of
+        // distances before the block is full is dc.rs:245-246
+        if (bad) err = RCZ_E_MALFORMED;
+        else if (i < N) {                                                     // out of distances: the reference still looks at the next run first
+            const unsigned stop = __shfl_sync(RCZ_FULL, nx, 1), sym = __shfl_sync(RCZ_FULL, sy, 0);
+            if (stop > N) err = RCZ_E_MALFORMED;
+            else { for (unsigned k = i + lane; k < stop; k += 32) out[k] = (uint8_t)sym; err = RCZ_E_UNEXPECTED_EOF; }
         }
         if (!err) {                                                           // dc.rs:230-231 assert_eq!
             bool bad = lane < A && (nx < N || nx >= N + A);

@@ -172,16 +172,19 @@ __device__ bool build_tree(Tree& t, uint16_t* symtab, uint32_t* lut, const uint8
     if (KIND == 1) {
         // second pass: an index whose low bits are a literal code and whose remaining bits decide another literal code gets both.
         // In-place is safe: a converted entry still tells its first literal (length in bits 8-11, byte in bits 16-23).
-        for (unsigned j = lane; j < (1u << lutbits); j += 32) {
+        for (unsigned j = lane; j < (1u << lutbits); j += 32) {                        // 32 entries per step: all reads, then all writes
             const unsigned e1 = lut[j];
-            if ((e1 & 0x70u) != 0 || (e1 & 15u) == 0) continue;                       // not a single literal
-            const unsigned l1 = e1 & 15u;
-            if (l1 >= (unsigned)lutbits) continue;
-            const unsigned e2 = lut[j >> l1];
-            if ((e2 & 0x30u) != 0 || (e2 & 15u) == 0) continue;                       // the next code is not a literal in the table
-            const unsigned l2 = (e2 & E_PAIR) ? (e2 >> 8) & 15u : e2 & 15u;
-            if (l1 + l2 > (unsigned)lutbits) continue;                                // ... or not decided by the bits that are left
-            lut[j] = (l1 + l2) | E_PAIR | (l1 << 8) | (e1 & 0x00ff0000u) | (((e2 >> 16) & 255u) << 24);
+            unsigned ne = e1;
+            if ((e1 & 0x70u) == 0 && (e1 & 15u) != 0 && (e1 & 15u) < (unsigned)lutbits) {  // a single literal with index bits to spare
+                const unsigned l1 = e1 & 15u;
+                const unsigned e2 = lut[j >> l1];
+                const unsigned l2 = (e2 & E_PAIR) ? (e2 >> 8) & 15u : e2 & 15u;
+                if ((e2 & 0x30u) == 0 && (e2 & 15u) != 0 && l1 + l2 <= (unsigned)lutbits)  // the next code is a literal decided by the bits that are left
+                    ne = (l1 + l2) | E_PAIR | (l1 << 8) | (e1 & 0x00ff0000u) | (((e2 >> 16) & 255u) << 24);
+            }
+            __syncwarp();
+            if (ne != e1) lut[j] = ne;
+            __syncwarp();
         }
         __syncwarp();
     }

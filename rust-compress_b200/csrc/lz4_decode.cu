@@ -809,7 +809,7 @@ lz4_mat_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__
                     ring_store(k, cro, v);
                     sm.cmask[tid] = pre;
                 }
-                if (tid == 0) sm.ja_next = ja;
+                if (tid == 0 && t == 0) sm.ja_next = 0;                   // (later tiles: ja_next already holds ja; rewriting it would race with the slower threads' read below)
                 __syncthreads();
                 // ---- sequences in batches of MT: pieces per sequence, prefix scan, then one piece per thread and round
                 for (unsigned j0 = ja;; j0 += MT) {

@@ -17,3 +17,10 @@ timeout 900 $N -k regex:ari_decode_kernel -s 1 -c 1 -o gpurun_out/r2_prof_ari_de
 timeout 900 $N -k regex:lz4_encode_kernel -s 1 -c 1 -o gpurun_out/r2_prof_lz4_encode python tools/opbench.py lz4enc --blocks 16 --reps 1 > /dev/null 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r2_launches_bench.csv python bench.py --steps 2 --warmup 3 > gpurun_out/r2_launches_bench.log 2>&1
 ls -la gpurun_out/r2_prof_* | awk '{print $5, $9}'
+# racecheck again on the three kernels whose (benign) findings were removed
+CS=/usr/local/cuda/bin/compute-sanitizer
+timeout 900 $CS --tool racecheck --print-limit 20 --error-exitcode 0 python -m pytest tests/test_lz4_kernel.py -m gpu -x -q -k "gpu_window_cases and True" > gpurun_out/sanitize2_lz4_racecheck.txt 2>&1
+timeout 600 $CS --tool racecheck --print-limit 20 --error-exitcode 0 python -m pytest tests/test_bwt_decode_kernel.py -m gpu -x -q -k "gpu_cases and True" > gpurun_out/sanitize2_ibwt_racecheck.txt 2>&1
+timeout 600 $CS --tool racecheck --print-limit 20 --error-exitcode 0 python -m pytest tests/test_flate_kernel.py -m gpu -x -q -k "test_inflate_gpu and True" > gpurun_out/sanitize2_flate_racecheck.txt 2>&1
+grep -h "RACECHECK SUMMARY\|passed\|failed" gpurun_out/sanitize2_*.txt
+timeout 300 python tools/opbench.py dc --blocks 64 --reps 3 2>&1 | grep dc_ 
