@@ -64,6 +64,17 @@ def build_emu(force=False):
     return LIB_EMU
 
 
+def build_cli(force=False):
+    """rcz_cli: the reference's test application (main.rs) over the host mirrors, linked against the product library."""
+    src = os.path.join(HERE, "host", "rcz_cli.cpp")
+    out = os.path.join(HERE, "rcz_cli")
+    deps = [src, os.path.join(HERE, "host", "rcz_stream.hpp"), os.path.join(HERE, "..", "include", "rcz.h"), LIB]
+    if force or not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(HERE, "..", "include"), "-I", os.path.join(HERE, "host"), src, "-o", out,
+                               "-L", HERE, "-l:librcz.so", "-Wl,-rpath," + HERE])
+    return out
+
+
 if __name__ == "__main__":
     if "--emu" in sys.argv:
         print(build_emu(force="--force" in sys.argv))
