@@ -116,11 +116,13 @@ scan_kernel(const Blk* __restrict__ blks, const unsigned* __restrict__ state, un
     const Blk bk = blks[b];
     if (bk.skip || state[b] != ACTIVE) return;
     unsigned run = 0;
-    for (unsigned t = 0; t < bk.ntiles; ++t) {
-        const size_t idx = (size_t)(bk.tile0 + t) * 256 + c;
-        const unsigned hcnt = tile_hist[idx];
-        tile_hist[idx] = run;
-        run += hcnt;
+    for (unsigned t0 = 0; t0 < bk.ntiles; t0 += 16) {                         // 16 independent loads in flight, then the running sums
+        unsigned hc[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) hc[k] = t0 + k < bk.ntiles ? tile_hist[(size_t)(bk.tile0 + t0 + k) * 256 + c] : 0u;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (t0 + k < bk.ntiles) { tile_hist[(size_t)(bk.tile0 + t0 + k) * 256 + c] = run; run += hc[k]; }
     }
     unsigned total;
     const unsigned ex = block_excl_scan_add<256>(run, scratch, &total);
@@ -153,12 +155,21 @@ scatter_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* _
 
     for (unsigned i = tid; i < NW * 256; i += NT) (&sm.wcnt[0][0])[i] = 0;
     __syncthreads();
-    for (unsigned g = 0; g < WSPAN / 32; ++g) {                                // per-warp digit counts
+    // per-warp digit counts, and for every key its rank among the equal digits of the warp's 1024-key span (count before this group of
+    // 32 + rank inside the group): the 8 ballots are done ONCE per 32 keys and the ranks kept in registers, two per register
+    unsigned rb[WSPAN / 64];
+#pragma unroll
+    for (unsigned g = 0; g < WSPAN / 32; ++g) {
         const unsigned i = lo + w * WSPAN + g * 32 + lane;
         const bool valid = i < hi;
         const unsigned d = valid ? (unsigned)(kin[i] >> shift) & 255u : 0u;
         const unsigned m = warp_match_u8(d, valid);
-        if (valid && (m & ((1u << lane) - 1u)) == 0) sm.wcnt[w][d] += (unsigned)__popc(m);
+        const unsigned r = __popc(m & ((1u << lane) - 1u));
+        unsigned old = 0;
+        if (valid && r == 0) { old = sm.wcnt[w][d]; sm.wcnt[w][d] = old + (unsigned)__popc(m); }
+        old = __shfl_sync(RCZ_FULL, old, m ? __ffs((int)m) - 1 : 0);
+        const unsigned v = old + r;                                            // < 1024 + 32
+        if (g & 1) rb[g >> 1] |= v << 16; else rb[g >> 1] = v;
         __syncwarp();
     }
     __syncthreads();
@@ -170,20 +181,16 @@ scatter_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* _
     sm.symbase[tid] = sb;
     sm.gbase[tid] = cbase[(size_t)b * 256 + tid] + tile_hist[(size_t)tile * 256 + tid] - sb;   // dst of sorted index j: gbase[d] + j
     __syncthreads();
-    for (unsigned g = 0; g < WSPAN / 32; ++g) {                                // stable ranking, 32 keys at a time per warp
+#pragma unroll
+    for (unsigned g = 0; g < WSPAN / 32; ++g) {                                // place (keys come back from L1 / L2; no ballots left)
         const unsigned i = lo + w * WSPAN + g * 32 + lane;
-        const bool valid = i < hi;
-        const unsigned long long key = valid ? kin[i] : 0ull;
-        const unsigned val = valid ? vin[i] : 0u;
-        const unsigned d = valid ? (unsigned)(key >> shift) & 255u : 0u;
-        const unsigned m = warp_match_u8(d, valid);
-        const unsigned r = __popc(m & ((1u << lane) - 1u));
-        unsigned base = 0;
-        if (valid) base = sm.wcnt[w][d];
-        __syncwarp();
-        if (valid && r == 0) sm.wcnt[w][d] = base + __popc(m);
-        __syncwarp();
-        if (valid) { const unsigned p = sm.symbase[d] + base + r; sm.skey[p] = key; sm.sval[p] = val; }
+        if (i < hi) {
+            const unsigned long long key = kin[i];
+            const unsigned d = (unsigned)(key >> shift) & 255u;
+            const unsigned v = (g & 1) ? rb[g >> 1] >> 16 : rb[g >> 1] & 0xffffu;
+            const unsigned p = sm.symbase[d] + sm.wcnt[w][d] + v;
+            sm.skey[p] = key; sm.sval[p] = vin[i];
+        }
     }
     __syncthreads();
     unsigned long long* kout = Kout + bk.e0;
