@@ -485,11 +485,14 @@ int rcz_bwt_decode_run(rcz_ctx* c, const void* in_base, const uint64_t* in_off, 
     for (size_t i = 0; i < nblocks; ++i) if (in_off[i] > (1ull << 62) || out_off[i] > (1ull << 62)) return RCZ_E_ARG;
     rt_set_device(c->device);
 
-    // ---- host-side geometry.  Blocks are processed in GROUPS of <= 16 Mi symbols, one kernel sequence per group: the
-    // group's link tables (4 B / symbol, <= 64 MiB) are written by the partition kernel and walked right away, so the
-    // n dependent random hops per block hit the 126 MB L2 instead of HBM (measured with tools/micro/gather_bench.cu:
-    // ~285 G hops/s for a <= 64 MiB working set vs ~73 G hops/s from HBM).  All offsets in Blk are group-relative and the
-    // workspaces are reused by every group.  RCZ_IBWT_* are tuning overrides for tools/ibwt_sweep.sh.
+    // ---- host-side geometry.  Blocks are processed in GROUPS of <= group_syms symbols (default 2^30: one group for 256 blocks of
+    // 4 MiB), one kernel sequence per group; all offsets in Blk are group-relative and the workspaces are reused by every group.
+    // L2 residency of the link tables does not come from small groups (a group of a few blocks leaves the GPU idle at every
+    // kernel boundary and pays a chain tail per group: measured 2-6x slower, profiles/r2_ibwt_sweeps.txt) but from SHORT chains:
+    // rows are sampled every 2^slog = 16, so a chain lives for ~16 hops and the work queue (block-major) keeps the live chains
+    // inside the last one or two blocks' tables (L2 hit rate 69 % against 32 % with a stride of 64, profiles/r2_ibwt_walk_kernel.txt).
+    // Ceiling for this access pattern, tools/micro/gather_bench2.cu: 285 G hops/s while the table fits L2.  RCZ_IBWT_* are tuning
+    // overrides used by the sweeps.
     const unsigned tune_slog = getenv("RCZ_IBWT_SLOG") ? (unsigned)atoi(getenv("RCZ_IBWT_SLOG")) : 4u;
     const unsigned tune_place = getenv("RCZ_IBWT_PLACE_CTAS") ? (unsigned)atoi(getenv("RCZ_IBWT_PLACE_CTAS")) : 8u;
     const unsigned tune_ctas = getenv("RCZ_IBWT_WALK_CTAS") ? (unsigned)atoi(getenv("RCZ_IBWT_WALK_CTAS")) : 4u;

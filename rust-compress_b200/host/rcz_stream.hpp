@@ -342,7 +342,11 @@ inline std::vector<uint8_t> decode_simple(Context& ctx, const uint8_t* input, si
 template <class W> class Encoder {                                           // bwt/mod.rs:437-518
   public:
     size_t batch_blocks = 64;
-    Encoder(Context& ctx, W w, size_t block_size) : ctx_(ctx), w_(std::move(w)), block_size_(block_size) {}
+    // block_size <= 16,777,214: the inverse transform's link table packs a 24-bit position (rcz.h); the reference's own docs suggest
+    // 4 MiB (bwt/mod.rs:32).  Refusing here keeps the Encoder from writing streams its own Decoder cannot read back.
+    Encoder(Context& ctx, W w, size_t block_size) : ctx_(ctx), w_(std::move(w)), block_size_(block_size) {
+        if (block_size == 0 || block_size > 0xFFFFFEu) throw io_error(ErrorKind::InvalidInput, "bwt::Encoder: block_size must be in 1..16777214", RCZ_E_UNSUPPORTED);
+    }
     size_t write(const uint8_t* buf, size_t len) {
         if (!wrote_header_) { detail::write_u32_le(w_, (uint32_t)block_size_); wrote_header_ = true; }   // even for an empty write (App. B #2)
         size_t done = 0;
