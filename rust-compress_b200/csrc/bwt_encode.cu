@@ -6,15 +6,18 @@
 // encoder at bwt/mod.rs:470-475.  The suffix array is unique, so any correct sort is bit-exact; the order is the
 // reference's slice order: a suffix that is a proper prefix of another sorts first (implicit end marker below 0x00).
 //
-// Shape on the GPU — prefix doubling over LSD radix sorts, all blocks of a batch in lock step:
-//   round 0   key = first 7 symbols, 9 bits each (byte+1; 0 = past the end)           -> 8 radix passes
-//   round r   key = (rank_h[i] << b) | (i+h < n ? rank_h[i+h]+1 : 0),  h = 7 * 2^(r-1)  -> ceil(2b/8) passes
-//   after every round: group heads in the sorted keys give the new ranks; a block whose n keys are all distinct is
-//   finished and its L column / origin are gathered at once.  Random data (BASELINE config 3) finishes in round 0.
-// One radix pass = per-tile digit histogram, per-block exclusive scan, stable 256-way partition per tile
-// (ballot-based equal-key ranking inside each warp, shared-memory staging so every (tile, digit) run leaves as one contiguous
-// store).  No host synchronisation is needed: finished blocks are skipped on the device (state[]), so the whole
-// round schedule can be enqueued blind (DEVICE_ASYNC); the synchronous modes read one counter per round to stop early.
+// Shape on the GPU — prefix doubling (Larsson-Sadakane) over LSD radix sorts with DISCARDING, all blocks of a batch in lock step:
+//   round 0   key = first 5 symbols, 9 bits each (byte+1; 0 = past the end)                                   -> 6 radix passes over n keys
+//   round r   only the suffixes whose group (equal key so far) still has more than one member are sorted again:
+//             key = (group head << b) | (i+h < n ? rank[i+h]+1 : 0),  h = 5 * 2^(r-1)                         -> 6 passes over the ACTIVE keys
+//   after every round the sorted active keys are cut into groups again: a suffix takes the place `group head + offset inside its
+//   old group`, its rank becomes the head of its new (finer) group, and a group of one is resolved for good.  Random data (BASELINE
+//   config 3) is resolved after round 0 except for a handful of suffixes; hexdump text needs round 1 in full and a few per cent of
+//   round 2.  (Round 1 of this file sorted all n keys in every round: 8 + 6 passes per round.)
+// One radix pass = per-tile digit histogram, per-block exclusive scan, stable 256-way partition per tile (ballot-based equal-key
+// ranking inside each warp, done once and kept in registers; shared-memory staging so every (tile, digit) run leaves as one contiguous
+// store).  No host synchronisation is needed: finished blocks are skipped on the device (state[]), so the whole round schedule can be
+// enqueued blind (DEVICE_ASYNC); the synchronous modes read one counter per round to stop early.
 #include "rcz_internal.h"
 #include <algorithm>
 
@@ -26,6 +29,7 @@ constexpr int NW = NT / 32;
 constexpr int WSPAN = TB / NW;            // 1024 consecutive elements per warp
 constexpr int SPAN = 1024;                // rank-assignment granularity (one warp)
 constexpr unsigned NONE = 0xFFFFFFFFu;
+constexpr int NSYM0 = 5;                 // symbols in a round-0 key (45 bits: 6 radix passes)
 constexpr unsigned ACTIVE = 0;
 
 struct Blk {
@@ -61,39 +65,24 @@ init_keys_kernel(const uint8_t* __restrict__ in_base, const Blk* __restrict__ bl
         const unsigned i = lo + j;
         unsigned long long key = 0;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) key = (key << 9) | (i + k < bk.n ? (unsigned long long)s[j + k] + 1ull : 0ull);
+        for (int k = 0; k < NSYM0; ++k) key = (key << 9) | (i + k < bk.n ? (unsigned long long)s[j + k] + 1ull : 0ull);
         K[bk.e0 + i] = key;
-        V[bk.e0 + i] = i;
-    }
-}
-
-// ------------------------------------------------------------------------------------------ round-r keys
-__global__ void __launch_bounds__(NT)
-double_keys_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* __restrict__ state, const unsigned* __restrict__ R,
-                   unsigned h, unsigned bits, unsigned long long* __restrict__ K, unsigned* __restrict__ V) {
-    const unsigned tile = blockIdx.x, tid = threadIdx.x;
-    const unsigned b = find_blk_tile(blks, nblocks, tile);
-    const Blk bk = blks[b];
-    if (bk.skip || state[b] != ACTIVE) return;
-    const unsigned lo = (tile - bk.tile0) * TB, hi = min(bk.n, lo + TB);
-    const unsigned* r = R + bk.e0;
-    for (unsigned i = lo + tid; i < hi; i += NT) {
-        const unsigned long long r2 = (i + h < bk.n && i + h >= i) ? (unsigned long long)r[i + h] + 1ull : 0ull;
-        K[bk.e0 + i] = ((unsigned long long)r[i] << bits) | r2;
         V[bk.e0 + i] = i;
     }
 }
 
 // ------------------------------------------------------------------------------------------ radix pass: histogram
 __global__ void __launch_bounds__(NT)
-hist_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* __restrict__ state, const unsigned long long* __restrict__ K,
-            unsigned shift, unsigned* __restrict__ tile_hist) {
+hist_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* __restrict__ state, const unsigned* __restrict__ cnt,
+            const unsigned long long* __restrict__ K, unsigned shift, unsigned* __restrict__ tile_hist) {
     __shared__ unsigned hsm[256];
     const unsigned tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const unsigned b = find_blk_tile(blks, nblocks, tile);
     const Blk bk = blks[b];
     if (bk.skip || state[b] != ACTIVE) return;
-    const unsigned lo = (tile - bk.tile0) * TB, hi = min(bk.n, lo + TB);
+    const unsigned nn = cnt[b];                                                // keys being sorted in this round (n in round 0, the active ones later)
+    const unsigned lo = (tile - bk.tile0) * TB, hi = min(nn, lo + TB);
+    if (lo >= nn) return;
     hsm[tid] = 0;
     __syncthreads();
     const unsigned long long* k = K + bk.e0;
@@ -110,19 +99,21 @@ hist_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* __re
 
 // tile_hist[tile][d] <- number of d's in earlier tiles of the block; cbase[blk][d] <- number of digits < d
 __global__ void __launch_bounds__(256)
-scan_kernel(const Blk* __restrict__ blks, const unsigned* __restrict__ state, unsigned* __restrict__ tile_hist, unsigned* __restrict__ cbase) {
+scan_kernel(const Blk* __restrict__ blks, const unsigned* __restrict__ state, const unsigned* __restrict__ cnt, unsigned* __restrict__ tile_hist,
+            unsigned* __restrict__ cbase) {
     __shared__ unsigned scratch[40];
     const unsigned b = blockIdx.x, c = threadIdx.x;
     const Blk bk = blks[b];
     if (bk.skip || state[b] != ACTIVE) return;
     unsigned run = 0;
-    for (unsigned t0 = 0; t0 < bk.ntiles; t0 += 16) {                         // 16 independent loads in flight, then the running sums
+    const unsigned nt = (cnt[b] + TB - 1) / TB;                                // tiles that hold keys in this round
+    for (unsigned t0 = 0; t0 < nt; t0 += 16) {                                // 16 independent loads in flight, then the running sums
         unsigned hc[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) hc[k] = t0 + k < bk.ntiles ? tile_hist[(size_t)(bk.tile0 + t0 + k) * 256 + c] : 0u;
+        for (int k = 0; k < 16; ++k) hc[k] = t0 + k < nt ? tile_hist[(size_t)(bk.tile0 + t0 + k) * 256 + c] : 0u;
 #pragma unroll
         for (int k = 0; k < 16; ++k)
-            if (t0 + k < bk.ntiles) { tile_hist[(size_t)(bk.tile0 + t0 + k) * 256 + c] = run; run += hc[k]; }
+            if (t0 + k < nt) { tile_hist[(size_t)(bk.tile0 + t0 + k) * 256 + c] = run; run += hc[k]; }
     }
     unsigned total;
     const unsigned ex = block_excl_scan_add<256>(run, scratch, &total);
@@ -140,8 +131,8 @@ struct ScatSmem {
 };
 
 __global__ void __launch_bounds__(NT, 2)
-scatter_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* __restrict__ state, const unsigned long long* __restrict__ Kin,
-               const unsigned* __restrict__ Vin, unsigned long long* __restrict__ Kout, unsigned* __restrict__ Vout, unsigned shift,
+scatter_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* __restrict__ state, const unsigned* __restrict__ cnt,
+               const unsigned long long* __restrict__ Kin, const unsigned* __restrict__ Vin, unsigned long long* __restrict__ Kout, unsigned* __restrict__ Vout, unsigned shift,
                const unsigned* __restrict__ tile_hist, const unsigned* __restrict__ cbase) {
     RCZ_DYN_SMEM(raw);
     ScatSmem& sm = *reinterpret_cast<ScatSmem*>(raw);
@@ -149,7 +140,10 @@ scatter_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* _
     const unsigned b = find_blk_tile(blks, nblocks, tile);
     const Blk bk = blks[b];
     if (bk.skip || state[b] != ACTIVE) return;
-    const unsigned lo = (tile - bk.tile0) * TB, hi = min(bk.n, lo + TB), tlen = hi - lo;
+    const unsigned nn = cnt[b];
+    const unsigned lo = (tile - bk.tile0) * TB;
+    if (lo >= nn) return;
+    const unsigned hi = min(nn, lo + TB), tlen = hi - lo;
     const unsigned long long* kin = Kin + bk.e0;
     const unsigned* vin = Vin + bk.e0;
 
@@ -203,65 +197,109 @@ scatter_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* _
     }
 }
 
-// ------------------------------------------------------------------------------------------ group heads per span
+// ------------------------------------------------------------------------------------------ regrouping after a sort
+// The sorted (active) keys of a block, cnt[b] of them, one warp per span of 1024: where subgroups (equal key) and groups (equal
+// high part = old group head) begin.
 __global__ void __launch_bounds__(128)
-heads_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nspans, const unsigned* __restrict__ state,
-             const unsigned long long* __restrict__ K, unsigned* __restrict__ span_heads, unsigned* __restrict__ span_last) {
+heads_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nspans, const unsigned* __restrict__ state, const unsigned* __restrict__ cnt,
+             const unsigned long long* __restrict__ K, unsigned bits, unsigned* __restrict__ span_last, unsigned* __restrict__ span_glast) {
     const unsigned lane = threadIdx.x & 31;
     const unsigned span = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (span >= nspans) return;
     const unsigned b = find_blk_span(blks, nblocks, span);
     const Blk bk = blks[b];
     if (bk.skip || state[b] != ACTIVE) return;
-    const unsigned lo = (span - bk.span0) * SPAN, hi = min(bk.n, lo + SPAN);
+    const unsigned nn = cnt[b];
+    const unsigned lo = (span - bk.span0) * SPAN, hi = min(nn, lo + SPAN);
     const unsigned long long* k = K + bk.e0;
-    unsigned cnt = 0, last = NONE;
+    unsigned last = NONE, glast = NONE;
     for (unsigned base = lo; base < hi; base += 32) {
         const unsigned j = base + lane;
-        const bool head = j < hi && (j == 0 || k[j] != k[j - 1]);
-        const unsigned m = __ballot_sync(RCZ_FULL, head);
-        cnt += __popc(m);
+        const unsigned long long kj = j < hi ? k[j] : 0ull, kp = (j < hi && j > 0) ? k[j - 1] : 0ull;
+        const unsigned m = __ballot_sync(RCZ_FULL, j < hi && (j == 0 || kj != kp));
+        const unsigned gm = __ballot_sync(RCZ_FULL, j < hi && (j == 0 || (kj >> bits) != (kp >> bits)));
         if (m) last = base + 31u - (unsigned)__clz((int)m);
+        if (gm) glast = base + 31u - (unsigned)__clz((int)gm);
     }
-    if (lane == 0) { span_heads[span] = cnt; span_last[span] = last; }
+    if (lane == 0) { span_last[span] = last; span_glast[span] = glast; }
 }
 
-// per block: all keys distinct -> state = round + 1 (finished in this round); else span_last <- last head before the span
+// per block: span_last / span_glast <- the last (sub)group head BEFORE the span (position 0 is always a head)
 __global__ void __launch_bounds__(256)
-block_state_kernel(const Blk* __restrict__ blks, unsigned* __restrict__ state, const unsigned* __restrict__ span_heads,
-                   unsigned* __restrict__ span_last, unsigned round, unsigned* __restrict__ nactive) {
-    __shared__ unsigned ssum[256], smax[256];
-    __shared__ unsigned done;
+carry_kernel(const Blk* __restrict__ blks, const unsigned* __restrict__ state, unsigned* __restrict__ span_last, unsigned* __restrict__ span_glast) {
+    __shared__ unsigned smax[2][256];
     const unsigned b = blockIdx.x, t = threadIdx.x;
     const Blk bk = blks[b];
     if (bk.skip || state[b] != ACTIVE) return;
     const unsigned per = (bk.nspans + 255) / 256;
     const unsigned s0 = min(bk.nspans, t * per), s1 = min(bk.nspans, s0 + per);
-    unsigned sum = 0, mx = 0;                                                  // positions are stored +1 so that 0 == none
-    for (unsigned s = s0; s < s1; ++s) { sum += span_heads[bk.span0 + s]; const unsigned l = span_last[bk.span0 + s]; if (l != NONE) mx = l + 1; }
-    ssum[t] = sum; smax[t] = mx;
-    __syncthreads();
-    if (t == 0) {
-        unsigned total = 0, run = 0;
-        for (unsigned i = 0; i < 256; ++i) { total += ssum[i]; const unsigned m = smax[i]; smax[i] = run; if (m) run = m; }
-        done = total == bk.n;
-        if (done) state[b] = round + 1; else atomicAdd(nactive, 1u);
-    }
-    __syncthreads();
-    if (done) return;
-    unsigned run = smax[t];
+    unsigned mx = 0, gmx = 0;                                                  // positions are stored +1 so that 0 == none
     for (unsigned s = s0; s < s1; ++s) {
-        const unsigned l = span_last[bk.span0 + s];
-        span_last[bk.span0 + s] = run ? run - 1 : 0u;                          // position 0 is always a head
+        const unsigned l = span_last[bk.span0 + s], g = span_glast[bk.span0 + s];
+        if (l != NONE) mx = l + 1;
+        if (g != NONE) gmx = g + 1;
+    }
+    smax[0][t] = mx; smax[1][t] = gmx;
+    __syncthreads();
+    if (t < 2) { unsigned run = 0; for (unsigned i = 0; i < 256; ++i) { const unsigned m = smax[t][i]; smax[t][i] = run; if (m) run = m; } }
+    __syncthreads();
+    unsigned run = smax[0][t], grun = smax[1][t];
+    for (unsigned s = s0; s < s1; ++s) {
+        const unsigned l = span_last[bk.span0 + s], g = span_glast[bk.span0 + s];
+        span_last[bk.span0 + s] = run ? run - 1 : 0u;
+        span_glast[bk.span0 + s] = grun ? grun - 1 : 0u;
         if (l != NONE) run = l + 1;
+        if (g != NONE) grun = g + 1;
     }
 }
 
-// R[V[j]] = position of the head of j's group
+// Every sorted active key p (old group head g in its high bits): new place in the suffix array = g + (p - first p of the group),
+// new rank = g + (head of p's subgroup - first p of the group); a subgroup of one is resolved (flag 0).
 __global__ void __launch_bounds__(128)
-assign_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nspans, const unsigned* __restrict__ state,
-              const unsigned long long* __restrict__ K, const unsigned* __restrict__ V, const unsigned* __restrict__ span_carry,
-              unsigned* __restrict__ R) {
+update_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nspans, const unsigned* __restrict__ state, const unsigned* __restrict__ cnt,
+              const unsigned long long* __restrict__ K, const unsigned* __restrict__ V, unsigned bits, const unsigned* __restrict__ span_carry,
+              const unsigned* __restrict__ span_gcarry, unsigned* __restrict__ SA, unsigned* __restrict__ R, uint8_t* __restrict__ aflag) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned span = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (span >= nspans) return;
+    const unsigned b = find_blk_span(blks, nblocks, span);
+    const Blk bk = blks[b];
+    if (bk.skip || state[b] != ACTIVE) return;
+    const unsigned nn = cnt[b];
+    const unsigned lo = (span - bk.span0) * SPAN, hi = min(nn, lo + SPAN);
+    const unsigned long long* k = K + bk.e0;
+    const unsigned* v = V + bk.e0;
+    unsigned* sa = SA + bk.e0;
+    unsigned* r = R + bk.e0;
+    uint8_t* af = aflag + bk.e0;
+    unsigned carry = span_carry[span], gcarry = span_gcarry[span];
+    for (unsigned base = lo; base < hi; base += 32) {
+        const unsigned j = base + lane;
+        const bool in = j < hi;
+        const unsigned long long kj = in ? k[j] : 0ull, kp = (in && j > 0) ? k[j - 1] : 0ull;
+        const unsigned long long kn = (in && j + 1 < nn) ? k[j + 1] : ~0ull;
+        const bool head = in && (j == 0 || kj != kp);
+        const bool ghead = in && (j == 0 || (kj >> bits) != (kp >> bits));
+        const unsigned m = __ballot_sync(RCZ_FULL, head), gm = __ballot_sync(RCZ_FULL, ghead);
+        const unsigned upto = 0xFFFFFFFFu >> (31 - lane);
+        const unsigned hp = (m & upto) ? base + 31u - (unsigned)__clz((int)(m & upto)) : carry;
+        const unsigned gp = (gm & upto) ? base + 31u - (unsigned)__clz((int)(gm & upto)) : gcarry;
+        if (in) {
+            const unsigned g = (unsigned)(kj >> bits);
+            const unsigned pos = g + (j - gp), val = v[j];
+            sa[pos] = val;
+            r[val] = g + (hp - gp);
+            af[pos] = (head && (j + 1 >= nn || kn != kj)) ? 0 : 1;            // alone in its subgroup: resolved
+        }
+        if (m) carry = base + 31u - (unsigned)__clz((int)m);
+        if (gm) gcarry = base + 31u - (unsigned)__clz((int)gm);
+    }
+}
+
+// active suffixes per span of the suffix array (all n positions)
+__global__ void __launch_bounds__(128)
+count_active_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nspans, const unsigned* __restrict__ state,
+                    const uint8_t* __restrict__ aflag, unsigned* __restrict__ span_act) {
     const unsigned lane = threadIdx.x & 31;
     const unsigned span = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (span >= nspans) return;
@@ -269,18 +307,68 @@ assign_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nspans, c
     const Blk bk = blks[b];
     if (bk.skip || state[b] != ACTIVE) return;
     const unsigned lo = (span - bk.span0) * SPAN, hi = min(bk.n, lo + SPAN);
-    const unsigned long long* k = K + bk.e0;
-    const unsigned* v = V + bk.e0;
-    unsigned* r = R + bk.e0;
-    unsigned carry = span_carry[span];
+    const uint8_t* af = aflag + bk.e0;
+    unsigned c = 0;
+    for (unsigned j = lo + lane; j < hi; j += 32) c += af[j] ? 1u : 0u;
+    c = warp_reduce_add(c);
+    if (lane == 0) span_act[span] = c;
+}
+
+// per block: span_act <- active suffixes before the span; cnt_next[b] = their total; none left -> the block is finished in this round
+__global__ void __launch_bounds__(256)
+active_scan_kernel(const Blk* __restrict__ blks, unsigned* __restrict__ state, unsigned* __restrict__ span_act, unsigned* __restrict__ cnt_next,
+                   unsigned round, unsigned* __restrict__ nactive) {
+    __shared__ unsigned ssum[256];
+    const unsigned b = blockIdx.x, t = threadIdx.x;
+    const Blk bk = blks[b];
+    if (bk.skip || state[b] != ACTIVE) return;
+    const unsigned per = (bk.nspans + 255) / 256;
+    const unsigned s0 = min(bk.nspans, t * per), s1 = min(bk.nspans, s0 + per);
+    unsigned sum = 0;
+    for (unsigned s = s0; s < s1; ++s) sum += span_act[bk.span0 + s];
+    ssum[t] = sum;
+    __syncthreads();
+    if (t == 0) {
+        unsigned run = 0;
+        for (unsigned i = 0; i < 256; ++i) { const unsigned x = ssum[i]; ssum[i] = run; run += x; }
+        cnt_next[b] = run;
+        if (run == 0) state[b] = round + 1; else atomicAdd(nactive, 1u);
+    }
+    __syncthreads();
+    unsigned run = ssum[t];
+    for (unsigned s = s0; s < s1; ++s) { const unsigned x = span_act[bk.span0 + s]; span_act[bk.span0 + s] = run; run += x; }
+}
+
+// next round's keys: the active suffixes in suffix-array order, key = (rank (= group head) << bits) | (rank of the suffix h further + 1)
+__global__ void __launch_bounds__(128)
+compact_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nspans, const unsigned* __restrict__ state, const uint8_t* __restrict__ aflag,
+               const unsigned* __restrict__ span_abase, const unsigned* __restrict__ SA, const unsigned* __restrict__ R, unsigned h, unsigned bits,
+               unsigned long long* __restrict__ K, unsigned* __restrict__ V) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned span = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (span >= nspans) return;
+    const unsigned b = find_blk_span(blks, nblocks, span);
+    const Blk bk = blks[b];
+    if (bk.skip || state[b] != ACTIVE) return;
+    const unsigned lo = (span - bk.span0) * SPAN, hi = min(bk.n, lo + SPAN);
+    const uint8_t* af = aflag + bk.e0;
+    const unsigned* sa = SA + bk.e0;
+    const unsigned* r = R + bk.e0;
+    unsigned long long* k = K + bk.e0;
+    unsigned* v = V + bk.e0;
+    unsigned p0 = span_abase[span];
     for (unsigned base = lo; base < hi; base += 32) {
         const unsigned j = base + lane;
-        const bool head = j < hi && (j == 0 || k[j] != k[j - 1]);
-        const unsigned m = __ballot_sync(RCZ_FULL, head);
-        const unsigned below = m & (0xFFFFFFFFu >> (31 - lane));
-        const unsigned rank = below ? base + 31u - (unsigned)__clz((int)below) : carry;
-        if (j < hi) r[v[j]] = rank;
-        if (m) carry = base + 31u - (unsigned)__clz((int)m);
+        const bool act = j < hi && af[j] != 0;
+        const unsigned m = __ballot_sync(RCZ_FULL, act);
+        if (act) {
+            const unsigned p = p0 + __popc(m & ((1u << lane) - 1u));
+            const unsigned i = sa[j];
+            const unsigned long long r2 = (i + h < bk.n && i + h >= i) ? (unsigned long long)r[i + h] + 1ull : 0ull;
+            k[p] = ((unsigned long long)r[i] << bits) | r2;
+            v[p] = i;
+        }
+        p0 += __popc(m);
     }
 }
 
@@ -306,11 +394,12 @@ gather_kernel(const uint8_t* __restrict__ in_base, const Blk* __restrict__ blks,
 
 __global__ void init_state_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned* __restrict__ state, unsigned* __restrict__ nactive,
                                   unsigned nrounds, uint32_t* __restrict__ origin, int32_t* __restrict__ status,
-                                  const int32_t* __restrict__ host_status) {
+                                  const int32_t* __restrict__ host_status, unsigned* __restrict__ cnt0) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nrounds) nactive[i] = 0;
     if (i < nblocks) {
         state[i] = ACTIVE;
+        cnt0[i] = blks[i].n;
         origin[i] = 0;
         status[i] = blks[i].skip ? host_status[i] : RCZ_E_CUDA;               // overwritten by gather_kernel when the block finishes
     }
@@ -376,18 +465,22 @@ extern "C" int rcz_bwt_encode_blocks(rcz_ctx* c, const void* in_base, const uint
     void *wK, *wV, *wR, *wM;
     st = ctx_ws(c, WS_A, al((size_t)max_elems * 8) * 2 + 256, &wK); if (st) return st;
     st = ctx_ws(c, WS_B, al((size_t)max_elems * 4) * 2 + 256, &wV); if (st) return st;
-    st = ctx_ws(c, WS_C, al((size_t)max_elems * 4) + 256, &wR); if (st) return st;
+    st = ctx_ws(c, WS_C, al((size_t)max_elems * 4) * 2 + al((size_t)max_elems) + 256, &wR); if (st) return st;   // ranks | suffix array | active flags
     const size_t sz_hist = al((size_t)max_tiles * 256 * 4), sz_cb = al(max_blocks * 256 * 4), sz_sp = al((size_t)max_spans * 4), sz_state = al(max_blocks * 4);
-    st = ctx_ws(c, WS_D, sz_hist + sz_cb + 2 * sz_sp + sz_state + 1024, &wM); if (st) return st;
+    st = ctx_ws(c, WS_D, sz_hist + sz_cb + 3 * sz_sp + 3 * sz_state + 1024, &wM); if (st) return st;
     unsigned long long* K[2] = {(unsigned long long*)wK, (unsigned long long*)((uint8_t*)wK + al((size_t)max_elems * 8))};
     unsigned* V[2] = {(unsigned*)wV, (unsigned*)((uint8_t*)wV + al((size_t)max_elems * 4))};
     unsigned* R = (unsigned*)wR;
+    unsigned* SA = (unsigned*)((uint8_t*)wR + al((size_t)max_elems * 4));
+    uint8_t* aflag = (uint8_t*)wR + 2 * al((size_t)max_elems * 4);
     uint8_t* m = (uint8_t*)wM;
     unsigned* tile_hist = (unsigned*)m; m += sz_hist;
     unsigned* cbase = (unsigned*)m; m += sz_cb;
-    unsigned* span_heads = (unsigned*)m; m += sz_sp;
     unsigned* span_last = (unsigned*)m; m += sz_sp;
+    unsigned* span_glast = (unsigned*)m; m += sz_sp;
+    unsigned* span_act = (unsigned*)m; m += sz_sp;
     unsigned* state = (unsigned*)m; m += sz_state;
+    unsigned* cntbuf[2] = {(unsigned*)m, (unsigned*)(m + sz_state)}; m += 2 * sz_state;
     unsigned* nactive = (unsigned*)m;                                          // one counter per round (<= 64)
 
     RCZ_CK(c, RCZ_KERNEL_SMEM_OPTIN(scatter_kernel, sizeof(ScatSmem)));
@@ -398,30 +491,37 @@ extern "C" int rcz_bwt_encode_blocks(rcz_ctx* c, const void* in_base, const uint
         uint32_t* d_org = ds.out_ptr<uint32_t>(o_org) + g.b0;
         int32_t* d_st = ds.out_ptr<int32_t>(o_st) + g.b0;
         unsigned bits = 1; while ((1ull << bits) <= g.nmax) ++bits;            // rank2 takes values 0..n
-        unsigned nrounds = 1; while (7ull << (nrounds - 1) < g.nmax) ++nrounds; // after round r ranks cover 7 * 2^r symbols
+        unsigned nrounds = 1; while ((unsigned long long)NSYM0 << (nrounds - 1) < g.nmax) ++nrounds;   // after round r ranks cover NSYM0 * 2^r symbols
         if (nrounds > 60) nrounds = 60;
         RCZ_KLAUNCH(c, init_state_kernel, (std::max(nb, 64u) + 255) / 256, 256, 0, dblk, nb, state, nactive, 64u, d_org, d_st,
-                    ds.in_ptr<int32_t>(i_hst) + g.b0);
+                    ds.in_ptr<int32_t>(i_hst) + g.b0, cntbuf[0]);
         if (g.ntiles == 0) continue;
         const unsigned sgrid = (g.nspans + 3) / 4;
         for (unsigned round = 0; round < nrounds; ++round) {
-            unsigned npass;
+            const unsigned* cnt = cntbuf[round & 1];
+            unsigned* cnt_next = cntbuf[(round & 1) ^ 1];
+            unsigned npass, gbits;
             if (round == 0) {
                 RCZ_KLAUNCH(c, init_keys_kernel, g.ntiles, NT, 0, din, dblk, nb, K[0], V[0]);
-                npass = 8;
+                npass = (9 * NSYM0 + 7) / 8; npass += npass & 1;              // even: the sorted data ends up in buffer 0
+                gbits = 63;                                                    // round 0: one group (the whole block), head 0
             } else {
-                RCZ_KLAUNCH(c, double_keys_kernel, g.ntiles, NT, 0, dblk, nb, state, R, (unsigned)(7u << (round - 1)), bits, K[0], V[0]);
-                npass = (2 * bits + 7) / 8; npass += npass & 1;               // even: the sorted data ends up in buffer 0
+                RCZ_KLAUNCH(c, compact_kernel, sgrid, 128, 0, dblk, nb, g.nspans, state, aflag, span_act, SA, R, (unsigned)((unsigned)NSYM0 << (round - 1)), bits, K[0], V[0]);
+                npass = (2 * bits + 7) / 8; npass += npass & 1;
+                gbits = bits;
             }
             for (unsigned p = 0; p < npass; ++p) {
                 const unsigned a = p & 1;
-                RCZ_KLAUNCH(c, hist_kernel, g.ntiles, NT, 0, dblk, nb, state, K[a], p * 8, tile_hist);
-                RCZ_KLAUNCH(c, scan_kernel, nb, 256, 0, dblk, state, tile_hist, cbase);
-                RCZ_KLAUNCH(c, scatter_kernel, g.ntiles, NT, sizeof(ScatSmem), dblk, nb, state, K[a], V[a], K[a ^ 1], V[a ^ 1], p * 8, tile_hist, cbase);
+                RCZ_KLAUNCH(c, hist_kernel, g.ntiles, NT, 0, dblk, nb, state, cnt, K[a], p * 8, tile_hist);
+                RCZ_KLAUNCH(c, scan_kernel, nb, 256, 0, dblk, state, cnt, tile_hist, cbase);
+                RCZ_KLAUNCH(c, scatter_kernel, g.ntiles, NT, sizeof(ScatSmem), dblk, nb, state, cnt, K[a], V[a], K[a ^ 1], V[a ^ 1], p * 8, tile_hist, cbase);
             }
-            RCZ_KLAUNCH(c, heads_kernel, sgrid, 128, 0, dblk, nb, g.nspans, state, K[0], span_heads, span_last);
-            RCZ_KLAUNCH(c, block_state_kernel, nb, 256, 0, dblk, state, span_heads, span_last, round, nactive + round);
-            RCZ_KLAUNCH(c, gather_kernel, g.ntiles, NT, 0, din, dblk, nb, state, round, V[0], dout, d_org, d_st);
+            RCZ_KLAUNCH(c, heads_kernel, sgrid, 128, 0, dblk, nb, g.nspans, state, cnt, K[0], gbits, span_last, span_glast);
+            RCZ_KLAUNCH(c, carry_kernel, nb, 256, 0, dblk, state, span_last, span_glast);
+            RCZ_KLAUNCH(c, update_kernel, sgrid, 128, 0, dblk, nb, g.nspans, state, cnt, K[0], V[0], gbits, span_last, span_glast, SA, R, aflag);
+            RCZ_KLAUNCH(c, count_active_kernel, sgrid, 128, 0, dblk, nb, g.nspans, state, aflag, span_act);
+            RCZ_KLAUNCH(c, active_scan_kernel, nb, 256, 0, dblk, state, span_act, cnt_next, round, nactive + round);
+            RCZ_KLAUNCH(c, gather_kernel, g.ntiles, NT, 0, din, dblk, nb, state, round, SA, dout, d_org, d_st);
             if (round + 1 == nrounds) break;
             if (mem_kind != RCZ_MEM_DEVICE_ASYNC) {                            // stop as soon as every block is finished
                 unsigned left = 0;
@@ -429,7 +529,6 @@ extern "C" int rcz_bwt_encode_blocks(rcz_ctx* c, const void* in_base, const uint
                 RCZ_CK(c, rt_stream_sync(c->stream));
                 if (left == 0) break;
             }
-            RCZ_KLAUNCH(c, assign_kernel, sgrid, 128, 0, dblk, nb, g.nspans, state, K[0], V[0], span_last, R);
         }
     }
     st = ctx_timer_end(c); if (st) return st;

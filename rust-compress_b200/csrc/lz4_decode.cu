@@ -291,7 +291,6 @@ lz4_parse_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict
         // ---- levels A and B: this warp's 1 KiB group, segments in reverse order
         const unsigned gbase = warp * 1024u, gend = gbase + 1024u;
         unsigned aA[16];                                                  // exit of (segment s, this lane) from the segment, two per register
-#pragma unroll
         const unsigned pbase = gbase + lane;                              // position of this lane in segment 0 of the group
         const uint8_t* const cpb = c + pbase;
         uint16_t* const ebb = sm.exitB + pbase;
@@ -1021,7 +1020,6 @@ static int lz4_host_pipelined(rcz_ctx* c, DescStager& ds, const Lz4Job& job, con
     void* pin; st = ctx_pinned(c, nblocks * 12 + 64, &pin); if (st) return st;
     uint64_t* p_len = (uint64_t*)pin; int32_t* p_st = (int32_t*)((uint8_t*)pin + nblocks * 8);
     const rt_stream_t dsm = c->aux[0];
-    bool all_full = true;
     for (size_t k = 0; k < nchunks; ++k) {
         RCZ_CK(c, rt_stream_wait_event(dsm, c->events[3 * k + 1]));
         size_t i = cut[k];
@@ -1031,7 +1029,6 @@ static int lz4_host_pipelined(rcz_ctx* c, DescStager& ds, const Lz4Job& job, con
         uint64_t csum = 0, isum = 0;
         for (size_t q = i; q < e; ++q) { csum += out_cap[q]; isum += in_len[q]; }
         if (csum > 8 * isum + (1u << 20)) {
-            all_full = false;
             RCZ_CK(c, rt_d2h(p_len + i, d_len + i, (e - i) * 8, dsm));
             RCZ_CK(c, rt_d2h(p_st + i, d_st + i, (e - i) * 4, dsm));
             RCZ_CK(c, rt_stream_sync(dsm));
@@ -1054,7 +1051,6 @@ static int lz4_host_pipelined(rcz_ctx* c, DescStager& ds, const Lz4Job& job, con
             i = j;
         }
     }
-    (void)all_full;
     RCZ_CK(c, rt_d2h(p_len, d_len, nblocks * 8, dsm));
     RCZ_CK(c, rt_d2h(p_st, d_st, nblocks * 4, dsm));
     RCZ_CK(c, rt_stream_sync(dsm));
