@@ -38,38 +38,36 @@ struct Blk {
     unsigned n, tile0, ntiles, span0, nspans, skip;
 };
 
-// Persistent grids: a kernel runs sm_count * k CTAs that share out the (block, tile) or (block, span) units that actually hold work in
-// this round — `units` of block b, counted from the device-side key counts — so a round in which most blocks are finished or nearly
-// resolved costs a few microseconds per kernel instead of a launch of ~10^5 CTAs that all look up their block and leave.
-// first unit of `units` (global ids [base, base + units)) for worker `me` of `nworkers`
-__device__ __forceinline__ unsigned first_unit(unsigned base, unsigned me, unsigned nworkers) { return (me + nworkers - base % nworkers) % nworkers; }
+__device__ __forceinline__ unsigned find_blk_tile(const Blk* blks, unsigned nblocks, unsigned tile) {
+    unsigned lo = 0, hi = nblocks;
+    while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (blks[mid].tile0 <= tile) lo = mid; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ unsigned find_blk_span(const Blk* blks, unsigned nblocks, unsigned span) {
+    unsigned lo = 0, hi = nblocks;
+    while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (blks[mid].span0 <= span) lo = mid; else hi = mid; }
+    return lo;
+}
 
 // ------------------------------------------------------------------------------------------ round-0 keys
 __global__ void __launch_bounds__(NT)
 init_keys_kernel(const uint8_t* __restrict__ in_base, const Blk* __restrict__ blks, unsigned nblocks, unsigned long long* __restrict__ K,
                  unsigned* __restrict__ V) {
     __shared__ uint8_t s[TB + 8];
-    const unsigned tid = threadIdx.x;
-    unsigned ubase = 0;
-    for (unsigned b = 0; b < nblocks; ++b) {
-        const Blk bk = blks[b];
-        if (bk.skip) continue;
-        const uint8_t* in = in_base + bk.in_off;
-        for (unsigned tl = first_unit(ubase, blockIdx.x, gridDim.x); tl < bk.ntiles; tl += gridDim.x) {
-            const unsigned lo = tl * TB, hi = min(bk.n, lo + TB);
-            for (unsigned j = tid; j < TB + 8; j += NT) s[j] = lo + j < bk.n ? in[lo + j] : 0;
-            __syncthreads();
-            for (unsigned j = tid; lo + j < hi; j += NT) {
-                const unsigned i = lo + j;
-                unsigned long long key = 0;
+    const unsigned tile = blockIdx.x, tid = threadIdx.x;
+    const Blk bk = blks[find_blk_tile(blks, nblocks, tile)];
+    if (bk.skip) return;
+    const uint8_t* in = in_base + bk.in_off;
+    const unsigned lo = (tile - bk.tile0) * TB, hi = min(bk.n, lo + TB);
+    for (unsigned j = tid; j < TB + 8; j += NT) s[j] = lo + j < bk.n ? in[lo + j] : 0;
+    __syncthreads();
+    for (unsigned j = tid; lo + j < hi; j += NT) {
+        const unsigned i = lo + j;
+        unsigned long long key = 0;
 #pragma unroll
-                for (int k = 0; k < NSYM0; ++k) key = (key << 9) | (i + k < bk.n ? (unsigned long long)s[j + k] + 1ull : 0ull);
-                K[bk.e0 + i] = key;
-                V[bk.e0 + i] = i;
-            }
-            __syncthreads();
-        }
-        ubase += bk.ntiles;
+        for (int k = 0; k < NSYM0; ++k) key = (key << 9) | (i + k < bk.n ? (unsigned long long)s[j + k] + 1ull : 0ull);
+        K[bk.e0 + i] = key;
+        V[bk.e0 + i] = i;
     }
 }
 
@@ -78,31 +76,25 @@ __global__ void __launch_bounds__(NT)
 hist_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* __restrict__ state, const unsigned* __restrict__ cnt,
             const unsigned long long* __restrict__ K, unsigned shift, unsigned* __restrict__ tile_hist) {
     __shared__ unsigned hsm[256];
-    const unsigned tid = threadIdx.x, lane = tid & 31;
-    unsigned ubase = 0;
-    for (unsigned b = 0; b < nblocks; ++b) {
-        if (state[b] != ACTIVE) continue;
-        const unsigned nn = cnt[b];                                            // keys being sorted in this round (n in round 0, the active ones later)
-        const unsigned nt = (nn + TB - 1) / TB;
-        if (nt == 0) continue;
-        const unsigned tile0 = blks[b].tile0;
-        const unsigned long long* k = K + blks[b].e0;
-        for (unsigned tl = first_unit(ubase, blockIdx.x, gridDim.x); tl < nt; tl += gridDim.x) {
-            const unsigned lo = tl * TB, hi = min(nn, lo + TB);
-            hsm[tid] = 0;
-            __syncthreads();
-            for (unsigned base = lo; base < hi; base += NT) {
-                const unsigned i = base + tid;
-                const bool valid = i < hi;
-                const unsigned d = valid ? (unsigned)(k[i] >> shift) & 255u : 0u;
-                const unsigned m = warp_match_u8(d, valid);
-                if (valid && (m & ((1u << lane) - 1u)) == 0) atomicAdd(&hsm[d], (unsigned)__popc(m));
-            }
-            __syncthreads();
-            tile_hist[(size_t)(tile0 + tl) * 256 + tid] = hsm[tid];
-        }
-        ubase += nt;
+    const unsigned tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const unsigned b = find_blk_tile(blks, nblocks, tile);
+    const Blk bk = blks[b];
+    if (bk.skip || state[b] != ACTIVE) return;
+    const unsigned nn = cnt[b];                                                // keys being sorted in this round (n in round 0, the active ones later)
+    const unsigned lo = (tile - bk.tile0) * TB, hi = min(nn, lo + TB);
+    if (lo >= nn) return;
+    hsm[tid] = 0;
+    __syncthreads();
+    const unsigned long long* k = K + bk.e0;
+    for (unsigned base = lo; base < hi; base += NT) {
+        const unsigned i = base + tid;
+        const bool valid = i < hi;
+        const unsigned d = valid ? (unsigned)(k[i] >> shift) & 255u : 0u;
+        const unsigned m = warp_match_u8(d, valid);
+        if (valid && (m & ((1u << lane) - 1u)) == 0) atomicAdd(&hsm[d], (unsigned)__popc(m));
     }
+    __syncthreads();
+    tile_hist[(size_t)tile * 256 + tid] = hsm[tid];
 }
 
 // tile_hist[tile][d] <- number of d's in earlier tiles of the block; cbase[blk][d] <- number of digits < d
@@ -144,71 +136,64 @@ scatter_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* _
                const unsigned* __restrict__ tile_hist, const unsigned* __restrict__ cbase) {
     RCZ_DYN_SMEM(raw);
     ScatSmem& sm = *reinterpret_cast<ScatSmem*>(raw);
-    const unsigned tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    unsigned ubase = 0;
-    for (unsigned b = 0; b < nblocks; ++b) {
-        if (state[b] != ACTIVE) continue;
-        const unsigned nn = cnt[b];
-        const unsigned nt = (nn + TB - 1) / TB;
-        if (nt == 0) continue;
-        const Blk bk = blks[b];
-        const unsigned long long* kin = Kin + bk.e0;
-        const unsigned* vin = Vin + bk.e0;
-        for (unsigned tl = first_unit(ubase, blockIdx.x, gridDim.x); tl < nt; tl += gridDim.x) {
-        const unsigned tile = bk.tile0 + tl;
-        const unsigned lo = tl * TB, hi = min(nn, lo + TB), tlen = hi - lo;
+    const unsigned tile = blockIdx.x, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const unsigned b = find_blk_tile(blks, nblocks, tile);
+    const Blk bk = blks[b];
+    if (bk.skip || state[b] != ACTIVE) return;
+    const unsigned nn = cnt[b];
+    const unsigned lo = (tile - bk.tile0) * TB;
+    if (lo >= nn) return;
+    const unsigned hi = min(nn, lo + TB), tlen = hi - lo;
+    const unsigned long long* kin = Kin + bk.e0;
+    const unsigned* vin = Vin + bk.e0;
 
-            for (unsigned i = tid; i < NW * 256; i += NT) (&sm.wcnt[0][0])[i] = 0;
-            __syncthreads();
-            // per-warp digit counts, and for every key its rank among the equal digits of the warp's 1024-key span (count before this group of
-            // 32 + rank inside the group): the 8 ballots are done ONCE per 32 keys and the ranks kept in registers, two per register
-            unsigned rb[WSPAN / 64];
-        #pragma unroll
-            for (unsigned g = 0; g < WSPAN / 32; ++g) {
-                const unsigned i = lo + w * WSPAN + g * 32 + lane;
-                const bool valid = i < hi;
-                const unsigned d = valid ? (unsigned)(kin[i] >> shift) & 255u : 0u;
-                const unsigned m = warp_match_u8(d, valid);
-                const unsigned r = __popc(m & ((1u << lane) - 1u));
-                unsigned old = 0;
-                if (valid && r == 0) { old = sm.wcnt[w][d]; sm.wcnt[w][d] = old + (unsigned)__popc(m); }
-                old = __shfl_sync(RCZ_FULL, old, m ? __ffs((int)m) - 1 : 0);
-                const unsigned v = old + r;                                            // < 1024 + 32
-                if (g & 1) rb[g >> 1] |= v << 16; else rb[g >> 1] = v;
-                __syncwarp();
-            }
-            __syncthreads();
-            unsigned tot = 0;                                                          // exclusive scan over warps, then digits
-        #pragma unroll
-            for (int k = 0; k < NW; ++k) { const unsigned x = sm.wcnt[k][tid]; sm.wcnt[k][tid] = tot; tot += x; }
-            unsigned dummy;
-            const unsigned sb = block_excl_scan_add<NT>(tot, sm.scratch, &dummy);
-            sm.symbase[tid] = sb;
-            sm.gbase[tid] = cbase[(size_t)b * 256 + tid] + tile_hist[(size_t)tile * 256 + tid] - sb;   // dst of sorted index j: gbase[d] + j
-            __syncthreads();
-        #pragma unroll
-            for (unsigned g = 0; g < WSPAN / 32; ++g) {                                // place (keys come back from L1 / L2; no ballots left)
-                const unsigned i = lo + w * WSPAN + g * 32 + lane;
-                if (i < hi) {
-                    const unsigned long long key = kin[i];
-                    const unsigned d = (unsigned)(key >> shift) & 255u;
-                    const unsigned v = (g & 1) ? rb[g >> 1] >> 16 : rb[g >> 1] & 0xffffu;
-                    const unsigned p = sm.symbase[d] + sm.wcnt[w][d] + v;
-                    sm.skey[p] = key; sm.sval[p] = vin[i];
-                }
-            }
-            __syncthreads();
-            unsigned long long* kout = Kout + bk.e0;
-            unsigned* vout = Vout + bk.e0;
-            for (unsigned j = tid; j < tlen; j += NT) {
-                const unsigned long long key = sm.skey[j];
-                const unsigned dst = sm.gbase[(unsigned)(key >> shift) & 255u] + j;
-                kout[dst] = key;
-                vout[dst] = sm.sval[j];
-            }
-        __syncthreads();                                                       // the staging arrays are reused by the next tile
+    for (unsigned i = tid; i < NW * 256; i += NT) (&sm.wcnt[0][0])[i] = 0;
+    __syncthreads();
+    // per-warp digit counts, and for every key its rank among the equal digits of the warp's 1024-key span (count before this group of
+    // 32 + rank inside the group): the 8 ballots are done ONCE per 32 keys and the ranks kept in registers, two per register
+    unsigned rb[WSPAN / 64];
+#pragma unroll
+    for (unsigned g = 0; g < WSPAN / 32; ++g) {
+        const unsigned i = lo + w * WSPAN + g * 32 + lane;
+        const bool valid = i < hi;
+        const unsigned d = valid ? (unsigned)(kin[i] >> shift) & 255u : 0u;
+        const unsigned m = warp_match_u8(d, valid);
+        const unsigned r = __popc(m & ((1u << lane) - 1u));
+        unsigned old = 0;
+        if (valid && r == 0) { old = sm.wcnt[w][d]; sm.wcnt[w][d] = old + (unsigned)__popc(m); }
+        old = __shfl_sync(RCZ_FULL, old, m ? __ffs((int)m) - 1 : 0);
+        const unsigned v = old + r;                                            // < 1024 + 32
+        if (g & 1) rb[g >> 1] |= v << 16; else rb[g >> 1] = v;
+        __syncwarp();
+    }
+    __syncthreads();
+    unsigned tot = 0;                                                          // exclusive scan over warps, then digits
+#pragma unroll
+    for (int k = 0; k < NW; ++k) { const unsigned x = sm.wcnt[k][tid]; sm.wcnt[k][tid] = tot; tot += x; }
+    unsigned dummy;
+    const unsigned sb = block_excl_scan_add<NT>(tot, sm.scratch, &dummy);
+    sm.symbase[tid] = sb;
+    sm.gbase[tid] = cbase[(size_t)b * 256 + tid] + tile_hist[(size_t)tile * 256 + tid] - sb;   // dst of sorted index j: gbase[d] + j
+    __syncthreads();
+#pragma unroll
+    for (unsigned g = 0; g < WSPAN / 32; ++g) {                                // place (keys come back from L1 / L2; no ballots left)
+        const unsigned i = lo + w * WSPAN + g * 32 + lane;
+        if (i < hi) {
+            const unsigned long long key = kin[i];
+            const unsigned d = (unsigned)(key >> shift) & 255u;
+            const unsigned v = (g & 1) ? rb[g >> 1] >> 16 : rb[g >> 1] & 0xffffu;
+            const unsigned p = sm.symbase[d] + sm.wcnt[w][d] + v;
+            sm.skey[p] = key; sm.sval[p] = vin[i];
         }
-        ubase += nt;
+    }
+    __syncthreads();
+    unsigned long long* kout = Kout + bk.e0;
+    unsigned* vout = Vout + bk.e0;
+    for (unsigned j = tid; j < tlen; j += NT) {
+        const unsigned long long key = sm.skey[j];
+        const unsigned dst = sm.gbase[(unsigned)(key >> shift) & 255u] + j;
+        kout[dst] = key;
+        vout[dst] = sm.sval[j];
     }
 }
 
@@ -219,31 +204,24 @@ __global__ void __launch_bounds__(128)
 heads_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nspans, const unsigned* __restrict__ state, const unsigned* __restrict__ cnt,
              const unsigned long long* __restrict__ K, unsigned bits, unsigned* __restrict__ span_last, unsigned* __restrict__ span_glast) {
     const unsigned lane = threadIdx.x & 31;
-    const unsigned me = blockIdx.x * 4 + (threadIdx.x >> 5), nworkers = gridDim.x * 4;      // one warp per span
-    unsigned ubase = 0;
-    for (unsigned b = 0; b < nblocks; ++b) {
-        if (state[b] != ACTIVE) continue;
-        const Blk bk = blks[b];
-        if (bk.skip) continue;
-        const unsigned units = (cnt[b] + SPAN - 1) / SPAN;
-        for (unsigned sl = first_unit(ubase, me, nworkers); sl < units; sl += nworkers) {
-        const unsigned span = bk.span0 + sl;
-            const unsigned nn = cnt[b];
-            const unsigned lo = (span - bk.span0) * SPAN, hi = min(nn, lo + SPAN);
-            const unsigned long long* k = K + bk.e0;
-            unsigned last = NONE, glast = NONE;
-            for (unsigned base = lo; base < hi; base += 32) {
-                const unsigned j = base + lane;
-                const unsigned long long kj = j < hi ? k[j] : 0ull, kp = (j < hi && j > 0) ? k[j - 1] : 0ull;
-                const unsigned m = __ballot_sync(RCZ_FULL, j < hi && (j == 0 || kj != kp));
-                const unsigned gm = __ballot_sync(RCZ_FULL, j < hi && (j == 0 || (kj >> bits) != (kp >> bits)));
-                if (m) last = base + 31u - (unsigned)__clz((int)m);
-                if (gm) glast = base + 31u - (unsigned)__clz((int)gm);
-            }
-            if (lane == 0) { span_last[span] = last; span_glast[span] = glast; }
-        }
-        ubase += units;
+    const unsigned span = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (span >= nspans) return;
+    const unsigned b = find_blk_span(blks, nblocks, span);
+    const Blk bk = blks[b];
+    if (bk.skip || state[b] != ACTIVE) return;
+    const unsigned nn = cnt[b];
+    const unsigned lo = (span - bk.span0) * SPAN, hi = min(nn, lo + SPAN);
+    const unsigned long long* k = K + bk.e0;
+    unsigned last = NONE, glast = NONE;
+    for (unsigned base = lo; base < hi; base += 32) {
+        const unsigned j = base + lane;
+        const unsigned long long kj = j < hi ? k[j] : 0ull, kp = (j < hi && j > 0) ? k[j - 1] : 0ull;
+        const unsigned m = __ballot_sync(RCZ_FULL, j < hi && (j == 0 || kj != kp));
+        const unsigned gm = __ballot_sync(RCZ_FULL, j < hi && (j == 0 || (kj >> bits) != (kp >> bits)));
+        if (m) last = base + 31u - (unsigned)__clz((int)m);
+        if (gm) glast = base + 31u - (unsigned)__clz((int)gm);
     }
+    if (lane == 0) { span_last[span] = last; span_glast[span] = glast; }
 }
 
 // per block: span_last / span_glast <- the last (sub)group head BEFORE the span (position 0 is always a head)
@@ -282,46 +260,39 @@ update_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nspans, c
               const unsigned long long* __restrict__ K, const unsigned* __restrict__ V, unsigned bits, const unsigned* __restrict__ span_carry,
               const unsigned* __restrict__ span_gcarry, unsigned* __restrict__ SA, unsigned* __restrict__ R, uint8_t* __restrict__ aflag) {
     const unsigned lane = threadIdx.x & 31;
-    const unsigned me = blockIdx.x * 4 + (threadIdx.x >> 5), nworkers = gridDim.x * 4;      // one warp per span
-    unsigned ubase = 0;
-    for (unsigned b = 0; b < nblocks; ++b) {
-        if (state[b] != ACTIVE) continue;
-        const Blk bk = blks[b];
-        if (bk.skip) continue;
-        const unsigned units = (cnt[b] + SPAN - 1) / SPAN;
-        for (unsigned sl = first_unit(ubase, me, nworkers); sl < units; sl += nworkers) {
-        const unsigned span = bk.span0 + sl;
-            const unsigned nn = cnt[b];
-            const unsigned lo = (span - bk.span0) * SPAN, hi = min(nn, lo + SPAN);
-            const unsigned long long* k = K + bk.e0;
-            const unsigned* v = V + bk.e0;
-            unsigned* sa = SA + bk.e0;
-            unsigned* r = R + bk.e0;
-            uint8_t* af = aflag + bk.e0;
-            unsigned carry = span_carry[span], gcarry = span_gcarry[span];
-            for (unsigned base = lo; base < hi; base += 32) {
-                const unsigned j = base + lane;
-                const bool in = j < hi;
-                const unsigned long long kj = in ? k[j] : 0ull, kp = (in && j > 0) ? k[j - 1] : 0ull;
-                const unsigned long long kn = (in && j + 1 < nn) ? k[j + 1] : ~0ull;
-                const bool head = in && (j == 0 || kj != kp);
-                const bool ghead = in && (j == 0 || (kj >> bits) != (kp >> bits));
-                const unsigned m = __ballot_sync(RCZ_FULL, head), gm = __ballot_sync(RCZ_FULL, ghead);
-                const unsigned upto = 0xFFFFFFFFu >> (31 - lane);
-                const unsigned hp = (m & upto) ? base + 31u - (unsigned)__clz((int)(m & upto)) : carry;
-                const unsigned gp = (gm & upto) ? base + 31u - (unsigned)__clz((int)(gm & upto)) : gcarry;
-                if (in) {
-                    const unsigned g = (unsigned)(kj >> bits);
-                    const unsigned pos = g + (j - gp), val = v[j];
-                    sa[pos] = val;
-                    r[val] = g + (hp - gp);
-                    af[pos] = (head && (j + 1 >= nn || kn != kj)) ? 0 : 1;            // alone in its subgroup: resolved
-                }
-                if (m) carry = base + 31u - (unsigned)__clz((int)m);
-                if (gm) gcarry = base + 31u - (unsigned)__clz((int)gm);
-            }
+    const unsigned span = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (span >= nspans) return;
+    const unsigned b = find_blk_span(blks, nblocks, span);
+    const Blk bk = blks[b];
+    if (bk.skip || state[b] != ACTIVE) return;
+    const unsigned nn = cnt[b];
+    const unsigned lo = (span - bk.span0) * SPAN, hi = min(nn, lo + SPAN);
+    const unsigned long long* k = K + bk.e0;
+    const unsigned* v = V + bk.e0;
+    unsigned* sa = SA + bk.e0;
+    unsigned* r = R + bk.e0;
+    uint8_t* af = aflag + bk.e0;
+    unsigned carry = span_carry[span], gcarry = span_gcarry[span];
+    for (unsigned base = lo; base < hi; base += 32) {
+        const unsigned j = base + lane;
+        const bool in = j < hi;
+        const unsigned long long kj = in ? k[j] : 0ull, kp = (in && j > 0) ? k[j - 1] : 0ull;
+        const unsigned long long kn = (in && j + 1 < nn) ? k[j + 1] : ~0ull;
+        const bool head = in && (j == 0 || kj != kp);
+        const bool ghead = in && (j == 0 || (kj >> bits) != (kp >> bits));
+        const unsigned m = __ballot_sync(RCZ_FULL, head), gm = __ballot_sync(RCZ_FULL, ghead);
+        const unsigned upto = 0xFFFFFFFFu >> (31 - lane);
+        const unsigned hp = (m & upto) ? base + 31u - (unsigned)__clz((int)(m & upto)) : carry;
+        const unsigned gp = (gm & upto) ? base + 31u - (unsigned)__clz((int)(gm & upto)) : gcarry;
+        if (in) {
+            const unsigned g = (unsigned)(kj >> bits);
+            const unsigned pos = g + (j - gp), val = v[j];
+            sa[pos] = val;
+            r[val] = g + (hp - gp);
+            af[pos] = (head && (j + 1 >= nn || kn != kj)) ? 0 : 1;            // alone in its subgroup: resolved
         }
-        ubase += units;
+        if (m) carry = base + 31u - (unsigned)__clz((int)m);
+        if (gm) gcarry = base + 31u - (unsigned)__clz((int)gm);
     }
 }
 
@@ -330,24 +301,17 @@ __global__ void __launch_bounds__(128)
 count_active_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nspans, const unsigned* __restrict__ state,
                     const uint8_t* __restrict__ aflag, unsigned* __restrict__ span_act) {
     const unsigned lane = threadIdx.x & 31;
-    const unsigned me = blockIdx.x * 4 + (threadIdx.x >> 5), nworkers = gridDim.x * 4;      // one warp per span
-    unsigned ubase = 0;
-    for (unsigned b = 0; b < nblocks; ++b) {
-        if (state[b] != ACTIVE) continue;
-        const Blk bk = blks[b];
-        if (bk.skip) continue;
-        const unsigned units = bk.nspans;
-        for (unsigned sl = first_unit(ubase, me, nworkers); sl < units; sl += nworkers) {
-        const unsigned span = bk.span0 + sl;
-            const unsigned lo = (span - bk.span0) * SPAN, hi = min(bk.n, lo + SPAN);
-            const uint8_t* af = aflag + bk.e0;
-            unsigned c = 0;
-            for (unsigned j = lo + lane; j < hi; j += 32) c += af[j] ? 1u : 0u;
-            c = warp_reduce_add(c);
-            if (lane == 0) span_act[span] = c;
-        }
-        ubase += units;
-    }
+    const unsigned span = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (span >= nspans) return;
+    const unsigned b = find_blk_span(blks, nblocks, span);
+    const Blk bk = blks[b];
+    if (bk.skip || state[b] != ACTIVE) return;
+    const unsigned lo = (span - bk.span0) * SPAN, hi = min(bk.n, lo + SPAN);
+    const uint8_t* af = aflag + bk.e0;
+    unsigned c = 0;
+    for (unsigned j = lo + lane; j < hi; j += 32) c += af[j] ? 1u : 0u;
+    c = warp_reduce_add(c);
+    if (lane == 0) span_act[span] = c;
 }
 
 // per block: span_act <- active suffixes before the span; cnt_next[b] = their total; none left -> the block is finished in this round
@@ -381,37 +345,30 @@ compact_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nspans, 
                const unsigned* __restrict__ span_abase, const unsigned* __restrict__ SA, const unsigned* __restrict__ R, unsigned h, unsigned bits,
                unsigned long long* __restrict__ K, unsigned* __restrict__ V) {
     const unsigned lane = threadIdx.x & 31;
-    const unsigned me = blockIdx.x * 4 + (threadIdx.x >> 5), nworkers = gridDim.x * 4;      // one warp per span
-    unsigned ubase = 0;
-    for (unsigned b = 0; b < nblocks; ++b) {
-        if (state[b] != ACTIVE) continue;
-        const Blk bk = blks[b];
-        if (bk.skip) continue;
-        const unsigned units = bk.nspans;
-        for (unsigned sl = first_unit(ubase, me, nworkers); sl < units; sl += nworkers) {
-        const unsigned span = bk.span0 + sl;
-            const unsigned lo = (span - bk.span0) * SPAN, hi = min(bk.n, lo + SPAN);
-            const uint8_t* af = aflag + bk.e0;
-            const unsigned* sa = SA + bk.e0;
-            const unsigned* r = R + bk.e0;
-            unsigned long long* k = K + bk.e0;
-            unsigned* v = V + bk.e0;
-            unsigned p0 = span_abase[span];
-            for (unsigned base = lo; base < hi; base += 32) {
-                const unsigned j = base + lane;
-                const bool act = j < hi && af[j] != 0;
-                const unsigned m = __ballot_sync(RCZ_FULL, act);
-                if (act) {
-                    const unsigned p = p0 + __popc(m & ((1u << lane) - 1u));
-                    const unsigned i = sa[j];
-                    const unsigned long long r2 = (i + h < bk.n && i + h >= i) ? (unsigned long long)r[i + h] + 1ull : 0ull;
-                    k[p] = ((unsigned long long)r[i] << bits) | r2;
-                    v[p] = i;
-                }
-                p0 += __popc(m);
-            }
+    const unsigned span = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (span >= nspans) return;
+    const unsigned b = find_blk_span(blks, nblocks, span);
+    const Blk bk = blks[b];
+    if (bk.skip || state[b] != ACTIVE) return;
+    const unsigned lo = (span - bk.span0) * SPAN, hi = min(bk.n, lo + SPAN);
+    const uint8_t* af = aflag + bk.e0;
+    const unsigned* sa = SA + bk.e0;
+    const unsigned* r = R + bk.e0;
+    unsigned long long* k = K + bk.e0;
+    unsigned* v = V + bk.e0;
+    unsigned p0 = span_abase[span];
+    for (unsigned base = lo; base < hi; base += 32) {
+        const unsigned j = base + lane;
+        const bool act = j < hi && af[j] != 0;
+        const unsigned m = __ballot_sync(RCZ_FULL, act);
+        if (act) {
+            const unsigned p = p0 + __popc(m & ((1u << lane) - 1u));
+            const unsigned i = sa[j];
+            const unsigned long long r2 = (i + h < bk.n && i + h >= i) ? (unsigned long long)r[i + h] + 1ull : 0ull;
+            k[p] = ((unsigned long long)r[i] << bits) | r2;
+            v[p] = i;
         }
-        ubase += units;
+        p0 += __popc(m);
     }
 }
 
@@ -420,24 +377,18 @@ __global__ void __launch_bounds__(NT)
 gather_kernel(const uint8_t* __restrict__ in_base, const Blk* __restrict__ blks, unsigned nblocks, const unsigned* __restrict__ state,
               unsigned round, const unsigned* __restrict__ V, uint8_t* __restrict__ out_base, uint32_t* __restrict__ origin,
               int32_t* __restrict__ status) {
-    const unsigned tid = threadIdx.x;
-    unsigned ubase = 0;
-    for (unsigned b = 0; b < nblocks; ++b) {
-        if (state[b] != round + 1) continue;
-        const Blk bk = blks[b];
-        if (bk.skip) continue;
-        const uint8_t* in = in_base + bk.in_off;
-        uint8_t* out = out_base + bk.out_off;
-        const unsigned* v = V + bk.e0;
-        for (unsigned tl = first_unit(ubase, blockIdx.x, gridDim.x); tl < bk.ntiles; tl += gridDim.x) {
-            const unsigned lo = tl * TB, hi = min(bk.n, lo + TB);
-            for (unsigned j = lo + tid; j < hi; j += NT) {
-                const unsigned p = v[j];
-                if (p == 0) { out[j] = in[bk.n - 1]; origin[b] = j; status[b] = RCZ_OK; }
-                else out[j] = in[p - 1];
-            }
-        }
-        ubase += bk.ntiles;
+    const unsigned tile = blockIdx.x, tid = threadIdx.x;
+    const unsigned b = find_blk_tile(blks, nblocks, tile);
+    const Blk bk = blks[b];
+    if (bk.skip || state[b] != round + 1) return;
+    const uint8_t* in = in_base + bk.in_off;
+    uint8_t* out = out_base + bk.out_off;
+    const unsigned* v = V + bk.e0;
+    const unsigned lo = (tile - bk.tile0) * TB, hi = min(bk.n, lo + TB);
+    for (unsigned j = lo + tid; j < hi; j += NT) {
+        const unsigned p = v[j];
+        if (p == 0) { out[j] = in[bk.n - 1]; origin[b] = j; status[b] = RCZ_OK; }
+        else out[j] = in[p - 1];
     }
 }
 
@@ -546,32 +497,31 @@ extern "C" int rcz_bwt_encode_blocks(rcz_ctx* c, const void* in_base, const uint
                     ds.in_ptr<int32_t>(i_hst) + g.b0, cntbuf[0]);
         if (g.ntiles == 0) continue;
         const unsigned sgrid = (g.nspans + 3) / 4;
-        const unsigned pg2 = (unsigned)c->sm_count * 2, pg8 = (unsigned)c->sm_count * 8, pg16 = (unsigned)c->sm_count * 16;   // persistent grids
         for (unsigned round = 0; round < nrounds; ++round) {
             const unsigned* cnt = cntbuf[round & 1];
             unsigned* cnt_next = cntbuf[(round & 1) ^ 1];
             unsigned npass, gbits;
             if (round == 0) {
-                RCZ_KLAUNCH(c, init_keys_kernel, std::min(g.ntiles, pg8), NT, 0, din, dblk, nb, K[0], V[0]);
+                RCZ_KLAUNCH(c, init_keys_kernel, g.ntiles, NT, 0, din, dblk, nb, K[0], V[0]);
                 npass = (9 * NSYM0 + 7) / 8; npass += npass & 1;              // even: the sorted data ends up in buffer 0
                 gbits = 63;                                                    // round 0: one group (the whole block), head 0
             } else {
-                RCZ_KLAUNCH(c, compact_kernel, std::min(sgrid, pg16), 128, 0, dblk, nb, g.nspans, state, aflag, span_act, SA, R, (unsigned)((unsigned)NSYM0 << (round - 1)), bits, K[0], V[0]);
+                RCZ_KLAUNCH(c, compact_kernel, sgrid, 128, 0, dblk, nb, g.nspans, state, aflag, span_act, SA, R, (unsigned)((unsigned)NSYM0 << (round - 1)), bits, K[0], V[0]);
                 npass = (2 * bits + 7) / 8; npass += npass & 1;
                 gbits = bits;
             }
             for (unsigned p = 0; p < npass; ++p) {
                 const unsigned a = p & 1;
-                RCZ_KLAUNCH(c, hist_kernel, std::min(g.ntiles, pg8), NT, 0, dblk, nb, state, cnt, K[a], p * 8, tile_hist);
+                RCZ_KLAUNCH(c, hist_kernel, g.ntiles, NT, 0, dblk, nb, state, cnt, K[a], p * 8, tile_hist);
                 RCZ_KLAUNCH(c, scan_kernel, nb, 256, 0, dblk, state, cnt, tile_hist, cbase);
-                RCZ_KLAUNCH(c, scatter_kernel, std::min(g.ntiles, pg2), NT, sizeof(ScatSmem), dblk, nb, state, cnt, K[a], V[a], K[a ^ 1], V[a ^ 1], p * 8, tile_hist, cbase);
+                RCZ_KLAUNCH(c, scatter_kernel, g.ntiles, NT, sizeof(ScatSmem), dblk, nb, state, cnt, K[a], V[a], K[a ^ 1], V[a ^ 1], p * 8, tile_hist, cbase);
             }
-            RCZ_KLAUNCH(c, heads_kernel, std::min(sgrid, pg16), 128, 0, dblk, nb, g.nspans, state, cnt, K[0], gbits, span_last, span_glast);
+            RCZ_KLAUNCH(c, heads_kernel, sgrid, 128, 0, dblk, nb, g.nspans, state, cnt, K[0], gbits, span_last, span_glast);
             RCZ_KLAUNCH(c, carry_kernel, nb, 256, 0, dblk, state, span_last, span_glast);
-            RCZ_KLAUNCH(c, update_kernel, std::min(sgrid, pg16), 128, 0, dblk, nb, g.nspans, state, cnt, K[0], V[0], gbits, span_last, span_glast, SA, R, aflag);
-            RCZ_KLAUNCH(c, count_active_kernel, std::min(sgrid, pg16), 128, 0, dblk, nb, g.nspans, state, aflag, span_act);
+            RCZ_KLAUNCH(c, update_kernel, sgrid, 128, 0, dblk, nb, g.nspans, state, cnt, K[0], V[0], gbits, span_last, span_glast, SA, R, aflag);
+            RCZ_KLAUNCH(c, count_active_kernel, sgrid, 128, 0, dblk, nb, g.nspans, state, aflag, span_act);
             RCZ_KLAUNCH(c, active_scan_kernel, nb, 256, 0, dblk, state, span_act, cnt_next, round, nactive + round);
-            RCZ_KLAUNCH(c, gather_kernel, std::min(g.ntiles, pg8), NT, 0, din, dblk, nb, state, round, SA, dout, d_org, d_st);
+            RCZ_KLAUNCH(c, gather_kernel, g.ntiles, NT, 0, din, dblk, nb, state, round, SA, dout, d_org, d_st);
             if (round + 1 == nrounds) break;
             if (mem_kind != RCZ_MEM_DEVICE_ASYNC) {                            // stop as soon as every block is finished
                 unsigned left = 0;
