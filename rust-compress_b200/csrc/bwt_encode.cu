@@ -74,7 +74,8 @@ init_keys_kernel(const uint8_t* __restrict__ in_base, const Blk* __restrict__ bl
 // ------------------------------------------------------------------------------------------ radix pass: histogram
 __global__ void __launch_bounds__(NT)
 hist_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* __restrict__ state, const unsigned* __restrict__ cnt,
-            const unsigned long long* __restrict__ K, unsigned shift, unsigned* __restrict__ tile_hist) {
+            const unsigned long long* __restrict__ K, unsigned shift, unsigned* __restrict__ tile_hist, const unsigned* __restrict__ guard) {
+    if (guard && *guard == 0) return;                                          // the previous round left no unresolved block: nothing to do
     __shared__ unsigned hsm[256];
     const unsigned tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const unsigned b = find_blk_tile(blks, nblocks, tile);
@@ -100,7 +101,8 @@ hist_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* __re
 // tile_hist[tile][d] <- number of d's in earlier tiles of the block; cbase[blk][d] <- number of digits < d
 __global__ void __launch_bounds__(256)
 scan_kernel(const Blk* __restrict__ blks, const unsigned* __restrict__ state, const unsigned* __restrict__ cnt, unsigned* __restrict__ tile_hist,
-            unsigned* __restrict__ cbase) {
+            unsigned* __restrict__ cbase, const unsigned* __restrict__ guard) {
+    if (guard && *guard == 0) return;                                          // the previous round left no unresolved block: nothing to do
     __shared__ unsigned scratch[40];
     const unsigned b = blockIdx.x, c = threadIdx.x;
     const Blk bk = blks[b];
@@ -133,7 +135,8 @@ struct ScatSmem {
 __global__ void __launch_bounds__(NT, 2)
 scatter_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* __restrict__ state, const unsigned* __restrict__ cnt,
                const unsigned long long* __restrict__ Kin, const unsigned* __restrict__ Vin, unsigned long long* __restrict__ Kout, unsigned* __restrict__ Vout, unsigned shift,
-               const unsigned* __restrict__ tile_hist, const unsigned* __restrict__ cbase) {
+               const unsigned* __restrict__ tile_hist, const unsigned* __restrict__ cbase, const unsigned* __restrict__ guard) {
+    if (guard && *guard == 0) return;                                          // the previous round left no unresolved block: nothing to do
     RCZ_DYN_SMEM(raw);
     ScatSmem& sm = *reinterpret_cast<ScatSmem*>(raw);
     const unsigned tile = blockIdx.x, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
@@ -202,7 +205,8 @@ scatter_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* _
 // high part = old group head) begin.
 __global__ void __launch_bounds__(128)
 heads_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nspans, const unsigned* __restrict__ state, const unsigned* __restrict__ cnt,
-             const unsigned long long* __restrict__ K, unsigned bits, unsigned* __restrict__ span_last, unsigned* __restrict__ span_glast) {
+             const unsigned long long* __restrict__ K, unsigned bits, unsigned* __restrict__ span_last, unsigned* __restrict__ span_glast, const unsigned* __restrict__ guard) {
+    if (guard && *guard == 0) return;                                          // the previous round left no unresolved block: nothing to do
     const unsigned lane = threadIdx.x & 31;
     const unsigned span = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (span >= nspans) return;
@@ -226,7 +230,8 @@ heads_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nspans, co
 
 // per block: span_last / span_glast <- the last (sub)group head BEFORE the span (position 0 is always a head)
 __global__ void __launch_bounds__(256)
-carry_kernel(const Blk* __restrict__ blks, const unsigned* __restrict__ state, unsigned* __restrict__ span_last, unsigned* __restrict__ span_glast) {
+carry_kernel(const Blk* __restrict__ blks, const unsigned* __restrict__ state, unsigned* __restrict__ span_last, unsigned* __restrict__ span_glast, const unsigned* __restrict__ guard) {
+    if (guard && *guard == 0) return;                                          // the previous round left no unresolved block: nothing to do
     __shared__ unsigned smax[2][256];
     const unsigned b = blockIdx.x, t = threadIdx.x;
     const Blk bk = blks[b];
@@ -258,7 +263,8 @@ carry_kernel(const Blk* __restrict__ blks, const unsigned* __restrict__ state, u
 __global__ void __launch_bounds__(128)
 update_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nspans, const unsigned* __restrict__ state, const unsigned* __restrict__ cnt,
               const unsigned long long* __restrict__ K, const unsigned* __restrict__ V, unsigned bits, const unsigned* __restrict__ span_carry,
-              const unsigned* __restrict__ span_gcarry, unsigned* __restrict__ SA, unsigned* __restrict__ R, uint8_t* __restrict__ aflag) {
+              const unsigned* __restrict__ span_gcarry, unsigned* __restrict__ SA, unsigned* __restrict__ R, uint8_t* __restrict__ aflag, const unsigned* __restrict__ guard) {
+    if (guard && *guard == 0) return;                                          // the previous round left no unresolved block: nothing to do
     const unsigned lane = threadIdx.x & 31;
     const unsigned span = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (span >= nspans) return;
@@ -299,7 +305,8 @@ update_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nspans, c
 // active suffixes per span of the suffix array (all n positions)
 __global__ void __launch_bounds__(128)
 count_active_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nspans, const unsigned* __restrict__ state,
-                    const uint8_t* __restrict__ aflag, unsigned* __restrict__ span_act) {
+                    const uint8_t* __restrict__ aflag, unsigned* __restrict__ span_act, const unsigned* __restrict__ guard) {
+    if (guard && *guard == 0) return;                                          // the previous round left no unresolved block: nothing to do
     const unsigned lane = threadIdx.x & 31;
     const unsigned span = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (span >= nspans) return;
@@ -317,7 +324,8 @@ count_active_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nsp
 // per block: span_act <- active suffixes before the span; cnt_next[b] = their total; none left -> the block is finished in this round
 __global__ void __launch_bounds__(256)
 active_scan_kernel(const Blk* __restrict__ blks, unsigned* __restrict__ state, unsigned* __restrict__ span_act, unsigned* __restrict__ cnt_next,
-                   unsigned round, unsigned* __restrict__ nactive) {
+                   unsigned round, unsigned* __restrict__ nactive, const unsigned* __restrict__ guard) {
+    if (guard && *guard == 0) return;                                          // the previous round left no unresolved block: nothing to do
     __shared__ unsigned ssum[256];
     const unsigned b = blockIdx.x, t = threadIdx.x;
     const Blk bk = blks[b];
@@ -343,7 +351,8 @@ active_scan_kernel(const Blk* __restrict__ blks, unsigned* __restrict__ state, u
 __global__ void __launch_bounds__(128)
 compact_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nspans, const unsigned* __restrict__ state, const uint8_t* __restrict__ aflag,
                const unsigned* __restrict__ span_abase, const unsigned* __restrict__ SA, const unsigned* __restrict__ R, unsigned h, unsigned bits,
-               unsigned long long* __restrict__ K, unsigned* __restrict__ V) {
+               unsigned long long* __restrict__ K, unsigned* __restrict__ V, const unsigned* __restrict__ guard) {
+    if (guard && *guard == 0) return;                                          // the previous round left no unresolved block: nothing to do
     const unsigned lane = threadIdx.x & 31;
     const unsigned span = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (span >= nspans) return;
@@ -376,7 +385,8 @@ compact_kernel(const Blk* __restrict__ blks, unsigned nblocks, unsigned nspans, 
 __global__ void __launch_bounds__(NT)
 gather_kernel(const uint8_t* __restrict__ in_base, const Blk* __restrict__ blks, unsigned nblocks, const unsigned* __restrict__ state,
               unsigned round, const unsigned* __restrict__ V, uint8_t* __restrict__ out_base, uint32_t* __restrict__ origin,
-              int32_t* __restrict__ status) {
+              int32_t* __restrict__ status, const unsigned* __restrict__ guard) {
+    if (guard && *guard == 0) return;                                          // the previous round left no unresolved block: nothing to do
     const unsigned tile = blockIdx.x, tid = threadIdx.x;
     const unsigned b = find_blk_tile(blks, nblocks, tile);
     const Blk bk = blks[b];
@@ -499,6 +509,7 @@ extern "C" int rcz_bwt_encode_blocks(rcz_ctx* c, const void* in_base, const uint
         const unsigned sgrid = (g.nspans + 3) / 4;
         for (unsigned round = 0; round < nrounds; ++round) {
             const unsigned* cnt = cntbuf[round & 1];
+            const unsigned* guard = round ? nactive + (round - 1) : (const unsigned*)nullptr;   // blocks still unresolved after the previous round
             unsigned* cnt_next = cntbuf[(round & 1) ^ 1];
             unsigned npass, gbits;
             if (round == 0) {
@@ -506,22 +517,22 @@ extern "C" int rcz_bwt_encode_blocks(rcz_ctx* c, const void* in_base, const uint
                 npass = (9 * NSYM0 + 7) / 8; npass += npass & 1;              // even: the sorted data ends up in buffer 0
                 gbits = 63;                                                    // round 0: one group (the whole block), head 0
             } else {
-                RCZ_KLAUNCH(c, compact_kernel, sgrid, 128, 0, dblk, nb, g.nspans, state, aflag, span_act, SA, R, (unsigned)((unsigned)NSYM0 << (round - 1)), bits, K[0], V[0]);
+                RCZ_KLAUNCH(c, compact_kernel, sgrid, 128, 0, dblk, nb, g.nspans, state, aflag, span_act, SA, R, (unsigned)((unsigned)NSYM0 << (round - 1)), bits, K[0], V[0], guard);
                 npass = (2 * bits + 7) / 8; npass += npass & 1;
                 gbits = bits;
             }
             for (unsigned p = 0; p < npass; ++p) {
                 const unsigned a = p & 1;
-                RCZ_KLAUNCH(c, hist_kernel, g.ntiles, NT, 0, dblk, nb, state, cnt, K[a], p * 8, tile_hist);
-                RCZ_KLAUNCH(c, scan_kernel, nb, 256, 0, dblk, state, cnt, tile_hist, cbase);
-                RCZ_KLAUNCH(c, scatter_kernel, g.ntiles, NT, sizeof(ScatSmem), dblk, nb, state, cnt, K[a], V[a], K[a ^ 1], V[a ^ 1], p * 8, tile_hist, cbase);
+                RCZ_KLAUNCH(c, hist_kernel, g.ntiles, NT, 0, dblk, nb, state, cnt, K[a], p * 8, tile_hist, guard);
+                RCZ_KLAUNCH(c, scan_kernel, nb, 256, 0, dblk, state, cnt, tile_hist, cbase, guard);
+                RCZ_KLAUNCH(c, scatter_kernel, g.ntiles, NT, sizeof(ScatSmem), dblk, nb, state, cnt, K[a], V[a], K[a ^ 1], V[a ^ 1], p * 8, tile_hist, cbase, guard);
             }
-            RCZ_KLAUNCH(c, heads_kernel, sgrid, 128, 0, dblk, nb, g.nspans, state, cnt, K[0], gbits, span_last, span_glast);
-            RCZ_KLAUNCH(c, carry_kernel, nb, 256, 0, dblk, state, span_last, span_glast);
-            RCZ_KLAUNCH(c, update_kernel, sgrid, 128, 0, dblk, nb, g.nspans, state, cnt, K[0], V[0], gbits, span_last, span_glast, SA, R, aflag);
-            RCZ_KLAUNCH(c, count_active_kernel, sgrid, 128, 0, dblk, nb, g.nspans, state, aflag, span_act);
-            RCZ_KLAUNCH(c, active_scan_kernel, nb, 256, 0, dblk, state, span_act, cnt_next, round, nactive + round);
-            RCZ_KLAUNCH(c, gather_kernel, g.ntiles, NT, 0, din, dblk, nb, state, round, SA, dout, d_org, d_st);
+            RCZ_KLAUNCH(c, heads_kernel, sgrid, 128, 0, dblk, nb, g.nspans, state, cnt, K[0], gbits, span_last, span_glast, guard);
+            RCZ_KLAUNCH(c, carry_kernel, nb, 256, 0, dblk, state, span_last, span_glast, guard);
+            RCZ_KLAUNCH(c, update_kernel, sgrid, 128, 0, dblk, nb, g.nspans, state, cnt, K[0], V[0], gbits, span_last, span_glast, SA, R, aflag, guard);
+            RCZ_KLAUNCH(c, count_active_kernel, sgrid, 128, 0, dblk, nb, g.nspans, state, aflag, span_act, guard);
+            RCZ_KLAUNCH(c, active_scan_kernel, nb, 256, 0, dblk, state, span_act, cnt_next, round, nactive + round, guard);
+            RCZ_KLAUNCH(c, gather_kernel, g.ntiles, NT, 0, din, dblk, nb, state, round, SA, dout, d_org, d_st, guard);
             if (round + 1 == nrounds) break;
             if (mem_kind != RCZ_MEM_DEVICE_ASYNC) {                            // stop as soon as every block is finished
                 unsigned left = 0;
