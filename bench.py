@@ -435,7 +435,6 @@ def leg_lz4(env, args):
     if world > 1:
         flat = torch.empty(w["U"] * world, dtype=torch.uint8, device="cuda")
         gms = env.time_dev(lambda: dist.all_gather_into_tensor(flat, d_out), 3, 2)
-        del flat
         both = env.gather_time(step_dev, d_out, max(3, min(args.steps, 10)))
         gather = {"collective": "ncclAllGather of the uniform 1 GiB shards (torch.distributed, NCCL over NVLink), issued after the decode", "bytes_per_rank": w["U"],
                   "gather_alone_ms": gms, "busbw_GBps": w["U"] * (world - 1) / (gms * 1e-3) / 1e9, "decode_plus_gather_ms": both,
@@ -456,18 +455,16 @@ def leg_lz4(env, args):
             fms = env.time_dev(step_fused, max(3, min(args.steps, 10)), 2)
             env.barrier()
             assert int((res["f"][1] != 0).sum().item()) == 0
-            # every rank's shard must have arrived: byte sums of the received regions against the senders' own sums
-            sums = torch.stack([buf[p * U: (p + 1) * U].to(torch.int64).sum() for p in range(world)])
-            own = d_out.to(torch.int64).sum().reshape(1)
-            allown = torch.empty(world, dtype=torch.int64, device="cuda")
-            dist.all_gather_into_tensor(allown, own)
-            assert torch.equal(sums, allown) and torch.equal(mine, d_out), "fused gather: a peer's shard did not arrive intact"
-            gather["fused"] = {"what": "rcz_lz4_decode_blocks_gather: lz4_mat_kernel stores each 16-byte output chunk to the local buffer and to the same offset of the "
-                                       "%d peers' gathered buffers (torch symmetric memory, P2P stores over NVLink / NVSwitch); no collective call" % (world - 1),
+            # every rank's shard must have arrived: the gathered buffer equals what ncclAllGather delivered above, byte for byte
+            assert torch.equal(buf, flat) and torch.equal(mine, d_out), "fused gather: a peer's shard did not arrive intact"
+            gather["fused"] = {"what": "rcz_lz4_decode_blocks_gather: lz4_mat_kernel writes its output to the local buffer and pushes every finished tile from its "
+                                       "shared-memory ring to the same offset of the %d peers' gathered buffers with TMA bulk stores (torch symmetric memory, "
+                                       "P2P over NVLink / NVSwitch); no collective call" % (world - 1),
                                "decode_plus_gather_ms": fms, "value_with_gather": world * U / (fms * 1e-3) / 1e9}
             gather["nccl_value_with_gather"] = gather["value_with_gather"]
             gather["value_with_gather"] = max(gather["value_with_gather"], gather["fused"]["value_with_gather"])
             del buf
+            del flat
         except Exception as e:  # symmetric memory unavailable on this box / torch build: the NCCL figure stands
             traceback.print_exc(file=sys.stderr)
             gather["fused"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}

@@ -47,8 +47,10 @@ constexpr int MT = 512;                    // materialise: threads per CTA (2 CT
 constexpr int TCAP = 8192;                 // materialise: at most this many output bytes per tile (one chunk per thread)
 constexpr int NCH = TCAP / 16;
 constexpr int RING = 73760;                // output ring in shared memory: 64 KiB of history + one tile + 16-byte chunk slack
+constexpr int PEER_INFLIGHT = 5;           // fused gather: tiles whose bulk stores may still be reading the ring
 constexpr int DCAP = 544;                  // sequence descriptors of a unit staged in shared memory (the rest is read from HBM)
 static_assert(RING % 16 == 0 && RING > 65535 + TCAP + 16, "a tile must not overwrite history that its matches can reach");
+static_assert((PEER_INFLIGHT + 2) * TCAP <= RING - TCAP, "a tile must not overwrite ring bytes that a bulk store may still read");
 
 constexpr unsigned long long CH_VALID = 1ull << 63;
 enum { ST_RUN = 0, ST_END = 1, ST_DEAD = 2 };
@@ -495,9 +497,11 @@ lz4_scan_kernel(const uint32_t* __restrict__ wbase, const uint32_t* __restrict__
 // materialise
 // ======================================================================================================
 struct __align__(16) UnitInfo { uint32_t nseq, tot, ob, pad; };
-// Fused gather (multi-GPU): every 16-byte chunk that goes to this GPU's output also goes to the same offset of the output buffers
-// of up to 7 peers (pointers mapped over NVLink / NVSwitch), so the final gather of the decoded shards rides on the decode's own
-// stores instead of following it as a separate collective.  delta[p] = peer base - local base.
+// Fused gather (multi-GPU): every finished tile of this GPU's output also goes to the same offset of the output buffers of up to
+// 7 peers (pointers mapped over NVLink / NVSwitch), so the final gather of the decoded shards rides on the decode instead of
+// following it as a separate collective.  The tile's whole 16-byte chunks leave the shared-memory output ring as TMA bulk
+// stores (one per peer, issued by lanes 0..n-1 of warp 0: large NVLink writes, no store slots of the decoding warps); only the
+// ragged first / last chunk of a unit is written with byte stores.  delta[p] = peer base - local base (a multiple of 16).
 struct PeerOut { long long delta[7]; int n; };
 struct MatSmem {
     __align__(16) uint8_t ring_[32 + RING + 32];     // 32-byte mirrors of the other end on both sides: source windows may overhang
@@ -693,8 +697,7 @@ __device__ __forceinline__ void mat_piece(const MatCtx& k, const uint16_t* sbase
                     uint8_t* g = k.outb + T0 - k.h + 16u * cc;                  // pointer arithmetic: T0 - h alone may wrap below zero
                     const unsigned lo = cc ? 0u : k.h;
                     if (lo == 0 && hi == 16u) {
-                        *reinterpret_cast<uint4*>(g) = v;
-                        if (PEERS) for (int pp = 0; pp < k.npeer; ++pp) *reinterpret_cast<uint4*>(g + k.peer->delta[pp]) = v;
+                        *reinterpret_cast<uint4*>(g) = v;                           // (peers: with the tile's bulk store)
                     } else {
                         store_chunk_bytes(g, v, lo, hi);                        // first / last chunk of a unit (rare, out of line)
                         if (PEERS) for (int pp = 0; pp < k.npeer; ++pp) store_chunk_bytes(g + k.peer->delta[pp], v, lo, hi);
@@ -846,11 +849,28 @@ lz4_mat_kernel(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__
                     for (unsigned p0 = 0; p0 < P; p0 += MT) {
                         if (p0 + (tid & ~31u) < P) mat_piece<true, true, PEERS>(k, sm.sbase, sm.pseq, j0, p0 + tid, p0 + tid < P);    // warp-uniform
                     }
+                    if (PEERS) fence_proxy_async_smem();                  // this thread's ring writes, for the bulk stores below
                     if (!__syncthreads_or(more && j0 + MT < k.nseq)) break;
+                }
+                if (PEERS && tid < (unsigned)k.npeer) {
+                    // the tile is complete in the ring: its whole chunks go to peer `tid` in one bulk store (two where the ring wraps)
+                    const unsigned c_lo = k.h ? 1u : 0u, c_hi = (k.tend & 15u) ? k.nch - 1u : k.nch;
+                    if (c_hi > c_lo) {
+                        const unsigned r0 = ring_off(k, k.c00 + 16u * c_lo), bytes = 16u * (c_hi - c_lo);
+                        uint8_t* g = k.outb + k.T0 - k.h + 16u * c_lo + peers.delta[tid];
+                        const unsigned first = bytes < (unsigned)RING - r0 ? bytes : (unsigned)RING - r0;
+                        tma_store_1d(g, k.ring + r0, first);
+                        if (bytes > first) tma_store_1d(g + first, k.ring, bytes - first);
+                    }
+                    bulk_commit();
+                    // at most PEER_INFLIGHT tiles still being read from the ring: PEER_INFLIGHT + 2 tiles back from the tile
+                    // that is zeroed next stays below the 64 KiB + one tile that the ring keeps
+                    bulk_wait_read<PEER_INFLIGHT>();
                 }
                 ja = sm.ja_next;                                          // (every thread reads it before the next tile's barrier lets thread 0 overwrite it)
             }
         }
+        if (PEERS && tid < (unsigned)k.npeer) bulk_wait_read0();          // the next block starts the ring over (barrier at the loop head)
     }
 }
 
@@ -1101,7 +1121,11 @@ static int lz4_decode_impl(rcz_ctx* c, const void* in_base, const uint64_t* in_o
     Lz4Job job;
     int st = lz4_prepare(c, ds, in_len, nblocks, cut, job); if (st) return st;
     job.dev.peers.n = npeers;
-    for (int p = 0; p < npeers; ++p) job.dev.peers.delta[p] = (long long)((const uint8_t*)peer_out_base[p] - (const uint8_t*)out_base);
+    for (int p = 0; p < npeers; ++p) {
+        if (!peer_out_base[p]) return RCZ_E_ARG;
+        job.dev.peers.delta[p] = (long long)((const uint8_t*)peer_out_base[p] - (const uint8_t*)out_base);
+        if (job.dev.peers.delta[p] & 15) return RCZ_E_ARG;                  // bulk stores: peer chunks as aligned as the local ones
+    }
     if (pipelined) return lz4_host_pipelined(c, ds, job, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, nblocks);
     const uint8_t* din = (const uint8_t*)in_base; uint8_t* dout = (uint8_t*)out_base;
     if (mem_kind == RCZ_MEM_HOST) {

@@ -37,6 +37,7 @@ __device__ inline void fence_proxy_async_smem() {}
 __device__ inline void tma_store_1d(void* gdst, const void* ssrc, unsigned bytes) { memcpy(gdst, ssrc, bytes); }
 __device__ inline void bulk_commit() {}
 __device__ inline void bulk_wait_read0() {}
+template <int N> __device__ inline void bulk_wait_read() {}
 __device__ inline void bulk_wait0() {}
 __device__ inline void prefetch_l2(const void*, unsigned) {}
 __device__ inline void rcz_backoff(unsigned) {}
@@ -86,6 +87,8 @@ __device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, unsig
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk stores of this thread have finished READING shared memory (the source may be overwritten)
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the N most recent bulk groups of this thread have finished reading shared memory
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 // all committed bulk stores of this thread are complete (writes performed)
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // polling back-off: frees the issue slots of a warp that waits on a flag in shared memory

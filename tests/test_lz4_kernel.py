@@ -298,3 +298,66 @@ def test_lz4_emu_gather_peers(emu_ctx, oracle, gen):
     for o, r in zip(out_off, raw):
         for buf in (mine, p1, p2):
             assert buf[int(o): int(o) + len(r)].tobytes() == r
+    # nothing outside the blocks' regions is touched (the peers' whole-chunk bulk stores stop at the ragged edges)
+    assert mine.tobytes() == p1.tobytes() == p2.tobytes()
+    used = np.zeros(total, dtype=bool)
+    for o, r in zip(out_off, raw):
+        used[int(o): int(o) + len(r)] = True
+    assert not mine[~used].any()
+
+
+def test_lz4_emu_gather_many_blocks(emu_ctx, gen):
+    """the gather call on more blocks than one CTA wave of the emulator, ragged sizes and unaligned offsets"""
+    raw = [gen.one("lzsyn" if i % 3 else "hextext", 100 + i, 3000 + 517 * i) for i in range(37)]
+    units = [gen.lz4_compress(r) for r in raw]
+    inb, in_off, in_len = pack(units, pad_front=3, gap=1, align=1)
+    out_off, out_cap, total = out_layout([len(r) for r in raw], gap=5)
+    mine, p1 = (np.zeros(total, dtype=np.uint8) for _ in range(2))
+    out_len, status = emu_ctx.lz4_decode_blocks_gather(inb, in_off, in_len, mine, out_off, out_cap, [p1.ctypes.data], async_="emu-device")
+    assert (status == 0).all() and [int(x) for x in out_len] == [len(r) for r in raw]
+    for o, r in zip(out_off, raw):
+        assert mine[int(o): int(o) + len(r)].tobytes() == r
+    assert mine.tobytes() == p1.tobytes()
+
+
+def _host_pipeline_case(ctx, oracle, gen, sizes, pinned):
+    """The HOST-buffer pipeline (>= 8 blocks, several chunks): bytes, lengths and statuses equal the oracle's, a block that does not
+    fit included, and nothing outside the blocks' capacity regions is written to the caller's buffer."""
+    raw = [gen.one("lzsyn" if i % 2 else "hextext", 300 + i, n) for i, n in enumerate(sizes)]
+    units = [gen.lz4_compress(r) for r in raw]
+    inb, in_off, in_len = pack(units, pad_front=7, gap=2, align=1)
+    caps = [len(r) for r in raw]
+    caps[5] -= 100                                               # block 5 does not fit: OUTPUT_FULL, nothing of it is materialised
+    out_off, out_cap, total = out_layout(caps, gap=9)
+    if pinned:
+        import torch
+        keep = (torch.from_numpy(inb).pin_memory(), torch.full((total + 3,), 0xAA, dtype=torch.uint8).pin_memory())
+        inb_, out = keep[0].numpy(), keep[1].numpy()[3:]
+    else:
+        inb_, out = inb, np.full(total + 3, 0xAA, dtype=np.uint8)[3:]           # odd alignment of the host base
+    out_len, status = ctx.lz4_decode_blocks(inb_, in_off, in_len, out, out_off, out_cap)
+    ref = np.zeros(total, dtype=np.uint8)
+    ref_len, ref_st = oracle.lz4_decode_blocks_mt(inb, in_off, in_len, ref, out_off, out_cap, 2)
+    assert [int(x) for x in status] == [int(x) for x in ref_st] and status[5] != 0
+    used = np.zeros(total, dtype=bool)
+    for i, (o, r) in enumerate(zip(out_off, raw)):
+        if status[i] == 0:
+            assert int(out_len[i]) == len(r) and out[int(o): int(o) + len(r)].tobytes() == r
+            used[int(o): int(o) + len(r)] = True
+        else:
+            assert int(out_len[i]) == 0
+            used[int(o): int(o) + int(out_cap[i])] = True       # a failed block's region is unspecified (rcz.h)
+    assert (out[~used] == 0xAA).all()
+
+
+def test_lz4_emu_host_pipeline(emu_ctx, oracle, gen, monkeypatch):
+    monkeypatch.setenv("RCZ_LZ4_CHUNK_BYTES", "60000")
+    _host_pipeline_case(emu_ctx, oracle, gen, [9000 + 1301 * i for i in range(13)], False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pinned", [True, False])
+def test_lz4_gpu_host_pipeline_ragged(gpu_ctx, oracle, gen, pinned, monkeypatch):
+    """blocks of 0.2 - 3 MiB in 4 MiB chunks, page-locked and pageable host buffers"""
+    monkeypatch.setenv("RCZ_LZ4_CHUNK_BYTES", str(4 << 20))
+    _host_pipeline_case(gpu_ctx, oracle, gen, [200000 + 120001 * i for i in range(24)], pinned)
