@@ -14,11 +14,11 @@
 //
 // Decode replaces dc.rs:162-233 `decode` fed by `decode_simple`'s closure (dc.rs:236-252).  It is inherently
 // serial in the run index (every distance re-sorts the symbol list): one dependency chain per block, and what counts is
-// the length of that chain per run end.  One warp decodes one block: lane r holds rank r of the (next position, symbol)
-// list in two 32-bit registers, so the slide of dc.rs:215-218 costs one ballot + one shuffle at any rank (a BWT column of
-// hexdump text re-enters at rank ~14 on average: a scalar loop with the top four ranks in registers was measured 3x
-// slower than the warp form); ranks >= 32 live in shared memory; the distances arrive 32 at a time, the next group in
-// flight while one is used.
+// the length of that chain per run end.  One warp decodes one block with the whole (next position, symbol) list in
+// registers, 1 / 2 / 4 / 8 consecutive ranks per lane by alphabet size (dc_decode_list<R>), so the slide of dc.rs:215-218
+// costs register moves + one shuffle at any rank and there is no slow path for deep re-entries; a scalar loop with the
+// top four ranks in registers was measured 3x slower, and a version that kept ranks >= 32 in shared memory measured the
+// same as this one (~450 cycles per run end on a B200: ~110 dependent SASS instructions, one warp per scheduler).
 #include "rcz_internal.h"
 #include <algorithm>
 
@@ -140,6 +140,90 @@ dc_emit_kernel(const uint8_t* __restrict__ in_base, const Blk* __restrict__ blks
 // ---------------------------------------------------------------------------------------------- decode
 struct DecSmem { unsigned nx[WPB][256]; uint8_t sy[WPB][256]; };              // the (next position, symbol) list of every warp's block, by rank
 
+// dc.rs:199-229.  Every distance re-sorts the (next position, symbol) list, so the loop is one dependency chain per block and what
+// counts is the latency from one list state to the next, not the number of instructions (with one chain per block the GPU is
+// almost empty).  The whole list lives in registers, R consecutive ranks per lane (lane l holds ranks R*l .. R*l + R-1, 32-bit
+// positions, n < 2^31), whatever the alphabet: the slide of dc.rs:215-218 is a register move inside the lane plus ONE shuffle for
+// the entry that crosses lanes, the rank is a ballot over "all R of mine are passed" + the leading count of the first lane that
+// is not, and there is no slow path for deep re-entries (a BWT column of hexdump text has 96 symbols and re-enters at rank >= 32
+// in 18 % of the steps, at rank 16 on average).  The loop body is straight-line: the error tests only set a flag (and clamp, so
+// that nothing goes out of bounds) and are looked at when the loop ends.  The distances arrive 32 at a time, the next group in
+// flight while one is used.
+template <int R>
+__device__ __forceinline__ int dc_decode_list(const unsigned* tnx, const uint8_t* tsy, unsigned A, unsigned N, const uint32_t* __restrict__ dist,
+                                              unsigned long long ndist, uint8_t* __restrict__ out, unsigned lane) {
+    unsigned nx[R], sy[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const unsigned q = R * lane + i;
+        nx[i] = q < A ? tnx[q] : 0xFFFFFFFFu;                                 // (sentinel: never passed, future + q < 2^32)
+        sy[i] = q < A ? (unsigned)tsy[q] : 0u;
+    }
+    unsigned i = 0, di = 0;
+    const unsigned ND = ndist > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)ndist;   // (a block has at most n < 2^31 run ends)
+    unsigned dreg = lane < ND ? __ldg(dist + lane) : 0u;                      // distances [32g, 32g + 32) of the current group, one per lane
+    unsigned dnxt = 32u + lane < ND ? __ldg(dist + 32 + lane) : 0u;           // the next group
+    bool bad = false;
+    while (i < N && di < ND && !bad) {
+        // ranks 0 and 1: the current symbol and the end of its run
+        const unsigned sym = __shfl_sync(RCZ_FULL, sy[0], 0);
+        unsigned stop = R > 1 ? __shfl_sync(RCZ_FULL, nx[R > 1 ? 1 : 0], 0) : __shfl_sync(RCZ_FULL, nx[0], 1);
+        const unsigned cross_nx = __shfl_down_sync(RCZ_FULL, nx[0], 1), cross_sy = __shfl_down_sync(RCZ_FULL, sy[0], 1);   // rank R*(l+1), for the slide
+        unsigned d = __shfl_sync(RCZ_FULL, dreg, (int)(di & 31u));
+        bad = stop > N;                                                       // output[i] index panic
+        stop = stop > N ? N : stop;
+        bad |= d > N - stop;                                                  // dc.rs:213 assert!(future <= n)
+        d = d > N - stop ? N - stop : d;
+        if (stop > i) {                                                       // the run [i, stop): almost always a few bytes
+            if (lane < stop - i) out[i + lane] = (uint8_t)sym;
+            if (stop - i > 32u) for (unsigned k = i + 32u + lane; k < stop; k += 32) out[k] = (uint8_t)sym;
+            i = stop;
+        }
+        ++di;
+        if ((di & 31u) == 0) { dreg = dnxt; dnxt = (unsigned long long)di + 32 + lane < ND ? __ldg(dist + di + 32 + lane) : 0u; }
+        const unsigned future = stop + d;
+        // rank = 1 + #{leading q in [1, A) : future + q > next(list[q])}  (dc.rs:215-218; the reference stops at the first rank that
+        // fails the test: LEADING hits, not all hits).  Rank 0 (the symbol itself) counts as passed.
+        unsigned lead = 0;                                                    // leading passed entries among this lane's R
+        bool run = true;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const unsigned q = R * lane + r;
+            run = run && (q == 0 || future + q > nx[r]);
+            lead += run ? 1u : 0u;
+        }
+        const unsigned full = __ballot_sync(RCZ_FULL, lead == (unsigned)R);
+        const unsigned L = (unsigned)__ffs((int)~full) - 1u;                  // first lane with an entry that is not passed (lane 31 never is full
+        const unsigned rank = full == RCZ_FULL ? 32u * R : R * L + __shfl_sync(RCZ_FULL, lead, (int)(L & 31u));   //  when A < 32 R; else rank = A = 32 R)
+        // list[q] = list[q + 1] for q < rank - 1; list[rank - 1] = (future + rank - 1, sym)
+        const unsigned at = rank - 1u;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const unsigned q = R * lane + r;
+            const unsigned un = r + 1 < R ? nx[r + 1 < R ? r + 1 : r] : cross_nx, us = r + 1 < R ? sy[r + 1 < R ? r + 1 : r] : cross_sy;
+            nx[r] = q < at ? un : q == at ? future + at : nx[r];
+            sy[r] = q < at ? us : q == at ? sym : sy[r];
+        }
+    }
+    // a flagged step is where the reference panics (its list update is then meaningless and is not looked at); running out of
+    // distances before the block is full is dc.rs:245-246
+    int err = 0;
+    if (bad) err = RCZ_E_MALFORMED;
+    else if (i < N) {                                                         // out of distances: the reference still looks at the next run first
+        const unsigned stop = R > 1 ? __shfl_sync(RCZ_FULL, nx[R > 1 ? 1 : 0], 0) : __shfl_sync(RCZ_FULL, nx[0], 1);
+        const unsigned sym = __shfl_sync(RCZ_FULL, sy[0], 0);
+        if (stop > N) err = RCZ_E_MALFORMED;
+        else { for (unsigned k = i + lane; k < stop; k += 32) out[k] = (uint8_t)sym; err = RCZ_E_UNEXPECTED_EOF; }
+    }
+    if (!err) {                                                               // dc.rs:230-231 assert_eq!
+        bool off = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) off |= R * lane + r < A && (nx[r] < N || nx[r] >= N + A);
+        if (__any_sync(RCZ_FULL, off) || i != N) err = RCZ_E_MALFORMED;
+    }
+    return err;
+}
+
 __global__ void __launch_bounds__(NT)
 dc_decode_kernel(const uint32_t* __restrict__ in_base, const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ in_len,
                  uint8_t* __restrict__ out_base, const uint64_t* __restrict__ out_off, const uint64_t* __restrict__ n_arr,
@@ -184,86 +268,13 @@ dc_decode_kernel(const uint32_t* __restrict__ in_base, const uint64_t* __restric
             __syncwarp();
             continue;
         }
-        // ---- dc.rs:199-229.  Every distance re-sorts the list, so the loop is one dependency chain per block and what counts is its
-        // length per run end.  Lane r holds rank r of the list (two 32-bit registers); the slide of dc.rs:215-218 is one ballot + one
-        // shuffle whatever the rank (BWT columns of text re-enter at rank ~14 on average, far beyond what a scalar loop keeps in
-        // registers); ranks >= 32 live in shared memory.  All positions are 32-bit (n < 2^31).
-        const unsigned N = (unsigned)n;
-        unsigned* tnx = sm.nx[w]; uint8_t* tsy = sm.sy[w];
-        unsigned nx = lane < A ? tnx[lane] : 0xFFFFFFFFu, sy = lane < A ? (unsigned)tsy[lane] : 0u;
+        // ---- dc.rs:199-229: see dc_decode_list below; R = list entries per lane, the smallest that holds the block's alphabet
+        int err;
         __syncwarp();
-        int err = 0;
-        unsigned i = 0;
-        const unsigned ND = ndist > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)ndist;   // (a block has at most n < 2^31 run ends)
-        unsigned di = 0;
-        unsigned dreg = lane < ND ? __ldg(dist + lane) : 0u;                  // distances [32g, 32g + 32) of the current group, one per lane
-        unsigned dnxt = 32u + lane < ND ? __ldg(dist + 32 + lane) : 0u;       // the next group, in flight while this one is used
-        // The loop body is kept straight-line: with one chain per block the GPU is almost empty, so what counts is the latency of the
-        // dependent instructions from one list state to the next (shuffle -> add -> ballot -> ffs -> select), not their number; the error
-        // tests only set a flag (and clamp, so that nothing goes out of bounds) and are looked at when the loop ends.
-        bool bad = false;
-        while (i < N && di < ND && !bad) {
-            unsigned stop = __shfl_sync(RCZ_FULL, nx, 1);
-            const unsigned sym = __shfl_sync(RCZ_FULL, sy, 0);
-            const unsigned up_nx = __shfl_down_sync(RCZ_FULL, nx, 1), up_sy = __shfl_down_sync(RCZ_FULL, sy, 1);
-            unsigned d = __shfl_sync(RCZ_FULL, dreg, (int)(di & 31u));
-            bad = stop > N;                                                   // output[i] index panic
-            stop = stop > N ? N : stop;
-            bad |= d > N - stop;                                              // dc.rs:213 assert!(future <= n)
-            d = d > N - stop ? N - stop : d;
-            if (stop > i) {                                                   // the run [i, stop): almost always a few bytes
-                if (lane < stop - i) out[i + lane] = (uint8_t)sym;
-                if (stop - i > 32u) for (unsigned k = i + 32u + lane; k < stop; k += 32) out[k] = (uint8_t)sym;
-                i = stop;
-            }
-            ++di;
-            if ((di & 31u) == 0) { dreg = dnxt; dnxt = (unsigned long long)di + 32 + lane < ND ? __ldg(dist + di + 32 + lane) : 0u; }
-            const unsigned future = stop + d;
-            // rank = 1 + #{leading r in [1, A) : future + r > next(list[r])}  (dc.rs:215-218; the reference stops at the first rank that
-            // fails the test: count LEADING hits, not all hits)
-            const unsigned bal = __ballot_sync(RCZ_FULL, lane >= 1 && lane < A && future + lane > nx) >> 1;
-            unsigned rank = (unsigned)__ffs((int)~bal);                       // 1 + leading hits; bal has at most 31 bits set
-            if (rank == 32 && A > 32) {
-                for (unsigned r0 = 32; r0 < A; r0 += 32) {
-                    const unsigned r = r0 + lane;
-                    const unsigned bb = __ballot_sync(RCZ_FULL, r < A && future + r > tnx[r]);
-                    if (bb == RCZ_FULL) { rank += 32; continue; }
-                    rank += (unsigned)__ffs((int)~bb) - 1u;
-                    break;
-                }
-                if (rank > 32) {
-                    const unsigned v32n = tnx[32], v32s = tsy[32];
-                    if (lane < 31) { nx = up_nx; sy = up_sy; } else { nx = v32n; sy = v32s; }
-                    __syncwarp();                                             // entry 32 is read before anyone rewrites it
-                    for (unsigned r0 = 32; r0 + 1 < rank; r0 += 32) {         // tail[r] = tail[r+1] for r in [32, rank-1)
-                        const unsigned r = r0 + lane;
-                        const unsigned tn = (r + 1 < rank) ? tnx[r + 1] : 0u, ts = (r + 1 < rank) ? (unsigned)tsy[r + 1] : 0u;
-                        __syncwarp();
-                        if (r + 1 < rank) { tnx[r] = tn; tsy[r] = (uint8_t)ts; }
-                        __syncwarp();
-                    }
-                    if (lane == 0) { tnx[rank - 1] = future + rank - 1u; tsy[rank - 1] = (uint8_t)sym; }
-                    __syncwarp();
-                    continue;
-                }
-            }
-            const bool below = lane + 1 < rank, at = lane + 1 == rank;        // rank <= 32: everything stays in registers, no branch
-            nx = below ? up_nx : at ? future + rank - 1u : nx;
-            sy = below ? up_sy : at ? sym : sy;
-        }
-        // a flagged step is where the reference panics (its list update is then meaningless and is not looked at); running out of
-        // distances before the block is full is dc.rs:245-246
-        if (bad) err = RCZ_E_MALFORMED;
-        else if (i < N) {                                                     // out of distances: the reference still looks at the next run first
-            const unsigned stop = __shfl_sync(RCZ_FULL, nx, 1), sym = __shfl_sync(RCZ_FULL, sy, 0);
-            if (stop > N) err = RCZ_E_MALFORMED;
-            else { for (unsigned k = i + lane; k < stop; k += 32) out[k] = (uint8_t)sym; err = RCZ_E_UNEXPECTED_EOF; }
-        }
-        if (!err) {                                                           // dc.rs:230-231 assert_eq!
-            bool bad = lane < A && (nx < N || nx >= N + A);
-            for (unsigned r = 32 + lane; r < A; r += 32) bad |= tnx[r] < N || tnx[r] >= N + A;
-            if (__any_sync(RCZ_FULL, bad) || i != N) err = RCZ_E_MALFORMED;
-        }
+        if (A <= 32) err = dc_decode_list<1>(sm.nx[w], sm.sy[w], A, (unsigned)n, dist, ndist, out, lane);
+        else if (A <= 64) err = dc_decode_list<2>(sm.nx[w], sm.sy[w], A, (unsigned)n, dist, ndist, out, lane);
+        else if (A <= 128) err = dc_decode_list<4>(sm.nx[w], sm.sy[w], A, (unsigned)n, dist, ndist, out, lane);
+        else err = dc_decode_list<8>(sm.nx[w], sm.sy[w], A, (unsigned)n, dist, ndist, out, lane);
         __syncwarp();
         if (lane == 0) status[b] = err;
     }

@@ -525,6 +525,40 @@ template <class R> class Decoder {                                           // 
     bool decoded_ = false, pending_err_ = false;
     io_error pending_{ErrorKind::Other, ""};
 };
+// Many independent raw-DEFLATE streams in ONE C-ABI call — the shape the GPU path is built for (BASELINE configs[3]: 131,072
+// streams of 64 KiB, one warp per stream).  A `Decoder` above drives one stream per call, i.e. one warp of the whole GPU; a
+// caller that holds many streams (archive members, pages, chunks of a chunked format) uses this instead of a loop of Decoders.
+// caps[i] = room for stream i's output (the sizes a container's directory declares); a stream that needs more ends with
+// RCZ_E_OUTPUT_FULL in status[i] and is the caller's to retry with a larger cap.  Statuses follow flate.rs's errors
+// (error_from_status turns one into the io_error a Decoder would throw).
+struct Many {
+    std::vector<uint8_t> bytes;                     // all outputs, stream i at [off[i], off[i] + len[i])
+    std::vector<uint64_t> off, len, used;           // used[i]: bytes of the stream that belong to the DEFLATE data
+    std::vector<int32_t> status, detail;
+    std::vector<uint32_t> adler;                    // zlib::decode_many only: Adler-32 of every stream's output
+    std::vector<uint8_t> get(size_t i) const { return std::vector<uint8_t>(bytes.begin() + (long)off[i], bytes.begin() + (long)(off[i] + len[i])); }
+};
+namespace detail_many {
+inline void layout(const std::vector<std::pair<const uint8_t*, size_t>>& streams, const std::vector<uint64_t>& caps, std::vector<uint8_t>& in,
+                   std::vector<uint64_t>& in_off, std::vector<uint64_t>& in_len, Many& m) {
+    if (caps.size() != streams.size()) throw io_error(ErrorKind::InvalidInput, "decode_many: one capacity per stream");
+    const size_t n = streams.size();
+    in_off.resize(n); in_len.resize(n); m.off.resize(n); m.len.assign(n, 0); m.used.assign(n, 0); m.status.assign(n, 0); m.detail.assign(n, 0);
+    uint64_t ti = 0, to = 0;
+    for (size_t i = 0; i < n; ++i) { in_off[i] = ti; in_len[i] = streams[i].second; ti += streams[i].second; m.off[i] = to; to += (caps[i] + 15) & ~(uint64_t)15; }
+    in.resize((size_t)ti + 64);
+    for (size_t i = 0; i < n; ++i) if (streams[i].second) memcpy(in.data() + in_off[i], streams[i].first, streams[i].second);
+    m.bytes.assign((size_t)to + 64, 0);
+}
+}  // namespace detail_many
+inline Many decode_many(Context& ctx, const std::vector<std::pair<const uint8_t*, size_t>>& streams, const std::vector<uint64_t>& caps) {
+    Many m; std::vector<uint8_t> in; std::vector<uint64_t> in_off, in_len;
+    detail_many::layout(streams, caps, in, in_off, in_len, m);
+    if (streams.empty()) return m;
+    ctx.check(rcz_flate_decode_streams(ctx.get(), in.data(), in_off.data(), in_len.data(), m.bytes.data(), m.off.data(), caps.data(), m.len.data(), m.used.data(),
+                                       m.status.data(), m.detail.data(), streams.size(), RCZ_MEM_HOST), "rcz_flate_decode_streams");
+    return m;
+}
 }  // namespace flate
 
 // ================================================================================================ zlib
@@ -582,6 +616,16 @@ template <class R> class Decoder {                                           // 
     bool decoded_ = false, pending_err_ = false;
     io_error pending_{ErrorKind::Other, ""};
 };
+// many independent zlib streams in one C-ABI call (see flate::decode_many); adler[i] = Adler-32 of stream i's output
+inline flate::Many decode_many(Context& ctx, const std::vector<std::pair<const uint8_t*, size_t>>& streams, const std::vector<uint64_t>& caps) {
+    flate::Many m; std::vector<uint8_t> in; std::vector<uint64_t> in_off, in_len;
+    flate::detail_many::layout(streams, caps, in, in_off, in_len, m);
+    m.adler.assign(streams.size(), 1);
+    if (streams.empty()) return m;
+    ctx.check(rcz_zlib_decode_streams(ctx.get(), in.data(), in_off.data(), in_len.data(), m.bytes.data(), m.off.data(), caps.data(), m.len.data(), m.used.data(),
+                                      m.status.data(), m.detail.data(), m.adler.data(), streams.size(), RCZ_MEM_HOST), "rcz_zlib_decode_streams");
+    return m;
+}
 }  // namespace zlib
 
 // ================================================================================================ ari

@@ -235,6 +235,30 @@ int main(int argc, char** argv) {
         CHECK(threw);
     });
 
+    run("flate::decode_many / zlib::decode_many (one call, many streams)", [&] {
+        std::vector<bytes> raw, z;
+        for (int i = 0; i <= 9; ++i) { z.push_back(load("ref_test.z." + std::to_string(i))); raw.push_back(fixup(z.back())); }
+        bytes bad = raw[5]; bad[0] |= 0x06;                                      // BTYPE 3
+        raw.push_back(bad);
+        raw.push_back(bytes());                                                  // empty stream: NotEnoughBits
+        std::vector<std::pair<const uint8_t*, size_t>> ss;
+        std::vector<uint64_t> caps;
+        for (auto& v : raw) { ss.emplace_back(v.data(), v.size()); caps.push_back(txt.size()); }
+        caps[3] = txt.size() - 1;                                                // too small
+        rcz::flate::Many m = rcz::flate::decode_many(ctx, ss, caps);
+        for (int i = 0; i <= 9; ++i) {
+            if (i == 3) { CHECK(m.status[3] == RCZ_E_OUTPUT_FULL); continue; }
+            CHECK(m.status[(size_t)i] == RCZ_OK && m.get((size_t)i) == txt && m.used[(size_t)i] == raw[(size_t)i].size());
+        }
+        CHECK(m.status[10] == RCZ_E_INVALID_INPUT && m.detail[10] == RCZ_FL_INVALID_BLOCK_CODE);
+        CHECK(m.status[11] != RCZ_OK);
+        ss.clear(); caps.clear();
+        for (auto& v : z) { ss.emplace_back(v.data(), v.size()); caps.push_back(txt.size() + 7); }
+        rcz::flate::Many mz = rcz::zlib::decode_many(ctx, ss, caps);
+        for (size_t i = 0; i < z.size(); ++i) CHECK(mz.status[i] == RCZ_OK && mz.get(i) == txt && mz.adler[i] == 0xfb4fcfa6u);
+        CHECK(rcz::flate::decode_many(ctx, {}, {}).status.empty());
+    });
+
     // ------------------------------------------------------------------------------------------ zlib (zlib.rs:140-205)
     run("zlib::decode fixtures", [&] {
         for (int i = 0; i <= 9; ++i) {

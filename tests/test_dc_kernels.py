@@ -108,6 +108,46 @@ def test_dc_emu(emu_ctx, oracle, gen):
     _check(emu_ctx, oracle, gen, 70000)
 
 
+def _alphabet_case(ctx, oracle, device=False, n=30000):
+    """decode keeps the whole symbol list in registers, 1 / 2 / 4 / 8 ranks per lane by alphabet size: sizes at and around every
+    class boundary, skewed symbol frequencies so that re-entries reach every depth"""
+    rs = np.random.RandomState(17)
+    blocks, streams = [], []
+    for a in (2, 3, 31, 32, 33, 63, 64, 65, 96, 127, 128, 129, 200, 255, 256):
+        syms = rs.permutation(256)[:a].astype(np.uint8)
+        w = 1.0 / (1.0 + np.arange(a)) ** 0.7
+        b = syms[rs.choice(a, size=n, p=w / w.sum())]
+        b[:a] = syms                                                # every symbol present
+        blocks.append(b.tobytes())
+        st, init, dist = oracle.dc_encode(blocks[-1])
+        assert st == 0
+        streams.append(np.concatenate([init, dist]).astype(np.uint32))
+    dec = _decode(ctx, streams, [len(b) for b in blocks], device=device)
+    for i, b in enumerate(blocks):
+        assert dec[i] == (0, b), "alphabet case %d differs" % i
+    # one corrupted distance each: status parity, bytes when it still decodes
+    bad = []
+    for s in streams:
+        t = s.copy()
+        t[256 + rs.randint(0, len(t) - 256)] += np.uint32(rs.randint(1, 9))
+        bad.append(t)
+    dec = _decode(ctx, bad, [len(b) for b in blocks], device=device)
+    for i, t in enumerate(bad):
+        ost, oout, used = oracle.dc_decode(len(blocks[i]), t[:256], t[256:])
+        assert dec[i][0] == ost, (i, dec[i][0], ost)
+        if ost == 0:
+            assert dec[i][1] == oout
+
+
+def test_dc_emu_alphabet_classes(emu_ctx, oracle):
+    _alphabet_case(emu_ctx, oracle)
+
+
+@pytest.mark.gpu
+def test_dc_gpu_alphabet_classes(gpu_ctx, oracle):
+    _alphabet_case(gpu_ctx, oracle, device=True, n=200000)
+
+
 def test_dc_emu_appendix_c(emu_ctx):
     got = _encode(emu_ctx, [b"teeesst_dc", b"abracadabra"])
     init = got[0][1][:256]
