@@ -39,7 +39,7 @@ COUNT = 256
 FL_UNIT = 65536
 FL_TOTAL = 131072          # configs[3]: 8 GiB of 64 KiB streams
 FL_UNIQUE = 16384          # generated and compressed once (1 GiB), tiled to FL_TOTAL
-ARI_CHUNK = 65536          # configs[4]: ByteEncoder streams of 64 KiB of serialised dc output
+ARI_CHUNK = int(os.environ.get("RCZ_BENCH_ARI_CHUNK", 16384))   # configs[4]: ByteEncoder streams of 16 KiB of serialised dc output (65,536 streams per GiB)
 
 
 def traffic_for(kernel):
@@ -678,7 +678,9 @@ def leg_pipeline(env, args):
     d_back = torch.zeros(UNIT * nb, dtype=torch.uint8, device="cuda")
     clen, org, st = ctx.bwt_dc_ari_encode_blocks(d_raw, off, n, d_cont, coff, caps, ari_chunk=ARI_CHUNK)
     assert (st == 0).all()
-    enc = lambda: ctx.bwt_dc_ari_encode_blocks(d_raw, off, n, d_cont, coff, caps, ari_chunk=ARI_CHUNK, async_=True)   # noqa: E731
+    # (encode in RCZ_MEM_DEVICE, not _ASYNC: the suffix sort may then read its round counter and stop after the last live round
+    #  instead of enqueueing all ~21 rounds; the call returns when the container is complete)
+    enc = lambda: ctx.bwt_dc_ari_encode_blocks(d_raw, off, n, d_cont, coff, caps, ari_chunk=ARI_CHUNK)   # noqa: E731
     dec = lambda: ctx.bwt_dc_ari_decode_blocks(d_cont, coff, clen, d_back, off, n, ari_chunk=ARI_CHUNK, async_=True)  # noqa: E731
     t0 = time.perf_counter(); enc(); torch.cuda.synchronize(); est_e = (time.perf_counter() - t0) * 1e3
     reps_e = env.reps_for(est_e, args.steps, 4000.0)

@@ -534,7 +534,7 @@ extern "C" int rcz_bwt_encode_blocks(rcz_ctx* c, const void* in_base, const uint
             RCZ_KLAUNCH(c, active_scan_kernel, nb, 256, 0, dblk, state, span_act, cnt_next, round, nactive + round, guard);
             RCZ_KLAUNCH(c, gather_kernel, g.ntiles, NT, 0, din, dblk, nb, state, round, SA, dout, d_org, d_st, guard);
             if (round + 1 == nrounds) break;
-            if (mem_kind != RCZ_MEM_DEVICE_ASYNC) {                            // stop as soon as every block is finished
+            if (mem_kind != RCZ_MEM_DEVICE_ASYNC || (c->nest && c->nest_may_sync)) {   // stop as soon as every block is finished
                 unsigned left = 0;
                 RCZ_CK(c, rt_d2h(&left, nactive + round, 4, c->stream));
                 RCZ_CK(c, rt_stream_sync(c->stream));

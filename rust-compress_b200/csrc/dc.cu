@@ -140,12 +140,18 @@ dc_emit_kernel(const uint8_t* __restrict__ in_base, const Blk* __restrict__ blks
 // ---------------------------------------------------------------------------------------------- decode
 struct DecSmem { unsigned nx[WPB][256]; uint8_t sy[WPB][256]; };              // the (next position, symbol) list of every warp's block, by rank
 
+// bytes [k0, stop) step 32 of a run longer than one warp store (rare in BWT columns of text; out of line so that the decode loop's
+// common path has no taken branch)
+__device__ __noinline__ void dc_fill_long(uint8_t* __restrict__ out, unsigned k0, unsigned stop, unsigned sym) {
+    for (unsigned k = k0; k < stop; k += 32) out[k] = (uint8_t)sym;
+}
+
 // dc.rs:199-229.  Every distance re-sorts the (next position, symbol) list, so the loop is one dependency chain per block and what
 // counts is the latency from one list state to the next, not the number of instructions (with one chain per block the GPU is
 // almost empty).  The whole list lives in registers, R consecutive ranks per lane (lane l holds ranks R*l .. R*l + R-1, 32-bit
 // positions, n < 2^31), whatever the alphabet: the slide of dc.rs:215-218 is a register move inside the lane plus ONE shuffle for
-// the entry that crosses lanes, the rank is a ballot over "all R of mine are passed" + the leading count of the first lane that
-// is not, and there is no slow path for deep re-entries (a BWT column of hexdump text has 96 symbols and re-enters at rank >= 32
+// the entry that crosses lanes, the rank comes from R independent ballots (one per register level), and there is no slow path
+// for deep re-entries (a BWT column of hexdump text has 96 symbols and re-enters at rank >= 32
 // in 18 % of the steps, at rank 16 on average).  The loop body is straight-line: the error tests only set a flag (and clamp, so
 // that nothing goes out of bounds) and are looked at when the loop ends.  The distances arrive 32 at a time, the next group in
 // flight while one is used.
@@ -160,9 +166,10 @@ __device__ __forceinline__ int dc_decode_list(const unsigned* tnx, const uint8_t
         sy[i] = q < A ? (unsigned)tsy[q] : 0u;
     }
     unsigned i = 0, di = 0;
-    const unsigned ND = ndist > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)ndist;   // (a block has at most n < 2^31 run ends)
+    const unsigned ND = ndist > 0x80000000ull ? 0x80000000u : (unsigned)ndist;   // (a block has at most n < 2^31 run ends)
     unsigned dreg = lane < ND ? __ldg(dist + lane) : 0u;                      // distances [32g, 32g + 32) of the current group, one per lane
     unsigned dnxt = 32u + lane < ND ? __ldg(dist + 32 + lane) : 0u;           // the next group
+    const uint32_t* dp = dist + 64 + lane;                                    // this lane's distance of the group after that
     bool bad = false;
     while (i < N && di < ND && !bad) {
         // ranks 0 and 1: the current symbol and the end of its run
@@ -174,27 +181,31 @@ __device__ __forceinline__ int dc_decode_list(const unsigned* tnx, const uint8_t
         stop = stop > N ? N : stop;
         bad |= d > N - stop;                                                  // dc.rs:213 assert!(future <= n)
         d = d > N - stop ? N - stop : d;
-        if (stop > i) {                                                       // the run [i, stop): almost always a few bytes
-            if (lane < stop - i) out[i + lane] = (uint8_t)sym;
-            if (stop - i > 32u) for (unsigned k = i + 32u + lane; k < stop; k += 32) out[k] = (uint8_t)sym;
-            i = stop;
-        }
+        // the run [i, stop): almost always a few bytes (one predicated store); the rest of a long one out of line
+        const unsigned run = stop > i ? stop - i : 0u;
+        if (lane < run) out[i + lane] = (uint8_t)sym;
+        if (run > 32u) dc_fill_long(out, i + 32u + lane, stop, sym);
+        i = stop > i ? stop : i;
         ++di;
-        if ((di & 31u) == 0) { dreg = dnxt; dnxt = (unsigned long long)di + 32 + lane < ND ? __ldg(dist + di + 32 + lane) : 0u; }
+        if ((di & 31u) == 0) {                                                // next group of 32 distances (short: stays predicated)
+            dreg = dnxt;
+            dnxt = di + 32u + lane < ND ? __ldg(dp) : 0u;
+            dp += 32;
+        }
         const unsigned future = stop + d;
         // rank = 1 + #{leading q in [1, A) : future + q > next(list[q])}  (dc.rs:215-218; the reference stops at the first rank that
-        // fails the test: LEADING hits, not all hits).  Rank 0 (the symbol itself) counts as passed.
-        unsigned lead = 0;                                                    // leading passed entries among this lane's R
-        bool run = true;
+        // fails the test: LEADING hits, not all hits).  Rank 0 (the symbol itself) counts as passed.  One ballot per register level,
+        // all independent; level r's first failing lane f gives the candidate rank R*f + r, the smallest candidate is the rank
+        // (no failing entry at all: A == 32 R, rank = A).
+        unsigned rank = 32u * R;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const unsigned q = R * lane + r;
-            run = run && (q == 0 || future + q > nx[r]);
-            lead += run ? 1u : 0u;
+            const unsigned pass = __ballot_sync(RCZ_FULL, q == 0 || future + q > nx[r]);
+            const unsigned f = (unsigned)__popc(pass & ~(pass + 1u));         // trailing ones: lanes before the first failing one
+            const unsigned cand = pass == RCZ_FULL ? 32u * R : R * f + r;
+            rank = cand < rank ? cand : rank;
         }
-        const unsigned full = __ballot_sync(RCZ_FULL, lead == (unsigned)R);
-        const unsigned L = (unsigned)__ffs((int)~full) - 1u;                  // first lane with an entry that is not passed (lane 31 never is full
-        const unsigned rank = full == RCZ_FULL ? 32u * R : R * L + __shfl_sync(RCZ_FULL, lead, (int)(L & 31u));   //  when A < 32 R; else rank = A = 32 R)
         // list[q] = list[q + 1] for q < rank - 1; list[rank - 1] = (future + rank - 1, sym)
         const unsigned at = rank - 1u;
 #pragma unroll

@@ -315,8 +315,10 @@ extern "C" int rcz_bwt_dc_ari_encode_blocks(rcz_ctx* c, const void* in_base, con
     st = ctx_timer_begin(c); if (st) return st;
     st = ctx_stage_mark(c, 0); if (st) return st;
     c->nest++;
+    c->nest_may_sync = mem_kind != RCZ_MEM_DEVICE_ASYNC;                      // then the suffix sort may look at its round counters and stop early
     // skipped blocks (n == 0 / too large) reach the stages with n = 0: they report their own error there, ours wins in enc_pack_kernel
     st = rcz_bwt_encode_blocks(c, din, in_off, g.n64.data(), wL, g.l_off.data(), d_org, d_bwt_st, nblocks, RCZ_MEM_DEVICE_ASYNC);
+    c->nest_may_sync = false;
     c->nest--;
     if (st) return st;
     st = ctx_stage_mark(c, 1); if (st) return st;

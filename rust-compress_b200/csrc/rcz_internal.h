@@ -20,6 +20,7 @@ struct rcz_ctx {
     rt_event_t stage_ev[RCZ_MAX_STAGES + 1] = {};   // stage boundaries of the most recent multi-kernel call
     int nstage = 0;
     int nest = 0;                     // > 0 while a composed call (pipeline.cu) drives the stage entry points: they leave the timers alone
+    bool nest_may_sync = false;       // the composed call itself is not RCZ_MEM_DEVICE_ASYNC: a stage may wait for the stream (forward BWT: stop after the last live round)
     char err[256] = {0};
     struct { void* p; size_t cap; } ws[WS_COUNT] = {};
     void* pinned = nullptr;
