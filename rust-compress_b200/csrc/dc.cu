@@ -235,6 +235,116 @@ __device__ __forceinline__ int dc_decode_list(const unsigned* tnx, const uint8_t
     return err;
 }
 
+// The same loop for lists whose positions are pairwise distinct (every well-formed stream; ties can only come from a damaged
+// init[] table and take dc_decode_list above).  A list without ties is strictly increasing in the rank and stays so, which makes
+// the test of dc.rs:215-218 monotone (passed ... passed, failed ... failed) and the whole update LOCAL to an entry and its
+// upper neighbour: with c[q] = "rank q is passed" = future + q > next(old[q])  (c[0] and c[1] always hold: the popped symbol's own
+// run ends where rank 1 begins),
+//        new[q] = old[q + 1]             if c[q + 1]
+//               = (future + q, sym)      else if c[q]
+//               = old[q]                 otherwise
+// — no ballot, no rank.  What is left of the step-to-step dependency is the front of the list, kept in uniform registers:
+//        sym' = symbol(old[1]),     new[1] = old[2] if c[2] else (future + 1, sym),
+// and old[2] is broadcast one step ahead, so a step's critical path is two integer instructions instead of the
+// shuffle -> compare -> ballot -> count -> shuffle -> select chain; what is left is the issue rate of a single warp, so the loop
+// is written for instruction count: an entry is ONE 32-bit key (position << 8 | symbol, hence n + 256 < 2^24 — every BWT block this
+// library accepts), "passed" is key < (future + q) << 8, and an entry costs one add, one compare and two selects per step.
+template <int R>
+__device__ __forceinline__ int dc_decode_sorted(const unsigned* tnx, const uint8_t* tsy, unsigned A, unsigned N, const uint32_t* __restrict__ dist,
+                                                unsigned long long ndist, uint8_t* __restrict__ out, unsigned lane) {
+    unsigned key[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const unsigned q = R * lane + r;
+        key[r] = q < A ? (tnx[q] << 8) | (unsigned)tsy[q] : 0xFFFFFFFFu;      // (sentinel: never passed)
+    }
+    // ranks 0, 1, 2 as every lane sees them
+    unsigned sym = __shfl_sync(RCZ_FULL, key[0], 0) & 0xFFu;
+    unsigned e1 = R > 1 ? __shfl_sync(RCZ_FULL, key[R > 1 ? 1 : 0], 0) : __shfl_sync(RCZ_FULL, key[0], 1);
+    unsigned e2 = R > 2 ? __shfl_sync(RCZ_FULL, key[R > 2 ? 2 : 0], 0) : __shfl_sync(RCZ_FULL, key[0], 2 / R);
+    unsigned i = 0;
+    const unsigned ND = ndist > 0x80000000ull ? 0x80000000u : (unsigned)ndist;   // (a block has at most n < 2^31 run ends)
+    unsigned dreg = lane < ND ? __ldg(dist + lane) : 0u;                      // distances [32g, 32g + 32) of the current group, one per lane
+    unsigned dnxt = 32u + lane < ND ? __ldg(dist + 32 + lane) : 0u;           // the next group
+    const uint32_t* dp = dist + 64 + lane;                                    // this lane's distance of the group after that
+    uint8_t* op = out + lane;                                                 // this lane's byte of the current run: out + i + lane
+#ifndef RCZ_EMU
+    asm volatile("" : "+l"(op));                                              // keep the pointer in registers (rebuilt from the parameter bank it costs a
+#endif                                                                        //  constant load per step, and a lone warp waits for every one of them)
+    bool bad = false;
+    // A single warp issues in order, so a result that is waited for stalls everything behind it (ncu: ~1 cycle per issued instruction,
+    // 5-13 per dependent or predicate-dependent one, ~30 per taken branch).  Every shuffle is issued as early as its operand exists and
+    // its result used as late as the step allows; the step's only taken branch is the loop's own: distances are consumed in groups of
+    // 32 with the refill between two inner loops, and a run longer than one warp store leaves the inner loop to be filled.
+    unsigned base = 0, k = 0, cnt = ND < 32u ? ND : 32u;                      // step index = base + k, k inside the current group of cnt distances
+    unsigned d = __shfl_sync(RCZ_FULL, dreg, 0);                              // the distance of the current step; the later ones are fetched one step ahead
+    unsigned run = 0, rsym = 0;
+    for (;;) {
+        bool go = k < cnt && i < N;
+        while (go) {
+            const unsigned stop = e1 >> 8;
+            const unsigned future = stop + d;                                 // (a flagged step ends the loop before the list is looked at again)
+            unsigned cross = __shfl_down_sync(RCZ_FULL, key[0], 1);           // rank R*(l+1); nothing lies above the last lane's entries
+            const unsigned fk = (future + R * lane) << 8;                     // rank q is passed  <=>  key[q] < (future + q) << 8
+            bool c[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) c[r] = key[r] < fk + ((unsigned)r << 8);
+#pragma unroll
+            for (int r = 0; r + 1 < R; ++r)                                   // entries whose upper neighbour is in this lane
+                key[r] = c[r + 1 < R ? r + 1 : r] ? key[r + 1 < R ? r + 1 : r] : c[r] ? (fk + ((unsigned)r << 8)) | sym : key[r];
+            unsigned e2_new = 0;
+            if (R > 1) e2_new = R > 2 ? __shfl_sync(RCZ_FULL, key[R > 2 ? 2 : 0], 0) : __shfl_sync(RCZ_FULL, key[0], 1);   // the new rank 2 is final
+            ++k;
+            const unsigned d_ahead = __shfl_sync(RCZ_FULL, dreg, (int)(k & 31u));
+            bad = d > N || future > N;                                        // output[i] index panic (stop > n); dc.rs:213 assert!(future <= n)
+            // the run [i, stop): almost always a few bytes, one predicated store.  stop only grows.
+            const unsigned stop_c = stop > N ? N : stop;
+            run = stop_c - i;
+            rsym = sym;
+            if (lane < run) *op = (uint8_t)sym;
+            op += run;
+            i = stop_c;
+            {                                                                 // the lane's last entry: its upper neighbour is the next lane's first
+                cross = lane == 31u ? 0xFFFFFFFFu : cross;
+                key[R - 1] = cross < fk + ((unsigned)R << 8) ? cross : c[R - 1] ? (fk + ((unsigned)(R - 1) << 8)) | sym : key[R - 1];
+            }
+            if (R == 1) e2_new = __shfl_sync(RCZ_FULL, key[0], 2);
+            // the front of the new list: rank 0 is the old rank 1; rank 1 is the old rank 2 if that one is passed, else the re-entered
+            // symbol; rank 2 came by broadcast
+            const unsigned e1_new = e2 < (future + 2u) << 8 ? e2 : ((future + 1u) << 8) | sym;
+            sym = e1 & 0xFFu;
+            e1 = e1_new; e2 = e2_new;
+            d = d_ahead;
+            go = k < cnt && i < N && !bad && run <= 32u;
+        }
+        if (run > 32u) { dc_fill_long(out, i - run + 32u + lane, i, rsym); run = 0; }   // the rest of a long run
+        if (bad || i >= N) break;
+        if (k == cnt) {                                                       // next group of 32 distances
+            base += k;
+            if (base >= ND) break;
+            dreg = dnxt;
+            dnxt = base + 32u + lane < ND ? __ldg(dp) : 0u;
+            dp += 32;
+            k = 0; cnt = ND - base < 32u ? ND - base : 32u;
+            d = __shfl_sync(RCZ_FULL, dreg, 0);
+        }
+    }
+    int err = 0;
+    if (bad) err = RCZ_E_MALFORMED;
+    else if (i < N) {                                                         // out of distances: the reference still looks at the next run first
+        const unsigned stop = e1 >> 8;
+        if (stop > N) err = RCZ_E_MALFORMED;
+        else { for (unsigned k = i + lane; k < stop; k += 32) out[k] = (uint8_t)sym; err = RCZ_E_UNEXPECTED_EOF; }
+    }
+    if (!err) {                                                               // dc.rs:230-231 assert_eq!
+        bool off = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) off |= R * lane + r < A && ((key[r] >> 8) < N || (key[r] >> 8) >= N + A);
+        if (__any_sync(RCZ_FULL, off) || i != N) err = RCZ_E_MALFORMED;
+    }
+    return err;
+}
+
 __global__ void __launch_bounds__(NT)
 dc_decode_kernel(const uint32_t* __restrict__ in_base, const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ in_len,
                  uint8_t* __restrict__ out_base, const uint64_t* __restrict__ out_off, const uint64_t* __restrict__ n_arr,
@@ -282,7 +392,14 @@ dc_decode_kernel(const uint32_t* __restrict__ in_base, const uint64_t* __restric
         // ---- dc.rs:199-229: see dc_decode_list below; R = list entries per lane, the smallest that holds the block's alphabet
         int err;
         __syncwarp();
-        if (A <= 32) err = dc_decode_list<1>(sm.nx[w], sm.sy[w], A, (unsigned)n, dist, ndist, out, lane);
+        bool tie = false;                                                     // two symbols with one first position: only in a damaged init[] table
+        for (unsigned q = lane; q + 1 < A; q += 32) tie |= sm.nx[w][q] == sm.nx[w][q + 1];
+        if (!__any_sync(RCZ_FULL, tie) && n + 256 < (1ull << 24)) {
+            if (A <= 32) err = dc_decode_sorted<1>(sm.nx[w], sm.sy[w], A, (unsigned)n, dist, ndist, out, lane);
+            else if (A <= 64) err = dc_decode_sorted<2>(sm.nx[w], sm.sy[w], A, (unsigned)n, dist, ndist, out, lane);
+            else if (A <= 128) err = dc_decode_sorted<4>(sm.nx[w], sm.sy[w], A, (unsigned)n, dist, ndist, out, lane);
+            else err = dc_decode_sorted<8>(sm.nx[w], sm.sy[w], A, (unsigned)n, dist, ndist, out, lane);
+        } else if (A <= 32) err = dc_decode_list<1>(sm.nx[w], sm.sy[w], A, (unsigned)n, dist, ndist, out, lane);
         else if (A <= 64) err = dc_decode_list<2>(sm.nx[w], sm.sy[w], A, (unsigned)n, dist, ndist, out, lane);
         else if (A <= 128) err = dc_decode_list<4>(sm.nx[w], sm.sy[w], A, (unsigned)n, dist, ndist, out, lane);
         else err = dc_decode_list<8>(sm.nx[w], sm.sy[w], A, (unsigned)n, dist, ndist, out, lane);

@@ -131,9 +131,18 @@ def _alphabet_case(ctx, oracle, device=False, n=30000):
         t = s.copy()
         t[256 + rs.randint(0, len(t) - 256)] += np.uint32(rs.randint(1, 9))
         bad.append(t)
-    dec = _decode(ctx, bad, [len(b) for b in blocks], device=device)
+    # two symbols with one first position (a damaged init[] table): the list has a tie, the decoder must take its exact path
+    # (leading-hits rank, dc.rs:215-218) and agree with the oracle in status and, where it still decodes, in bytes
+    for s_ in streams:
+        present = np.nonzero(s_[:256] < n)[0]
+        for k in (1, len(present) // 2, len(present) - 1):
+            t = s_.copy()
+            t[present[k]] = t[present[k - 1]]
+            bad.append(t)
+    ns = [len(blocks[0])] * len(bad)
+    dec = _decode(ctx, bad, ns, device=device)
     for i, t in enumerate(bad):
-        ost, oout, used = oracle.dc_decode(len(blocks[i]), t[:256], t[256:])
+        ost, oout, used = oracle.dc_decode(ns[i], t[:256], t[256:])
         assert dec[i][0] == ost, (i, dec[i][0], ost)
         if ost == 0:
             assert dec[i][1] == oout
