@@ -264,9 +264,12 @@ __device__ __forceinline__ int dc_decode_sorted(const unsigned* tnx, const uint8
     unsigned e2 = R > 2 ? __shfl_sync(RCZ_FULL, key[R > 2 ? 2 : 0], 0) : __shfl_sync(RCZ_FULL, key[0], 2 / R);
     unsigned i = 0;
     const unsigned ND = ndist > 0x80000000ull ? 0x80000000u : (unsigned)ndist;   // (a block has at most n < 2^31 run ends)
-    unsigned dreg = lane < ND ? __ldg(dist + lane) : 0u;                      // distances [32g, 32g + 32) of the current group, one per lane
-    unsigned dnxt = 32u + lane < ND ? __ldg(dist + 32 + lane) : 0u;           // the next group
-    const uint32_t* dp = dist + 64 + lane;                                    // this lane's distance of the group after that
+    const unsigned last = ND ? ND - 1u : 0u;
+    // distances in groups of 32, one per lane, in two registers used in turn: while one group is consumed the group after the next is
+    // already on its way into the other register, which nothing reads for a whole group (with one "next" register rotated into a
+    // "current" one, ptxas copies the loaded value right behind the load and the lone warp waits out the HBM latency per group)
+    unsigned dA = ND ? __ldg(dist + (lane < ND ? lane : last)) : 0u;
+    unsigned dB = ND ? __ldg(dist + (32u + lane < ND ? 32u + lane : last)) : 0u;
     uint8_t* op = out + lane;                                                 // this lane's byte of the current run: out + i + lane
 #ifndef RCZ_EMU
     asm volatile("" : "+l"(op));                                              // keep the pointer in registers (rebuilt from the parameter bank it costs a
@@ -274,60 +277,66 @@ __device__ __forceinline__ int dc_decode_sorted(const unsigned* tnx, const uint8
     bool bad = false;
     // A single warp issues in order, so a result that is waited for stalls everything behind it (ncu: ~1 cycle per issued instruction,
     // 5-13 per dependent or predicate-dependent one, ~30 per taken branch).  Every shuffle is issued as early as its operand exists and
-    // its result used as late as the step allows; the step's only taken branch is the loop's own: distances are consumed in groups of
-    // 32 with the refill between two inner loops, and a run longer than one warp store leaves the inner loop to be filled.
-    unsigned base = 0, k = 0, cnt = ND < 32u ? ND : 32u;                      // step index = base + k, k inside the current group of cnt distances
-    unsigned d = __shfl_sync(RCZ_FULL, dreg, 0);                              // the distance of the current step; the later ones are fetched one step ahead
+    // its result used as late as the step allows; the step's only taken branch is the loop's own: the refill sits between two groups,
+    // and a run longer than one warp store leaves the inner loop to be filled.
+    unsigned base = 0;                                                        // step index = base + k, k inside the current group
     unsigned run = 0, rsym = 0;
-    for (;;) {
-        bool go = k < cnt && i < N;
-        while (go) {
-            const unsigned stop = e1 >> 8;
-            const unsigned future = stop + d;                                 // (a flagged step ends the loop before the list is looked at again)
-            unsigned cross = __shfl_down_sync(RCZ_FULL, key[0], 1);           // rank R*(l+1); nothing lies above the last lane's entries
-            const unsigned fk = (future + R * lane) << 8;                     // rank q is passed  <=>  key[q] < (future + q) << 8
-            bool c[R];
+    auto run_group = [&](const unsigned dcur) {
+        const unsigned cnt = ND - base < 32u ? ND - base : 32u;
+        unsigned k = 0;
+        unsigned d = __shfl_sync(RCZ_FULL, dcur, 0);                          // the distance of the current step; the later ones are fetched one step ahead
+        for (;;) {
+            bool go = k < cnt && i < N && !bad;
+            while (go) {
+                const unsigned stop = e1 >> 8;
+                const unsigned future = stop + d;                             // (a flagged step ends the loop before the list is looked at again)
+                unsigned cross = __shfl_down_sync(RCZ_FULL, key[0], 1);       // rank R*(l+1); nothing lies above the last lane's entries
+                // the run [i, stop): almost always a few bytes, one predicated store — first thing in the step, its pointer moves on
+                // last (the add has to wait until the store has read its address).  stop only grows.
+                const unsigned stop_c = stop > N ? N : stop;
+                run = stop_c - i;
+                rsym = sym;
+                if (lane < run) *op = (uint8_t)sym;
+                const unsigned fk = (future + R * lane) << 8;                 // rank q is passed  <=>  key[q] < (future + q) << 8
+                bool c[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) c[r] = key[r] < fk + ((unsigned)r << 8);
+                for (int r = 0; r < R; ++r) c[r] = key[r] < fk + ((unsigned)r << 8);
 #pragma unroll
-            for (int r = 0; r + 1 < R; ++r)                                   // entries whose upper neighbour is in this lane
-                key[r] = c[r + 1 < R ? r + 1 : r] ? key[r + 1 < R ? r + 1 : r] : c[r] ? (fk + ((unsigned)r << 8)) | sym : key[r];
-            unsigned e2_new = 0;
-            if (R > 1) e2_new = R > 2 ? __shfl_sync(RCZ_FULL, key[R > 2 ? 2 : 0], 0) : __shfl_sync(RCZ_FULL, key[0], 1);   // the new rank 2 is final
-            ++k;
-            const unsigned d_ahead = __shfl_sync(RCZ_FULL, dreg, (int)(k & 31u));
-            bad = d > N || future > N;                                        // output[i] index panic (stop > n); dc.rs:213 assert!(future <= n)
-            // the run [i, stop): almost always a few bytes, one predicated store.  stop only grows.
-            const unsigned stop_c = stop > N ? N : stop;
-            run = stop_c - i;
-            rsym = sym;
-            if (lane < run) *op = (uint8_t)sym;
-            op += run;
-            i = stop_c;
-            {                                                                 // the lane's last entry: its upper neighbour is the next lane's first
-                cross = lane == 31u ? 0xFFFFFFFFu : cross;
-                key[R - 1] = cross < fk + ((unsigned)R << 8) ? cross : c[R - 1] ? (fk + ((unsigned)(R - 1) << 8)) | sym : key[R - 1];
+                for (int r = 0; r + 1 < R; ++r)                               // entries whose upper neighbour is in this lane
+                    key[r] = c[r + 1 < R ? r + 1 : r] ? key[r + 1 < R ? r + 1 : r] : c[r] ? (fk + ((unsigned)r << 8)) | sym : key[r];
+                unsigned e2_new = 0;
+                if (R > 1) e2_new = R > 2 ? __shfl_sync(RCZ_FULL, key[R > 2 ? 2 : 0], 0) : __shfl_sync(RCZ_FULL, key[0], 1);   // the new rank 2 is final
+                ++k;
+                const unsigned d_ahead = __shfl_sync(RCZ_FULL, dcur, (int)(k & 31u));
+                bad = d > N || future > N;                                    // output[i] index panic (stop > n); dc.rs:213 assert!(future <= n)
+                {                                                             // the lane's last entry: its upper neighbour is the next lane's first
+                    cross = lane == 31u ? 0xFFFFFFFFu : cross;
+                    key[R - 1] = cross < fk + ((unsigned)R << 8) ? cross : c[R - 1] ? (fk + ((unsigned)(R - 1) << 8)) | sym : key[R - 1];
+                }
+                if (R == 1) e2_new = __shfl_sync(RCZ_FULL, key[0], 2);
+                // the front of the new list: rank 0 is the old rank 1; rank 1 is the old rank 2 if that one is passed, else the
+                // re-entered symbol; rank 2 came by broadcast
+                const unsigned e1_new = e2 < (future + 2u) << 8 ? e2 : ((future + 1u) << 8) | sym;
+                sym = e1 & 0xFFu;
+                e1 = e1_new; e2 = e2_new;
+                d = d_ahead;
+                op += run;
+                i = stop_c;
+                go = k < cnt && i < N && !bad && run <= 32u;
             }
-            if (R == 1) e2_new = __shfl_sync(RCZ_FULL, key[0], 2);
-            // the front of the new list: rank 0 is the old rank 1; rank 1 is the old rank 2 if that one is passed, else the re-entered
-            // symbol; rank 2 came by broadcast
-            const unsigned e1_new = e2 < (future + 2u) << 8 ? e2 : ((future + 1u) << 8) | sym;
-            sym = e1 & 0xFFu;
-            e1 = e1_new; e2 = e2_new;
-            d = d_ahead;
-            go = k < cnt && i < N && !bad && run <= 32u;
+            if (run <= 32u) break;
+            dc_fill_long(out, i - run + 32u + lane, i, rsym);                 // the rest of a long run, then on with the group
+            run = 0;
         }
-        if (run > 32u) { dc_fill_long(out, i - run + 32u + lane, i, rsym); run = 0; }   // the rest of a long run
-        if (bad || i >= N) break;
-        if (k == cnt) {                                                       // next group of 32 distances
-            base += k;
-            if (base >= ND) break;
-            dreg = dnxt;
-            dnxt = base + 32u + lane < ND ? __ldg(dp) : 0u;
-            dp += 32;
-            k = 0; cnt = ND - base < 32u ? ND - base : 32u;
-            d = __shfl_sync(RCZ_FULL, dreg, 0);
-        }
+        base += k;
+    };
+    for (;;) {
+        run_group(dA);
+        if (bad || i >= N || base >= ND) break;
+        { const unsigned gi = base + 32u + lane; dA = __ldg(dist + (gi < ND ? gi : last)); }
+        run_group(dB);
+        if (bad || i >= N || base >= ND) break;
+        { const unsigned gi = base + 32u + lane; dB = __ldg(dist + (gi < ND ? gi : last)); }
     }
     int err = 0;
     if (bad) err = RCZ_E_MALFORMED;

@@ -361,3 +361,26 @@ def test_lz4_gpu_host_pipeline_ragged(gpu_ctx, oracle, gen, pinned, monkeypatch)
     """blocks of 0.2 - 3 MiB in 4 MiB chunks, page-locked and pageable host buffers"""
     monkeypatch.setenv("RCZ_LZ4_CHUNK_BYTES", str(4 << 20))
     _host_pipeline_case(gpu_ctx, oracle, gen, [200000 + 120001 * i for i in range(24)], pinned)
+
+
+@pytest.mark.gpu
+def test_lz4_gpu_gather_bulk_stores_one_gpu(gpu_ctx, gen):
+    """The fused gather on ONE GPU: the 'peers' are two more buffers of the same device, so the TMA bulk stores from the output ring
+    (and the byte stores of the ragged chunks) run exactly as they do over NVLink.  Ragged block sizes, unaligned offsets: all three
+    buffers must hold every block's bytes and nothing else."""
+    import torch
+    raw = [gen.one("lzsyn" if i % 3 else "hextext", 700 + i, 150000 + 91003 * i) for i in range(40)]
+    units = [gen.lz4_compress(r) for r in raw]
+    inb, in_off, in_len = pack(units, pad_front=5, gap=3, align=1)
+    out_off, out_cap, total = out_layout([len(r) for r in raw], gap=7)
+    d_in = torch.from_numpy(inb).cuda()
+    bufs = [torch.full((total,), 0xAA, dtype=torch.uint8, device="cuda") for _ in range(3)]
+    out_len, status = gpu_ctx.lz4_decode_blocks_gather(d_in, in_off, in_len, bufs[0], out_off, out_cap, [bufs[1].data_ptr(), bufs[2].data_ptr()])
+    torch.cuda.synchronize()
+    status = status.cpu().numpy() if hasattr(status, "cpu") else status
+    assert (status == 0).all()
+    want = np.full(total, 0xAA, dtype=np.uint8)
+    for o, r in zip(out_off, raw):
+        want[int(o): int(o) + len(r)] = np.frombuffer(r, dtype=np.uint8)
+    for b in bufs:
+        assert bytes(b.cpu().numpy()) == want.tobytes()
