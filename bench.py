@@ -234,7 +234,7 @@ def cpu_legs(cores, which, single):
         dt, reps = _timed_cpu(enc, 4.0, 2)
         clen, org, st = res["o"]
         assert (st == 0).all()
-        out["bwt_dc_ari_encode"] = dict(kind, value=nb_p * UNIT / dt / 1e9, sample="%d text blocks of 4 MiB, %d repetitions; oracle bwt + dc + ByteEncoder (64 KiB streams)" % (nb_p, reps))
+        out["bwt_dc_ari_encode"] = dict(kind, value=nb_p * UNIT / dt / 1e9, sample="%d text blocks of 4 MiB, %d repetitions; oracle bwt + dc + ByteEncoder (%d KiB streams)" % (nb_p, reps, ARI_CHUNK >> 10))
         back = np.zeros(UNIT * nb_p + 64, dtype=np.uint8)
         dt, reps = _timed_cpu(lambda: oracle.bda_decode_blocks_mt(cont, coff, clen, ARI_CHUNK, back, off, n, cores), 4.0, 3)
         assert bytes(back[: UNIT * nb_p]) == raw.tobytes()
