@@ -425,6 +425,15 @@ extern "C" int rcz_bwt_encode_blocks(rcz_ctx* c, const void* in_base, const uint
     if (!in_base || !in_off || !n_arr || !out_base || !out_off || !origin || !status || nblocks > 0x3fffffu) return RCZ_E_ARG;
     for (size_t i = 0; i < nblocks; ++i) if (in_off[i] > (1ull << 62) || out_off[i] > (1ull << 62)) return RCZ_E_ARG;
     rt_set_device(c->device);
+    if (mem_kind == RCZ_MEM_HOST && rcz_spans_ok(in_off, n_arr, nblocks)) {    // big host batches: pipelined chunks of 256 MiB
+        bool handled = false;
+        const int st = host_chunked(c, nblocks, 256ull << 20, in_base, in_off, n_arr, 1, out_base, out_off, n_arr, 1,
+            [&](size_t b0, size_t nb, const uint8_t* din, uint8_t* dout) {
+                return rcz_bwt_encode_blocks(c, din, in_off + b0, n_arr + b0, dout, out_off + b0, origin + b0, status + b0, nb, RCZ_MEM_DEVICE);
+            },
+            [&](size_t i) { return status[i] == RCZ_OK ? n_arr[i] : 0; }, &handled);
+        if (st || handled) return st;
+    }
 
     // ---- geometry; big batches are cut into groups so that the sort workspace (28 B / symbol) stays bounded
     constexpr unsigned long long GROUP_ELEMS = 1ull << 28;

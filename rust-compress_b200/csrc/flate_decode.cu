@@ -427,6 +427,16 @@ extern "C" int rcz_flate_decode_streams(rcz_ctx* c, const void* in_base, const u
     if (!in_base || !in_off || !in_len || !out_base || !out_off || !out_cap || !out_len || !status || n > 0x7fffffffu) return RCZ_E_ARG;
     rt_set_device(c->device);
     if (!rcz_spans_ok(in_off, in_len, n) || !rcz_spans_ok(out_off, out_cap, n)) return RCZ_E_ARG;
+    if (mem_kind == RCZ_MEM_HOST) {                                            // big host batches: chunks of ~1 GiB of output (>= 16 K streams of 64 KiB fill the GPU)
+        bool handled = false;
+        const int st = host_chunked(c, n, 1ull << 30, in_base, in_off, in_len, 1, out_base, out_off, out_cap, 1,
+            [&](size_t b0, size_t nb, const uint8_t* din, uint8_t* dout) {
+                return rcz_flate_decode_streams(c, din, in_off + b0, in_len + b0, dout, out_off + b0, out_cap + b0, out_len + b0, in_used ? in_used + b0 : nullptr,
+                                                status + b0, detail ? detail + b0 : nullptr, nb, RCZ_MEM_DEVICE);
+            },
+            [&](size_t i) { return out_len[i] < out_cap[i] ? out_len[i] : out_cap[i]; }, &handled);
+        if (st || handled) return st;
+    }
     DescStager ds(c, mem_kind, n);
     ds.add_in(in_off, n * 8); ds.add_in(in_len, n * 8); ds.add_in(out_off, n * 8); ds.add_in(out_cap, n * 8);
     ds.add_out(out_len, n * 8); ds.add_out(status, n * 4);
@@ -592,6 +602,16 @@ extern "C" int rcz_zlib_decode_streams(rcz_ctx* c, const void* in_base, const ui
     if (!in_base || !in_off || !in_len || !out_base || !out_off || !out_cap || !out_len || !status || n > 0x7fffffffu) return RCZ_E_ARG;
     rt_set_device(c->device);
     if (!rcz_spans_ok(in_off, in_len, n) || !rcz_spans_ok(out_off, out_cap, n)) return RCZ_E_ARG;
+    if (mem_kind == RCZ_MEM_HOST) {                                            // big host batches in pipelined chunks, as rcz_flate_decode_streams
+        bool handled = false;
+        const int st = host_chunked(c, n, 1ull << 30, in_base, in_off, in_len, 1, out_base, out_off, out_cap, 1,
+            [&](size_t b0, size_t nb, const uint8_t* din, uint8_t* dout) {
+                return rcz_zlib_decode_streams(c, din, in_off + b0, in_len + b0, dout, out_off + b0, out_cap + b0, out_len + b0, in_used ? in_used + b0 : nullptr,
+                                               status + b0, detail ? detail + b0 : nullptr, adler ? adler + b0 : nullptr, nb, RCZ_MEM_DEVICE);
+            },
+            [&](size_t i) { return out_len[i] < out_cap[i] ? out_len[i] : out_cap[i]; }, &handled);
+        if (st || handled) return st;
+    }
     // the DEFLATE stream starts after the two header bytes (zlib.rs:55-57)
     std::vector<uint64_t> off2(n), len2(n);
     for (size_t i = 0; i < n; ++i) { const uint64_t h = in_len[i] < 2 ? in_len[i] : 2; off2[i] = in_off[i] + h; len2[i] = in_len[i] - h; }

@@ -4,6 +4,8 @@
 #include "rt.h"
 #include <stdio.h>
 #include <vector>
+#include <algorithm>
+#include <stdlib.h>
 
 // WS_P*: intermediates owned by a composed call (pipeline.cu) that must survive the nested stage calls
 enum { WS_IN = 0, WS_OUT = 1, WS_DESC = 2, WS_A = 3, WS_B = 4, WS_C = 5, WS_D = 6, WS_E = 7, WS_P0 = 8, WS_P1 = 9, WS_P2 = 10, WS_P3 = 11, WS_P4 = 12, WS_COUNT = 13 };
@@ -170,6 +172,84 @@ inline int unstage_span_out(rcz_ctx* c, void* host_base, const uint8_t* dev_base
     RCZ_CK(c, rt_stream_sync(c->stream));
     return RCZ_OK;
 }
+// ------------------------------------------------------------------------------------------------
+// HOST-buffer batches in pipelined chunks.  A batch op's host path is "upload everything, run, download everything": three
+// phases of which two are PCIe copies.  This helper cuts the batch into chunks of consecutive units (about `chunk_bytes` of
+// max(input, output capacity) each, sized by the caller so that one chunk still fills the GPU) and runs the op's own
+// RCZ_MEM_DEVICE form on every chunk — call(b0, nb, dev_in_base, dev_out_base), which returns when the chunk's kernels are done —
+// while the next chunk's input goes up on one copy stream and the previous chunk's output comes down on another.  Device arenas
+// mirror the host arenas (same offsets), as in stage_span_in / stage_span_out.  *handled = false (nothing done) when the batch is
+// too small to cut or its units are not laid out in order (a chunk's span would drag in other chunks' bytes).
+// out_elems(i) = elements of unit i to bring back (looked at after the chunk's call, i.e. with its results in the host arrays).
+// ------------------------------------------------------------------------------------------------
+template <class Call, class OutElems>
+inline int host_chunked(rcz_ctx* c, size_t n, uint64_t chunk_bytes, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                        size_t in_elem, void* out_base, const uint64_t* out_off, const uint64_t* out_cap, size_t out_elem, Call call,
+                        OutElems out_elems, bool* handled) {
+    *handled = false;
+    if (c->nest || n < 2) return RCZ_OK;
+    if (const char* e = getenv("RCZ_HOST_CHUNK_BYTES")) chunk_bytes = strtoull(e, nullptr, 10);
+    if (chunk_bytes == 0) return RCZ_OK;
+    std::vector<size_t> cut{0};
+    uint64_t ai = 0, ao = 0;
+    for (size_t i = 0; i < n; ++i) {
+        ai += in_len[i] * in_elem; ao += out_cap[i] * out_elem;
+        if ((ai >= chunk_bytes || ao >= chunk_bytes) && i + 1 < n) { cut.push_back(i + 1); ai = ao = 0; }
+    }
+    cut.push_back(n);
+    const size_t nch = cut.size() - 1;
+    if (nch < 2) return RCZ_OK;
+    // input span of every chunk; the chunks' spans together must not be (much) more than the batch's span
+    std::vector<uint64_t> lo(nch, UINT64_MAX), hi(nch, 0);
+    uint64_t glo = UINT64_MAX, ghi = 0, sum = 0;
+    for (size_t k = 0; k < nch; ++k) {
+        for (size_t i = cut[k]; i < cut[k + 1]; ++i) {
+            if (!in_len[i]) continue;
+            lo[k] = std::min(lo[k], in_off[i]); hi[k] = std::max(hi[k], in_off[i] + in_len[i]);
+        }
+        if (lo[k] == UINT64_MAX) { lo[k] = hi[k] = 0; continue; }
+        glo = std::min(glo, lo[k]); ghi = std::max(ghi, hi[k]); sum += hi[k] - lo[k];
+    }
+    if (glo == UINT64_MAX) return RCZ_OK;
+    if (sum > (ghi - glo) + (ghi - glo) / 4 + 4096) return RCZ_OK;
+    int st = ctx_aux_streams(c); if (st) return st;
+    st = ctx_events(c, nch); if (st) return st;
+    const uint8_t* din; uint8_t* dout;
+    {
+        const uint64_t lo_al = (glo * in_elem) & ~(uint64_t)255;
+        void* d; st = ctx_ws(c, WS_IN, (size_t)(ghi * in_elem - lo_al) + 512, &d); if (st) return st;
+        din = (const uint8_t*)d - lo_al;
+    }
+    st = stage_span_out(c, WS_OUT, out_off, out_cap, n, out_elem, &dout); if (st) return st;
+    *handled = true;
+    const rt_stream_t up = c->aux[0], down = c->aux[1];
+    RCZ_CK(c, rt_stream_sync(c->stream));                                      // (workspace (re)allocation, earlier calls)
+    auto upload = [&](size_t k) -> int {
+        if (hi[k] > lo[k]) RCZ_CK(c, rt_h2d((uint8_t*)din + lo[k] * in_elem, (const uint8_t*)in_base + lo[k] * in_elem, (size_t)((hi[k] - lo[k]) * in_elem), up));
+        RCZ_CK(c, rt_event_record(c->events[k], up));
+        return RCZ_OK;
+    };
+    st = upload(0); if (st) return st;
+    for (size_t k = 0; k < nch; ++k) {
+        if (k + 1 < nch) { st = upload(k + 1); if (st) return st; }
+        RCZ_CK(c, rt_stream_wait_event(c->stream, c->events[k]));
+        st = call(cut[k], cut[k + 1] - cut[k], din, dout); if (st) return st;  // returns with the chunk's kernels done and its results on the host
+        size_t i = cut[k];
+        const size_t e = cut[k + 1];
+        while (i < e) {                                                        // adjacent units merged into one copy
+            const uint64_t li = out_elems(i);
+            if (li == 0) { ++i; continue; }
+            const uint64_t s0 = out_off[i]; uint64_t t = s0 + li;
+            size_t j = i + 1;
+            while (j < e) { const uint64_t lj = out_elems(j); if (lj && out_off[j] != t) break; t += lj; ++j; }
+            RCZ_CK(c, rt_d2h((uint8_t*)out_base + s0 * out_elem, dout + s0 * out_elem, (size_t)((t - s0) * out_elem), down));
+            i = j;
+        }
+    }
+    RCZ_CK(c, rt_stream_sync(down));
+    return RCZ_OK;
+}
+
 // ---- entry points with DEVICE descriptor arrays, for composed calls (pipeline.cu); they only enqueue on c->stream
 constexpr unsigned long long RCZ_STREAM_SKIP = ~0ull;     // in_len value of an unused stream slot: out_len = 0, status = OK
 int rcz_ari_launch(rcz_ctx* c, bool decode, const uint8_t* din, const uint64_t* d_in_off, const uint64_t* d_in_len, uint8_t* dout,
