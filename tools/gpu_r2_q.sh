@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2: DC decode with the register-resident list — parity tests, then the C5 pipeline leg (stage times)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_dc_kernels.py tests/test_pipeline.py -m gpu -x -q 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_dc_kernels.py tests/test_pipeline.py tests/test_ari_rle_kernels.py -m gpu -x -q 2>&1 | tail -3
 timeout 900 python bench.py --codecs pipeline > gpurun_out/r2_bench_q.json 2> gpurun_out/r2_bench_q.err
 python - <<PY
 import json
