@@ -55,7 +55,7 @@ def main():
         d_in, d_out = torch.from_numpy(packed).cuda(), torch.zeros(UNIT * nblk, dtype=torch.uint8, device="cuda")
         ms = timed(lambda: ctx.lz4_decode_blocks(d_in, ioff, ilen, d_out, off, n, async_=True), reps)
         assert torch.equal(d_out, torch.from_numpy(raw).cuda())
-        report("lz4_decode", UNIT * nblk, ms, {"C_bytes": int(ilen.sum())})
+        report("lz4_decode", UNIT * nblk, ms, {"C_bytes": int(ilen.sum()), "stage_ms": ctx.last_stage_ms()})
         for kind in ("hextext", "runs", "random"):          # other shapes of input: 9-byte sequences with in-tile chains, long matches, one literal run
             raw = gen.units(kind, gen.unit_seed(2, 0), UNIT, nblk)
             packed, ioff, ilen = gen.lz4_compress_units(raw, UNIT, nblk)
