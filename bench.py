@@ -584,7 +584,7 @@ def leg_bwt(env, args):
            "block_bytes": UNIT, "l2": "inputs larger than L2 (%.2f GiB per GPU per step)" % (2 * UNIT * nb / 2**30), "parallelism": "contiguous block ranges per rank (shard.partition), no data-path collective"}
     out = {}
     out["bwt_encode"] = {"config": cfg, "value": total_U / (ms_e * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_e, "steps": reps_e, "scaling": "strong", "dtype": "u8",
-                         "roofline": roofline(env, "bwte::scatter_kernel (no capture: traffic null)", alg, ms_e, ms_e, {"note": "op-level figure: the round-0 sort is 8 radix passes (hist, scan, scatter launches each); kernel_ms = the whole call"}),
+                         "roofline": roofline(env, "bwte::scatter_kernel (no capture: traffic null)", alg, ms_e, ms_e, {"note": "op-level figure: round 0 sorts 45-bit keys in 6 radix passes (hist, scan, scatter launches each), later rounds only the still-unresolved suffixes; kernel_ms = the whole call"}),
                          "e2e": {"value": total_U / e2e_e / 1e9, "unit": "GB/s", "h2d_bytes_per_step": UNIT * nb, "d2h_bytes_per_step": (UNIT + 4) * nb, "ms_per_step": e2e_e * 1e3},
                          "gpu_launches_per_step": per_call_e}
     walk_ms = max(kd_stage) if kd_stage else kd_ms
