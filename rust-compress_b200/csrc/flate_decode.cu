@@ -221,7 +221,16 @@ __device__ __noinline__ unsigned huff_slow(const Tree* t, const uint16_t* symtab
 
 // flate.rs:262-341 codes.  Every lane of the warp tracks the same bit-reader state (the symbol chain is serial); what the lanes share out
 // is the LZ77 copy.  One table load gives the symbol, its extra-bit count and its base value; literals leave through lane 0.
-__device__ int codes(St& s, WarpSmem& w, unsigned lane) {
+// A match copy is a load from the stream's own recent output (L2) followed by a store of what was loaded; issued back to back the
+// store waits out the load's round trip with the whole warp behind it (15 % of the kernel's stall samples).  So a short,
+// non-overlapping copy only LOADS, and its store is issued when the next match (whose source may lie in the copied bytes) or
+// the end of the block is reached — one or more symbol decodes later, when the data has arrived.
+struct PendingCopy { unsigned o, n, v; };                                                // n bytes at out[o + lane], this lane's byte in v
+__device__ __forceinline__ void commit(const St& s, PendingCopy& pc, unsigned lane) {
+    if (lane < pc.n) s.out[pc.o + lane] = (uint8_t)pc.v;
+    pc.n = 0;
+}
+__device__ __forceinline__ int codes_body(St& s, WarpSmem& w, unsigned lane, PendingCopy& pc) {
     for (;;) {
         s.br.refill();                                                                  // >= 33 bits: code (<= 15) + length extra (<= 5) ...
         unsigned e = w.llut[s.br.peek(LB)];
@@ -274,10 +283,13 @@ __device__ int codes(St& s, WarpSmem& w, unsigned lane) {
         const unsigned hist = s.o < HISTORY ? s.o : HISTORY;                            // flate.rs:314
         if (d > hist) { s.detail = RCZ_FL_INVALID_HUFFMAN_CODE; return F_INVALID; }
         if (len > s.cap - s.o) return F_FULL;
-        __syncwarp();                                                                   // lane 0's literal stores are ordered before the copy's loads
+        commit(s, pc, lane);                                                            // the previous copy's bytes may be this one's source
+        __syncwarp();                                                                   // the literal stores and that copy are ordered before the loads
         const uint8_t* src = s.out + s.o - d;
         uint8_t* dst = s.out + s.o;
-        if (d >= len) {                                                                 // source and destination do not overlap (the common case)
+        if (d >= len && len <= 32u) {                                                   // the common case: load now, store later
+            pc.o = s.o; pc.n = len; pc.v = lane < len ? (unsigned)src[lane] : 0u;
+        } else if (d >= len) {                                                          // source and destination do not overlap
             for (unsigned j = lane; j < len; j += 32) dst[j] = src[j];
         } else {
             for (unsigned j = lane; j < len; j += 32) dst[j] = src[j % d];              // flate.rs:325-334: the d bytes before the match, repeated
@@ -285,6 +297,14 @@ __device__ int codes(St& s, WarpSmem& w, unsigned lane) {
         __syncwarp();
         s.o += len;
     }
+}
+
+__device__ int codes(St& s, WarpSmem& w, unsigned lane) {
+    PendingCopy pc{0, 0, 0};
+    const int r = codes_body(s, w, lane, pc);
+    commit(s, pc, lane);
+    __syncwarp();
+    return r;
 }
 
 // flate.rs:237-246 statik
