@@ -113,7 +113,7 @@ def _alphabet_case(ctx, oracle, device=False, n=30000):
     class boundary, skewed symbol frequencies so that re-entries reach every depth"""
     rs = np.random.RandomState(17)
     blocks, streams = [], []
-    for a in (2, 3, 31, 32, 33, 63, 64, 65, 96, 127, 128, 129, 200, 255, 256):
+    for a in (2, 3, 31, 32, 33, 63, 64, 65, 96, 97, 127, 128, 129, 160, 161, 192, 193, 224, 225, 255, 256):
         syms = rs.permutation(256)[:a].astype(np.uint8)
         w = 1.0 / (1.0 + np.arange(a)) ** 0.7
         b = syms[rs.choice(a, size=n, p=w / w.sum())]
