@@ -84,3 +84,45 @@ def test_host_chunked_emu(emu_ctx, oracle, gen, chunk, monkeypatch):
 def test_host_chunked_gpu(gpu_ctx, oracle, gen, chunk, pinned, monkeypatch):
     monkeypatch.setenv("RCZ_HOST_CHUNK_BYTES", chunk)
     _run(gpu_ctx, oracle, gen, pinned)
+
+
+def test_host_chunked_layout_edge_cases_emu(emu_ctx, oracle, gen, monkeypatch):
+    """Layouts the chunk cutter must cope with: empty units between full ones, units stored in REVERSE order (a chunk's span would drag
+    in the other chunks' bytes: the batch must fall back to the single-shot path), a batch of one unit."""
+    monkeypatch.setenv("RCZ_HOST_CHUNK_BYTES", "8000")
+    raw = [gen.one("hextext", 40 + i, 2500 + 300 * i) for i in range(12)]
+    z = [pyzlib.compress(r, 6)[2:-4] for r in raw]
+    # (a) empty streams in between: status of an empty DEFLATE stream is the oracle's, the neighbours decode
+    units = []
+    for i, u in enumerate(z):
+        units.append(u)
+        if i % 3 == 0:
+            units.append(b"")
+    caps = [4000 + 300 * 12] * len(units)
+    zb, z_off, z_len = pack(units, pad_front=1, gap=2, align=1)
+    o_off, o_cap, tot = out_layout(caps, gap=3)
+    out = np.full(tot, 0xAA, dtype=np.uint8)
+    out_len, status, used, detail = emu_ctx.flate_decode_streams(zb, z_off, z_len, out, o_off, o_cap)
+    k = 0
+    for i, u in enumerate(units):
+        ref = oracle.flate_decode(u, caps[i])
+        assert int(status[i]) == ref[0], i
+        if u:
+            assert out[int(o_off[i]): int(o_off[i]) + int(out_len[i])].tobytes() == raw[k]
+            k += 1
+    # (b) the same streams, stored back to front
+    order = list(range(len(z)))[::-1]
+    zb, z_off, z_len = pack([z[i] for i in order], pad_front=0, gap=1, align=1)
+    z_off, z_len = z_off[::-1].copy(), z_len[::-1].copy()         # unit i is z[i] again, at descending offsets
+    caps = [len(r) for r in raw]
+    o_off, o_cap, tot = out_layout(caps, gap=3)
+    out = np.full(tot, 0xAA, dtype=np.uint8)
+    out_len, status, used, detail = emu_ctx.flate_decode_streams(zb, z_off, z_len, out, o_off, o_cap)
+    for i, r in enumerate(raw):
+        assert status[i] == 0 and out[int(o_off[i]): int(o_off[i]) + len(r)].tobytes() == r, i
+    # (c) one unit
+    zb, z_off, z_len = pack([z[0]], pad_front=3, gap=0, align=1)
+    o_off, o_cap, tot = out_layout([len(raw[0])], gap=0)
+    out = np.zeros(tot, dtype=np.uint8)
+    out_len, status, used, detail = emu_ctx.flate_decode_streams(zb, z_off, z_len, out, o_off, o_cap)
+    assert status[0] == 0 and out[: len(raw[0])].tobytes() == raw[0]
