@@ -15,7 +15,9 @@
  *   - every call returns an rcz_status; per-block outcomes go to status[i] (same codes).
  *   - mem_kind selects where the buffers live:
  *       RCZ_MEM_HOST          data + descriptor arrays in host memory; the library stages H2D/D2H and
- *                             returns when the results are in the caller's host buffers.
+ *                             returns when the results are in the caller's host buffers.  Big batches (lz4, bwt,
+ *                             flate, zlib) are cut into chunks of consecutive units whose uploads, kernels and
+ *                             downloads overlap; page-locked buffers (rcz_host_alloc) are what makes them overlap.
  *       RCZ_MEM_DEVICE        data pointers are device pointers; descriptor/result arrays
  *                             (offsets, lengths, status) are host arrays; returns when results are valid.
  *       RCZ_MEM_DEVICE_ASYNC  data pointers AND result arrays (out_len, status, origin-out, in_used, detail)
@@ -109,8 +111,9 @@ int rcz_lz4_decode_blocks(rcz_ctx* ctx, const void* in_base, const uint64_t* in_
 /* Multi-GPU form of rcz_lz4_decode_blocks (device pointers only): the same decode, and every output byte written at out_base + x is
  * also written at peer_out_base[p] + x for p < npeers (<= 7) — pointers into the other GPUs' output buffers, mapped into this process
  * over NVLink / NVSwitch (CUDA IPC or symmetric memory).  With one rank per GPU and every rank passing its own slot of a common layout,
- * the final gather of the decoded shards is done by the decode kernel's own stores; the caller synchronises the ranks
- * afterwards (stream sync + barrier) before reading. */
+ * the final gather of the decoded shards is done by the decode kernel itself (bulk stores of every finished output tile);
+ * the caller synchronises the ranks afterwards (stream sync + barrier) before reading.  Every peer_out_base[p] - out_base must be a
+ * multiple of 16 (the peers' chunks are stored as aligned as the local ones), else RCZ_E_ARG. */
 int rcz_lz4_decode_blocks_gather(rcz_ctx* ctx, const void* in_base, const uint64_t* in_off, const uint64_t* in_len,
                                  void* out_base, const uint64_t* out_off, const uint64_t* out_cap,
                                  uint64_t* out_len, int32_t* status, size_t nblocks, int mem_kind,
