@@ -23,10 +23,13 @@
 
 namespace bwte {
 
-constexpr int TB = 8192;                  // elements per radix tile
+// elements per radix tile.  Measured on 256 x 4 MiB random blocks (ms per GiB): 8192 (2 CTAs / SM: 128 registers, 108 KB) 139, 4096 (3) 124,
+// 3072 (4) 127, 2048 (4 CTAs / SM: 64 registers, 36 KB) 118, 1024 (5) 145 — the partition kernel is latency-bound, more resident CTAs
+// hide more of it until the per-tile bookkeeping (256-entry scans, the tile histograms) takes over.
+constexpr int TB = 2048;
 constexpr int NT = 256;                   // threads per tile CTA
 constexpr int NW = NT / 32;
-constexpr int WSPAN = TB / NW;            // 1024 consecutive elements per warp
+constexpr int WSPAN = TB / NW;            // consecutive elements per warp
 constexpr int SPAN = 1024;                // rank-assignment granularity (one warp)
 constexpr unsigned NONE = 0xFFFFFFFFu;
 constexpr int NSYM0 = 5;                 // symbols in a round-0 key (45 bits: 6 radix passes)
@@ -132,7 +135,7 @@ struct ScatSmem {
     unsigned scratch[40];
 };
 
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, 4)
 scatter_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* __restrict__ state, const unsigned* __restrict__ cnt,
                const unsigned long long* __restrict__ Kin, const unsigned* __restrict__ Vin, unsigned long long* __restrict__ Kout, unsigned* __restrict__ Vout, unsigned shift,
                const unsigned* __restrict__ tile_hist, const unsigned* __restrict__ cbase, const unsigned* __restrict__ guard) {
@@ -152,7 +155,7 @@ scatter_kernel(const Blk* __restrict__ blks, unsigned nblocks, const unsigned* _
 
     for (unsigned i = tid; i < NW * 256; i += NT) (&sm.wcnt[0][0])[i] = 0;
     __syncthreads();
-    // per-warp digit counts, and for every key its rank among the equal digits of the warp's 1024-key span (count before this group of
+    // per-warp digit counts, and for every key its rank among the equal digits of the warp's WSPAN-key span (count before this group of
     // 32 + rank inside the group): the 8 ballots are done ONCE per 32 keys and the ranks kept in registers, two per register
     unsigned rb[WSPAN / 64];
 #pragma unroll
