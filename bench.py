@@ -703,12 +703,12 @@ def leg_pipeline(env, args):
 
     def enc_host():
         r["e"] = ctx.bwt_dc_ari_encode_blocks(h_raw_np, off, n, h_cont.numpy(), coff, caps, ari_chunk=ARI_CHUNK)
-    e2e_e = env.time_host(enc_host, 1, 0)
+    e2e_e = env.time_host(enc_host, 2, 1)
     assert (r["e"][2] == 0).all() and (r["e"][0] == clen).all()
 
     def dec_host():
         r["d"] = ctx.bwt_dc_ari_decode_blocks(h_cont.numpy(), coff, clen, h_back.numpy(), off, n, ari_chunk=ARI_CHUNK)
-    e2e_d = env.time_host(dec_host, 1, 0)
+    e2e_d = env.time_host(dec_host, 2, 1)
     assert (r["d"][1] == 0).all() and bytes(h_back.numpy()[: UNIT * nb]) == raw.tobytes()
     total_U = world * nb * UNIT
     cfg = {"workload": "bwt -> dc -> entropy::ari (bzip-style) on %d hexdump-text blocks of 4 MiB per GPU; dc output serialised as u32 LE, ByteEncoder streams of %d bytes" % (nb, ARI_CHUNK),
