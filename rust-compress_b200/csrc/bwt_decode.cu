@@ -472,10 +472,10 @@ extern "C" int rcz_bwt_decode_blocks(rcz_ctx* c, const void* in_base, const uint
                                      uint64_t* out_len, int32_t* status, size_t nblocks, int mem_kind) {
     if (nblocks && !origin) return RCZ_E_ARG;
     if (mem_kind == RCZ_MEM_HOST && c && nblocks && in_base && in_off && n_arr && out_base && out_off && out_len && status &&
-        rcz_spans_ok(in_off, n_arr, nblocks) && rcz_spans_ok(out_off, n_arr, nblocks)) {   // big host batches: pipelined chunks of 256 MiB
+        rcz_spans_ok(in_off, n_arr, nblocks) && rcz_spans_ok(out_off, n_arr, nblocks)) {   // big host batches: pipelined chunks of 128 MiB (sweep: profiles/r2_host_chunk_sweep.txt)
         rt_set_device(c->device);
         bool handled = false;
-        const int st = host_chunked(c, nblocks, 256ull << 20, in_base, in_off, n_arr, 1, out_base, out_off, n_arr, 1,
+        const int st = host_chunked(c, nblocks, 128ull << 20, in_base, in_off, n_arr, 1, out_base, out_off, n_arr, 1,
             [&](size_t b0, size_t nb, const uint8_t* din, uint8_t* dout) {
                 return rcz_bwt_decode_run(c, din, in_off + b0, n_arr + b0, origin + b0, nullptr, dout, out_off + b0, out_len + b0, status + b0, nb, RCZ_MEM_DEVICE);
             },
