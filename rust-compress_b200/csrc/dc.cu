@@ -375,6 +375,12 @@ dc_decode_kernel(const uint32_t* __restrict__ in_base, const uint64_t* __restric
 #pragma unroll
         for (int k = 0; k < 8; ++k) present += init[k] < n ? 1u : 0u;
         const unsigned A = __reduce_add_sync(RCZ_FULL, present);
+        // dc.rs:230 looks at all 256 entries when the loop is over: a symbol that never occurs must still carry a "next position" in
+        // [n, n + alphabet) (the encoder writes n), else the block is malformed
+        bool stray = false;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) stray |= init[k] >= n && init[k] >= n + A;
+        const bool absent_bad = __any_sync(RCZ_FULL, stray);
         for (int src = 0; src < 32; ++src) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -412,6 +418,7 @@ dc_decode_kernel(const uint32_t* __restrict__ in_base, const uint64_t* __restric
         else if (A <= 64) err = dc_decode_list<2>(sm.nx[w], sm.sy[w], A, (unsigned)n, dist, ndist, out, lane);
         else if (A <= 128) err = dc_decode_list<4>(sm.nx[w], sm.sy[w], A, (unsigned)n, dist, ndist, out, lane);
         else err = dc_decode_list<8>(sm.nx[w], sm.sy[w], A, (unsigned)n, dist, ndist, out, lane);
+        if (!err && absent_bad) err = RCZ_E_MALFORMED;
         __syncwarp();
         if (lane == 0) status[b] = err;
     }

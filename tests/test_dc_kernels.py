@@ -139,6 +139,15 @@ def _alphabet_case(ctx, oracle, device=False, n=30000):
             t = s_.copy()
             t[present[k]] = t[present[k - 1]]
             bad.append(t)
+    # a symbol that never occurs whose init[] entry is not in [n, n + alphabet): the reference's closing assert (dc.rs:230) looks at
+    # all 256 entries (found by tools/stress_emu.py)
+    for s_ in streams[:6]:
+        absent = np.nonzero(s_[:256] >= n)[0]
+        for v in (0xFFFFFFFF, n + 256, n + 1):
+            if len(absent):
+                t = s_.copy()
+                t[absent[len(absent) // 2]] = v
+                bad.append(t)
     ns = [len(blocks[0])] * len(bad)
     dec = _decode(ctx, bad, ns, device=device)
     for i, t in enumerate(bad):
