@@ -250,13 +250,72 @@ def stress_pipeline(ctx, rs, secs):
     return cases
 
 
+def stress_zlib_adler(ctx, rs, secs):
+    t0, cases = time.time(), 0
+    while time.time() - t0 < secs:
+        raws = [rand_block(rs, rs.choice([0, 1, 10, 300, 5000, 40000])) for _ in range(8)]
+        units = []
+        for r in raws:
+            z = zlib.compress(r, rs.randrange(0, 10))
+            if rs.random() < 0.15:
+                z += zlib.compressobj(6, zlib.DEFLATED, -15).flush()[:0]
+            k = rs.random()
+            if k < 0.1:
+                z = z[:-rs.randrange(1, 5)]                      # trailer cut
+            elif k < 0.25 and len(z) > 6:
+                z = bytearray(z); z[rs.choice([0, 1, len(z) - 1, len(z) - 4, rs.randrange(len(z))])] ^= 1 << rs.randrange(8); z = bytes(z)
+            units.append(z)
+        caps = [len(r) + rs.choice([0, 0, 7]) for r in raws]
+        zb, z_off, z_len = pack(units, pad_front=rs.randrange(4), gap=rs.randrange(4), align=1)
+        o_off, o_cap, tot = out_layout(caps, gap=rs.randrange(5))
+        out = np.zeros(tot, dtype=np.uint8)
+        out_len, status, used, detail, adler = ctx.zlib_decode_streams(zb, z_off, z_len, out, o_off, o_cap)
+        for i in range(len(units)):
+            ref = oracle.zlib_decode(units[i], caps[i])
+            assert int(status[i]) == ref[0], ("zlib status", i, int(status[i]), ref[0])
+            k = min(int(out_len[i]), caps[i])
+            assert out[int(o_off[i]): int(o_off[i]) + k].tobytes() == bytes(ref[1][:k]), ("zlib bytes", i)
+            if ref[0] == 0:
+                assert int(adler[i]) == ref[4] and int(used[i]) == ref[2], ("zlib adler / used", i)
+        inb, in_off, in_len = pack(raws, pad_front=rs.randrange(17), gap=rs.randrange(3), align=1)
+        ad = ctx.adler32_streams(inb, in_off, in_len)
+        for i, r in enumerate(raws):
+            assert int(ad[i]) == (zlib.adler32(r) & 0xFFFFFFFF) == oracle.adler32(r), ("adler32", i)
+        cases += 2 * len(units)
+    return cases
+
+
+def stress_encoders(ctx, rs, secs):
+    t0, cases = time.time(), 0
+    while time.time() - t0 < secs:
+        raws = [rand_block(rs, rs.choice([0, 1, 11, 12, 13, 100, 3000, 30000, 70000])) for _ in range(5)]
+        inb, in_off, in_len = pack(raws, pad_front=rs.randrange(9), gap=rs.randrange(4), align=1)
+        caps = [oracle.lz4_compression_bound(len(r)) + 16 for r in raws]
+        o_off, o_cap, tot = out_layout(caps, gap=2)
+        out = np.zeros(tot, dtype=np.uint8)
+        out_len, status = ctx.lz4_encode_blocks(inb, in_off, in_len, out, o_off, o_cap)
+        for i, r in enumerate(raws):
+            assert status[i] == 0 and out[int(o_off[i]): int(o_off[i]) + int(out_len[i])].tobytes() == bytes(oracle.lz4_encode_block(r)), ("lz4 encode", i, len(r))
+        dcaps = [256 + len(r) for r in raws]
+        d_off, d_cap, dtot = out_layout(dcaps, gap=1)
+        dout = np.zeros(dtot, dtype=np.uint32)
+        out_len, status = ctx.dc_encode_blocks(inb, in_off, in_len, dout, d_off, d_cap)
+        for i, r in enumerate(raws):
+            st, init, dist = oracle.dc_encode(r)
+            ref = np.concatenate([init, dist]).astype(np.uint32)
+            assert status[i] == 0 and np.array_equal(dout[int(d_off[i]): int(d_off[i]) + int(out_len[i])], ref), ("dc encode", i, len(r))
+        cases += 2 * len(raws)
+    return cases
+
+
 def main():
     secs = float(sys.argv[1]) if len(sys.argv) > 1 else 20.0
     seed = int(os.environ.get("STRESS_SEED", "1"))
     rs = random.Random(seed)
     ctx = rcz.Context(emu=True)
     only = [a for a in sys.argv[2:]]
-    for name, fn in (("dc", stress_dc), ("flate", stress_flate), ("ari", stress_ari), ("lz4", stress_lz4), ("bwt", stress_bwt), ("mtf_rle", stress_mtf_rle), ("pipeline", stress_pipeline)):
+    for name, fn in (("dc", stress_dc), ("flate", stress_flate), ("ari", stress_ari), ("lz4", stress_lz4), ("bwt", stress_bwt), ("mtf_rle", stress_mtf_rle), ("pipeline", stress_pipeline),
+                     ("zlib_adler", stress_zlib_adler), ("encoders", stress_encoders)):
         if only and name not in only:
             continue
         n = fn(ctx, rs, secs)
