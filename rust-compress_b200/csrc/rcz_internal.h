@@ -242,9 +242,10 @@ inline int host_chunked(rcz_ctx* c, size_t n, uint64_t chunk_bytes, const void* 
     };
     st = upload(0); if (st) return st;
     for (size_t k = 0; k < nch; ++k) {
-        if (k + 1 < nch) { st = upload(k + 1); if (st) return st; }
+        if (k + 1 < nch) { st = upload(k + 1); if (st) { rt_stream_sync(up); rt_stream_sync(down); return st; } }
         RCZ_CK(c, rt_stream_wait_event(c->stream, c->events[k]));
-        st = call(cut[k], cut[k + 1] - cut[k], din, dout); if (st) return st;  // returns with the chunk's kernels done and its results on the host
+        st = call(cut[k], cut[k + 1] - cut[k], din, dout);                     // returns with the chunk's kernels done and its results on the host
+        if (st) { rt_stream_sync(up); rt_stream_sync(down); return st; }       // (no copy may still be touching the caller's buffers)
         size_t i = cut[k];
         const size_t e = cut[k + 1];
         while (i < e) {                                                        // adjacent units merged into one copy
