@@ -142,7 +142,8 @@ def stress_lz4(ctx, rs, secs):
                     c[rs.randrange(len(c))] = rs.randrange(256)
                 c = bytes(c[: rs.randrange(1, len(c) + 1)]) if rs.random() < 0.3 else bytes(c)
             units.append(c)
-        caps = [max(len(r) + rs.choice([0, 0, 0, 0, -1, -17, 100]), 0) for r in raws]
+        roomy = rs.random() < 0.15                                # capacities far beyond the data: the host pipeline's length-first copy path
+        caps = [max(len(r) + rs.choice([0, 0, 0, 0, -1, -17, 100]), 0) + (rs.choice([0, 300000, 2000000]) if roomy else 0) for r in raws]
         inb, in_off, in_len = pack(units, pad_front=rs.randrange(20), gap=rs.randrange(4), align=1)
         o_off, o_cap, tot = out_layout(caps, gap=rs.randrange(9))
         out = np.zeros(tot, dtype=np.uint8)
