@@ -310,15 +310,17 @@ def stress_encoders(ctx, rs, secs):
 
 
 def main():
+    import faulthandler
+    faulthandler.enable()                                         # a crash inside the emulated kernels still says where Python was
     secs = float(sys.argv[1]) if len(sys.argv) > 1 else 20.0
     seed = int(os.environ.get("STRESS_SEED", "1"))
-    rs = random.Random(seed)
     ctx = rcz.Context(emu=True)
     only = [a for a in sys.argv[2:]]
     for name, fn in (("dc", stress_dc), ("flate", stress_flate), ("ari", stress_ari), ("lz4", stress_lz4), ("bwt", stress_bwt), ("mtf_rle", stress_mtf_rle), ("pipeline", stress_pipeline),
                      ("zlib_adler", stress_zlib_adler), ("encoders", stress_encoders)):
         if only and name not in only:
             continue
+        rs = random.Random("%d/%s" % (seed, name))               # every op has its own sequence: a failure does not depend on what ran before
         n = fn(ctx, rs, secs)
         print("%s: %d random cases equal the oracle (seed %d)" % (name, n, seed), flush=True)
 
