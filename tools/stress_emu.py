@@ -122,7 +122,27 @@ def stress_ari(ctx, rs, secs):
         out_len, status = res[0], res[1]
         for i, r in enumerate(raws):
             assert status[i] == 0 and dec[int(d_off[i]): int(d_off[i]) + len(r)].tobytes() == r, ("ari decode", i)
-        cases += len(raws)
+        # damaged code streams: what decodes in the oracle must decode to the same bytes; what fails there must fail here
+        # (which of the reference's asserts a damaged stream trips first is not pinned)
+        bad = []
+        for c in codes:
+            b = bytearray(c)
+            if b and rs.random() < 0.7:
+                b[rs.randrange(len(b))] ^= 1 << rs.randrange(8)
+            bad.append(bytes(b[: rs.randrange(len(b) + 1)]) if rs.random() < 0.3 else bytes(b))
+        cb, c_off, c_len = pack(bad, pad_front=rs.randrange(17), gap=rs.randrange(3), align=1)
+        bcaps = [len(r) + 8 for r in raws]
+        d_off, d_cap, dtot = out_layout(bcaps, gap=2)
+        dec = np.zeros(dtot, dtype=np.uint8)
+        res = ctx.ari_decode_streams(cb, c_off, c_len, dec, d_off, d_cap)
+        out_len, status = res[0], res[1]
+        for i in range(len(bad)):
+            ref = oracle.ari_decode(bad[i], bcaps[i])
+            if ref[0] == 0:
+                assert status[i] == 0 and dec[int(d_off[i]): int(d_off[i]) + int(out_len[i])].tobytes() == bytes(ref[1]), ("ari damaged decode", i)
+            else:
+                assert status[i] != 0, ("ari damaged status", i, ref[0])
+        cases += 2 * len(raws)
     return cases
 
 
@@ -215,7 +235,26 @@ def stress_mtf_rle(ctx, rs, secs):
             out_len, status = res[0], res[1]
             for i, r in enumerate(raws):
                 assert status[i] == 0 and d[int(d_off[i]): int(d_off[i]) + len(r)].tobytes() == r, ("decode", dec.__name__, i)
-        cases += 2 * len(raws)
+        # damaged / truncated rle streams: status and the bytes delivered before the error follow the oracle (rle.rs:151-154, lib.rs:53-62)
+        rcodes = [bytes(oracle.rle_encode(r)) for r in raws]
+        bad = []
+        for c in rcodes:
+            b = bytearray(c)
+            if b and rs.random() < 0.7:
+                b[rs.randrange(len(b))] = rs.randrange(256)
+            bad.append(bytes(b[: rs.randrange(len(b) + 1)]) if rs.random() < 0.4 else bytes(b))
+        cb, c_off, c_len = pack(bad, pad_front=rs.randrange(5), gap=rs.randrange(3), align=1)
+        bcaps = [len(r) + rs.choice([0, 40, 400]) for r in raws]
+        d_off, d_cap, dtot = out_layout(bcaps, gap=2)
+        d = np.zeros(dtot, dtype=np.uint8)
+        res = ctx.rle_decode_streams(cb, c_off, c_len, d, d_off, d_cap)
+        out_len, status = res[0], res[1]
+        for i in range(len(bad)):
+            ost, oout = oracle.rle_decode(bad[i], bcaps[i])
+            assert int(status[i]) == ost, ("rle damaged status", i, int(status[i]), ost)
+            k = min(int(out_len[i]), bcaps[i])
+            assert d[int(d_off[i]): int(d_off[i]) + k].tobytes() == bytes(oout[:k]), ("rle damaged bytes", i)
+        cases += 3 * len(raws)
     return cases
 
 
